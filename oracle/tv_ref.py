@@ -1,0 +1,164 @@
+"""oracle/tv_ref.py -- TEST INFRASTRUCTURE ONLY.
+
+CPU restatement of the torchvision-side box ops the reference's hot path calls.
+
+The arithmetic of ``nms`` / ``batched_nms`` / ``box_iou`` lives in a third-party dependency
+that is NOT vendored under /root/reference: **torchvision** (version unpinned by the
+reference; the vendored detection files come from pytorch/vision ~v0.10; 0.26.0+cu128 is what
+the image ships).  Its published algorithm is restated here (stable descending sort, suppress
+iff ``inter / (area_i + area_j - inter) > thr`` with a double threshold) and pinned against
+the installed ``torchvision.ops`` CPU kernels by tests/test_oracle_pin.py, anchored on the
+reference's call sites: rpn.py:272, roi_heads.py:771, retinanet.py:463, ssd.py:423,
+yolo/benchmark.py:100, telemetry.py:207/248.
+
+The RPN pieces (``BoxCoder.decode_single``, ``filter_proposals``, ``Matcher``) are vendored in
+the reference and restated from there (torchvision_models/tvision/{_utils,rpn}.py).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+Tensor = torch.Tensor
+
+
+def _areas(boxes: Tensor) -> Tensor:
+    return (boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1])
+
+
+def nms(boxes: Tensor, scores: Tensor, iou_threshold: float) -> Tensor:
+    """torchvision.ops.nms (csrc/ops/cpu/nms_kernel.cpp): int64 kept indices, descending score
+    (stable: lower index first on ties)."""
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.zeros(0, dtype=torch.int64)
+    order = torch.sort(scores, descending=True, stable=True)[1]
+    b = boxes[order]
+    area = _areas(b)
+    dead = torch.zeros(n, dtype=torch.bool)
+    keep = []
+    thr = float(iou_threshold)
+    for i in range(n):
+        if dead[i]:
+            continue
+        keep.append(int(order[i]))
+        if i + 1 == n:
+            break
+        r = b[i + 1:]
+        w = (torch.minimum(r[:, 2], b[i, 2]) - torch.maximum(r[:, 0], b[i, 0])).clamp(min=0)
+        h = (torch.minimum(r[:, 3], b[i, 3]) - torch.maximum(r[:, 1], b[i, 1])).clamp(min=0)
+        inter = w * h
+        ovr = inter / (area[i] + area[i + 1:] - inter)
+        dead[i + 1:] |= ovr.double() > thr
+    return torch.tensor(keep, dtype=torch.int64)
+
+
+def batched_nms_vanilla(boxes: Tensor, scores: Tensor, idxs: Tensor, iou_threshold: float) -> Tensor:
+    """boxes.py ``_batched_nms_vanilla``: nms per distinct idx, union sorted by score."""
+    mask = torch.zeros_like(scores, dtype=torch.bool)
+    for c in torch.unique(idxs):
+        sel = torch.where(idxs == c)[0]
+        mask[sel[nms(boxes[sel], scores[sel], iou_threshold)]] = True
+    keep = torch.where(mask)[0]
+    return keep[torch.sort(scores[keep], descending=True, stable=True)[1]]
+
+
+def batched_nms_coordinate_trick(boxes: Tensor, scores: Tensor, idxs: Tensor,
+                                 iou_threshold: float) -> Tensor:
+    """boxes.py ``_batched_nms_coordinate_trick``: shift every class by (max+1)*idx in fp32."""
+    if boxes.numel() == 0:
+        return torch.zeros(0, dtype=torch.int64)
+    offsets = idxs.to(boxes) * (boxes.max() + torch.tensor(1).to(boxes))
+    return nms(boxes + offsets[:, None], scores, iou_threshold)
+
+
+def batched_nms(boxes: Tensor, scores: Tensor, idxs: Tensor, iou_threshold: float,
+                device_type: str = "cpu") -> Tensor:
+    """Dispatch rule of torchvision 0.26 ``batched_nms`` (numel > 4000 on CPU / 100000 on CUDA
+    -> vanilla, else coordinate trick)."""
+    if boxes.numel() > (4000 if device_type == "cpu" else 100_000):
+        return batched_nms_vanilla(boxes, scores, idxs, iou_threshold)
+    return batched_nms_coordinate_trick(boxes, scores, idxs, iou_threshold)
+
+
+def box_iou(boxes1: Tensor, boxes2: Tensor) -> Tensor:
+    """torchvision.ops.box_iou, xyxy: union = (area1 + area2) - inter."""
+    a1, a2 = _areas(boxes1), _areas(boxes2)
+    lt = torch.max(boxes1[:, None, :2], boxes2[None, :, :2])
+    rb = torch.min(boxes1[:, None, 2:], boxes2[None, :, 2:])
+    wh = (rb - lt).clamp(min=0)
+    inter = wh[..., 0] * wh[..., 1]
+    return inter / (a1[:, None] + a2[None, :] - inter)
+
+
+# --------------------------------------------------------------------------------------
+# RPN proposal filter  (torchvision_models/tvision/rpn.py:215-280, _utils.py:186-223)
+# --------------------------------------------------------------------------------------
+BBOX_XFORM_CLIP = math.log(1000.0 / 16)       # _utils.py:134
+
+
+def decode_single(rel_codes: Tensor, boxes: Tensor,
+                  weights: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)) -> Tensor:
+    """BoxCoder.decode_single for one box per row (_utils.py:186-223)."""
+    w = boxes[:, 2] - boxes[:, 0]
+    h = boxes[:, 3] - boxes[:, 1]
+    cx = boxes[:, 0] + 0.5 * w
+    cy = boxes[:, 1] + 0.5 * h
+    dx, dy = rel_codes[:, 0] / weights[0], rel_codes[:, 1] / weights[1]
+    dw = torch.clamp(rel_codes[:, 2] / weights[2], max=BBOX_XFORM_CLIP)
+    dh = torch.clamp(rel_codes[:, 3] / weights[3], max=BBOX_XFORM_CLIP)
+    pcx, pcy = dx * w + cx, dy * h + cy
+    pw, ph = torch.exp(dw) * w, torch.exp(dh) * h
+    half = torch.tensor(0.5, dtype=pw.dtype)
+    return torch.stack((pcx - half * pw, pcy - half * ph, pcx + half * pw, pcy + half * ph), dim=1)
+
+
+def filter_proposals(objectness: Tensor, deltas: Tensor, anchors: Tensor,
+                     per_level: Sequence[int], image_shapes: Sequence[Tuple[int, int]],
+                     pre_nms_top_n: int, post_nms_top_n: int, nms_thresh: float = 0.7,
+                     score_thresh: float = 0.0, min_size: float = 1e-3,
+                     device_type: str = "cpu") -> Tuple[List[Tensor], List[Tensor], List[Tensor]]:
+    """RegionProposalNetwork.filter_proposals (rpn.py:230-280) fed with raw deltas:
+    the reference decodes every anchor first (rpn.py:355) and then gathers the per-level
+    top-k; decoding only the gathered rows gives the same values.  Returns boxes, scores and
+    (extra, for index parity) the flat anchor index of every surviving proposal."""
+    bsz, total = objectness.shape
+    picks, lvl = [], []
+    off = 0
+    for li, n_l in enumerate(per_level):                                   # rpn.py:215-228
+        k = min(pre_nms_top_n, n_l)
+        picks.append(objectness[:, off:off + n_l].topk(k, dim=1)[1] + off)
+        lvl.append(torch.full((k,), li, dtype=torch.int64))
+        off += n_l
+    top = torch.cat(picks, dim=1)
+    lvl = torch.cat(lvl)
+    out_b, out_s, out_i = [], [], []
+    for b in range(bsz):
+        idx = top[b]
+        prob = torch.sigmoid(objectness[b, idx])                           # :255
+        boxes = decode_single(deltas[b, idx], anchors[idx])
+        hh, ww = image_shapes[b]
+        boxes = torch.stack((boxes[:, 0].clamp(0, ww), boxes[:, 1].clamp(0, hh),
+                             boxes[:, 2].clamp(0, ww), boxes[:, 3].clamp(0, hh)), dim=1)  # :260
+        ok = ((boxes[:, 2] - boxes[:, 0]) >= min_size) & ((boxes[:, 3] - boxes[:, 1]) >= min_size)
+        ok &= prob >= score_thresh                                         # :263-269
+        sel = torch.where(ok)[0]
+        boxes, prob, lv, ids = boxes[sel], prob[sel], lvl[sel], idx[sel]
+        keep = batched_nms(boxes, prob, lv, nms_thresh, device_type)[:post_nms_top_n]   # :272-275
+        out_b.append(boxes[keep]); out_s.append(prob[keep]); out_i.append(ids[keep])
+    return out_b, out_s, out_i
+
+
+def matcher(quality: Tensor, high: float, low: float, allow_low_quality: bool = False) -> Tensor:
+    """Matcher.__call__ (_utils.py:271-344) on an ``[M, N]`` quality matrix."""
+    vals, matches = quality.max(dim=0)
+    every = matches.clone()
+    matches[vals < low] = -1
+    matches[(vals >= low) & (vals < high)] = -2
+    if allow_low_quality:
+        row_best = quality.max(dim=1)[0]
+        tied = torch.where(quality == row_best[:, None])[1]                # _utils.py:315-344
+        matches[tied] = every[tied]
+    return matches

@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(/root/reference, Python) on seeded synthetic inputs.
+
+Runs only in the build container (the reference does not exist on the GPU box); the
+fixtures it writes are committed and are what tests/test_oracle_golden.py pins the oracle
+to.  Inputs are not stored: they are regenerated from ``object_detectors_b200.synthetic``
+seeds and checked against the sha256 recorded here.
+
+Shim recipe: stub pycocotools / lvis / hydra, point ``owd`` at the
+reference's yolo directory so IDFTransformer reads the shipped idf.csv, and give the three
+reference modules that hard-code ``'cuda'`` a torch proxy that maps it to the CPU.
+
+    python tests/golden/make_golden.py
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torchvision  # noqa: F401  (must be imported before the proxy is installed)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+from object_detectors_b200 import synthetic as syn  # noqa: E402
+
+
+# ----------------------------------------------------------------------------- shim
+class _TorchProxy(types.ModuleType):
+    """``torch`` with device('cuda') -> cpu; everything else forwarded."""
+
+    def __init__(self):
+        super().__init__("torch")
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+    @staticmethod
+    def device(*a, **k):
+        return torch.device("cpu")
+
+    @staticmethod
+    def _fix(kw):
+        if "device" in kw:
+            kw["device"] = "cpu"
+        return kw
+
+    def tensor(self, *a, **k):
+        return torch.tensor(*a, **self._fix(k))
+
+    def ones(self, *a, **k):
+        return torch.ones(*a, **self._fix(k))
+
+    def zeros(self, *a, **k):
+        return torch.zeros(*a, **self._fix(k))
+
+    def linspace(self, *a, **k):
+        return torch.linspace(*a, **self._fix(k))
+
+
+class AttrDict(dict):
+    __getattr__ = dict.__getitem__
+
+
+def _install():
+    for name in ("pycocotools", "pycocotools.coco", "pycocotools.cocoeval", "lvis", "hydra",
+                 "hydra.utils"):
+        m = types.ModuleType(name)
+        m.COCO = m.COCOeval = m.LVIS = m.LVISEval = m.LVISResults = object
+        sys.modules.setdefault(name, m)
+    os.environ["owd"] = os.path.join(REF, "yolo")
+    sys.path.insert(0, os.path.join(REF, "yolo"))
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.cuda.is_available = lambda: False
+    from nets import yolo_forw
+    from utilities import custom, helper
+    proxy = _TorchProxy()
+    for mod in (yolo_forw, custom, helper):
+        mod.torch = proxy
+    return yolo_forw, helper
+
+
+def _cfg(img, classes, anchors, dset, class_loss, tfidf):
+    yolo = AttrDict(classes=classes, img_size=img, ignore_threshold=0.5, lambda_iou=1, iou_type=1,
+                    lambda_xy=2.5, lambda_wh=2.5, lambda_conf=1.0, lambda_no_conf=0.1,
+                    lambda_cls=1.0, alpha=0.5, gamma=1, class_loss=class_loss, reduction="sum",
+                    inf_confidence=0.1, inf_iou_threshold=0.6, tfidf=tfidf,
+                    tfidf_variant="smooth", tfidf_norm=0, tfidf_batch=False)
+    dataset = AttrDict(anchors=[[list(p) for p in s] for s in anchors], dset_name=dset,
+                       train_annotations="none.json", inp_dim=img, num_classes=classes)
+    return AttrDict(yolo=yolo, dataset=dataset)
+
+
+def _sha(arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def _post(helper, pred, conf):
+    """test_one_epoch.py:24-36, reference code path, empties kept in place."""
+    pred = pred.clone()
+    pred[:, :, :4] = helper.get_abs_coord(pred[:, :, :4])
+    score = pred[:, :, 4] * (pred[:, :, 5:].max(axis=2)[0])
+    mask = score > conf
+    per_img = []
+    for e, m in enumerate(mask):
+        p = pred[e][m]
+        anchor = torch.nonzero(m).flatten()
+        if p.shape[0] == 0:
+            per_img.append((anchor, torch.zeros(0, 6), torch.zeros(0, 6)))
+            continue
+        det6 = torch.cat([p[:, :4], p[:, 4:5] * (p[:, 5:].max(axis=1)[0]).unsqueeze(1),
+                          (p[:, 5:].max(axis=1)[1]).unsqueeze(1)], axis=1)
+        kept = helper.nms_majority(det6.clone())
+        per_img.append((anchor, det6, kept))
+    return per_img
+
+
+def _pack_post(per_img):
+    out = {}
+    for i, (anchor, det6, kept) in enumerate(per_img):
+        out[f"anchor_{i}"] = anchor.numpy().astype(np.int32)
+        out[f"det6_{i}"] = det6.numpy()
+        out[f"kept_{i}"] = kept.numpy()
+    out["num_images"] = np.int64(len(per_img))
+    return out
+
+
+def main():
+    yolo_forw, helper = _install()
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+
+    # IDF vectors (the reference's shipped fixtures, column 'smooth') -------------------
+    import pandas as pd
+    idf = {}
+    for dset in ("coco", "lvis"):
+        col = pd.read_csv(os.path.join(REF, "yolo", f"{dset}_files", "idf.csv"))["smooth"]
+        idf[dset] = torch.tensor(list(col), dtype=torch.float32).numpy()
+        np.save(os.path.join(HERE, f"idf_{dset}_smooth.npy"), idf[dset])
+
+    # 1. tiny dense decode: img 64, B=2, both class modes, full [B,N,85] stored ----------
+    for tag, class_loss, tfidf, sig in (("softmax_idf", 1, [0, 1], False), ("sigmoid_plain", 0, [0, 0], True)):
+        heads = syn.yolo_heads(11, 2, 64, 80, syn.COCO_ANCHORS, "clustered", sigmoid_cls=sig, max_objects=3)
+        model = yolo_forw.YOLOForw(_cfg(64, 80, syn.COCO_ANCHORS, "coco", class_loss, tfidf))
+        pred = model([torch.from_numpy(h) for h in heads])
+        np.savez_compressed(os.path.join(HERE, f"decode_tiny_{tag}.npz"), pred=pred.numpy(),
+                            sha=_sha(heads), **_pack_post(_post(helper, pred, 0.1)))
+
+    # 2. C1: 416 / COCO-80 / b1, reference defaults (softmax, idf on) + idf off ---------
+    for tag, tfidf in (("idf", [0, 1]), ("plain", [0, 0])):
+        for seed in (3, 4):
+            heads = syn.yolo_heads(seed, 1, 416, 80, syn.COCO_ANCHORS, "clustered")
+            model = yolo_forw.YOLOForw(_cfg(416, 80, syn.COCO_ANCHORS, "coco", 1, tfidf))
+            pred = model([torch.from_numpy(h) for h in heads])
+            rows = torch.arange(0, pred.shape[1], 97)
+            np.savez_compressed(os.path.join(HERE, f"c1_416_{tag}_seed{seed}.npz"), sha=_sha(heads),
+                                sample_rows=rows.numpy(), sample_pred=pred[0, rows].numpy(),
+                                colsum=pred.double().sum(dim=1).numpy(),
+                                **_pack_post(_post(helper, pred, 0.1)))
+
+    # 3. 608 / COCO-80 / b4 (the C2 shape at a fixture-sized batch) ----------------------
+    heads = syn.yolo_heads(5, 4, 608, 80, syn.COCO_ANCHORS, "clustered")
+    model = yolo_forw.YOLOForw(_cfg(608, 80, syn.COCO_ANCHORS, "coco", 1, [0, 1]))
+    pred = model([torch.from_numpy(h) for h in heads])
+    np.savez_compressed(os.path.join(HERE, "c2_608_b4_seed5.npz"), sha=_sha(heads),
+                        colsum=pred.double().sum(dim=1).numpy(), **_pack_post(_post(helper, pred, 0.1)))
+
+    # 4. LVIS-1203, 6 anchors/scale, img 96, b2 (C3 shape family) ------------------------
+    heads = syn.yolo_heads(6, 2, 96, 1203, syn.LVIS_ANCHORS, "clustered", max_objects=4)
+    model = yolo_forw.YOLOForw(_cfg(96, 1203, syn.LVIS_ANCHORS, "lvis", 1, [0, 1]))
+    pred = model([torch.from_numpy(h) for h in heads])
+    np.savez_compressed(os.path.join(HERE, "c3_lvis_96_b2_seed6.npz"), sha=_sha(heads),
+                        colsum=pred.double().sum(dim=1).numpy(), **_pack_post(_post(helper, pred, 0.1)))
+
+    # 5. nms_majority on stand-alone cluttered boxes (relabel rule exercised) ------------
+    pack = {}
+    for i, (seed, n, k, c) in enumerate(((21, 300, 12, 5), (22, 1000, 25, 80), (23, 64, 3, 2), (24, 1, 0, 3))):
+        boxes, scores, labels = syn.random_boxes(seed, n, clusters=k, num_classes=c)
+        det6 = torch.from_numpy(np.concatenate([boxes, scores[:, None], labels[:, None].astype(np.float32)], 1))
+        kept = helper.nms_majority(det6.clone(), 0.6)
+        pack[f"kept_{i}"] = kept.numpy()
+        pack[f"args_{i}"] = np.array([seed, n, k, c])
+    np.savez_compressed(os.path.join(HERE, "nms_majority_boxes.npz"), **pack)
+
+    # 6. bbox_iou all four kinds + get_target (C4 family, small) --------------------------
+    model = yolo_forw.YOLOForw(_cfg(416, 80, syn.COCO_ANCHORS, "coco", 1, [0, 1]))
+    heads = [torch.zeros(1, 255, g, g) for g in (13, 26, 52)]
+    pack = {}
+    targets = syn.gt_targets(31, 3, 80, max_gt=20)
+    tt = [{k: torch.from_numpy(v) for k, v in t.items()} for t in targets]
+    # rebuild cxypwh / inw_inh exactly as forward() does, by calling forward's own code path
+    cx, inw = [], []
+    for k, h in enumerate(heads):
+        in_w = h.size(3)
+        stride = 416 / in_w
+        sa = torch.tensor([(a_w / stride, a_h / stride) for a_w, a_h in model.anchors[k]])
+        gx = torch.linspace(0, in_w - 1, in_w).repeat(in_w, 1).repeat(3, 1, 1).permute(1, 2, 0) + 0.5
+        gy = torch.linspace(0, in_w - 1, in_w).repeat(in_w, 1).t().repeat(3, 1, 1).permute(1, 2, 0) + 0.5
+        gx = torch.reshape(gx, [-1]) / in_w
+        gy = torch.reshape(gy, [-1]) / in_w
+        aw = torch.reshape((sa[:, 0] / in_w).repeat(1, in_w * in_w), [-1])
+        ah = torch.reshape((sa[:, 1] / in_w).repeat(1, in_w * in_w), [-1])
+        cx.append(torch.stack((gx, gy, aw, ah), axis=1))
+        inw.append(torch.ones(gy.shape) * in_w)
+    cx, inw = torch.cat(cx), torch.cat(inw)
+    pack["cxypwh_sample"] = cx[::101].numpy()
+    for kind in (0, 1):
+        model.iou_type = kind
+        tgt, tcls, obj, noobj = model.get_target(tt, cx, inw, ignore_threshold=0.5)
+        pack[f"tgt_{kind}"] = tgt.numpy()
+        pack[f"obj_{kind}"] = torch.cat(obj).numpy()
+        pack[f"noobj_{kind}"] = np.packbits(noobj.numpy())
+        pack[f"tcls_argmax_{kind}"] = tcls.argmax(1).numpy()
+    b1 = torch.from_numpy(targets[0]["bbox"])
+    for kind in (0, 1, 2, 3):
+        pack[f"iou_kind{kind}"] = helper.bbox_iou(b1.unsqueeze(1), cx[::53].unsqueeze(0), kind, CUDA=False).numpy()
+    np.savez_compressed(os.path.join(HERE, "match_416.npz"), **pack)
+
+    # 7. RPN filter_proposals through the reference's own class (C5 family, small image) --
+    sys.path.insert(0, os.path.join(REF, "torchvision_models"))
+    from tvision import rpn as ref_rpn
+    pack = {}
+    for tag, (ih, iw), bsz, pre, post in (("s", (224, 320), 2, 300, 300), ("m", (416, 608), 2, 1000, 1000)):
+        obj, deltas, anchors, per_level = syn.rpn_inputs(41, bsz, ih, iw)
+        r = ref_rpn.RegionProposalNetwork.__new__(ref_rpn.RegionProposalNetwork)
+        torch.nn.Module.__init__(r)
+        r._pre_nms_top_n = dict(training=pre, testing=pre)
+        r._post_nms_top_n = dict(training=post, testing=post)
+        r.nms_thresh, r.score_thresh, r.min_size = 0.7, 0.0, 1e-3
+        from tvision._utils import BoxCoder
+        coder = BoxCoder(weights=(1.0, 1.0, 1.0, 1.0))
+        a = torch.from_numpy(anchors)
+        props = coder.decode(torch.from_numpy(deltas).reshape(-1, 4), [a] * bsz).view(bsz, -1, 4)
+        fb, fs = r.filter_proposals(props, torch.from_numpy(obj).reshape(-1, 1), [(ih, iw)] * bsz, per_level)
+        for i in range(bsz):
+            pack[f"{tag}_boxes_{i}"] = fb[i].numpy()
+            pack[f"{tag}_scores_{i}"] = fs[i].numpy()
+        pack[f"{tag}_args"] = np.array([41, bsz, ih, iw, pre, post])
+    np.savez_compressed(os.path.join(HERE, "rpn_filter.npz"), **pack)
+    print("golden fixtures written to", HERE)
+    for f in sorted(os.listdir(HERE)):
+        print(f"  {f:40s} {os.path.getsize(os.path.join(HERE, f)):>9d} B")
+
+
+if __name__ == "__main__":
+    main()
