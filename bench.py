@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of decode + conf filter + NMS on synthetic YOLOv3-608 COCO head tensors.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (b200_yolo_postprocess: fused decode+filter kernel, then the
+per-image order+NMS kernel) over one batch of 64 images per GPU (weak scaling: every rank owns its
+own 64-image batch, as the reference's DistributedSampler does); at N > 1 each step ends with the
+one exchange the path has, an NCCL all-gather of the fixed-capacity kept-detection messages.
+
+Printed JSON (one line, rank 0):
+  value     whole-job images/s with the head tensors resident in HBM (device-timed, max over ranks)
+  roofline  fused decode+filter kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json);
+            achieved = algorithmic bytes (one read of the head tensors, B*N*(5+C)*4) / its mean
+            duration measured with CUDA events inside the timed region
+  e2e       same metric through the host-buffer C-ABI entry (pinned host -> device copies of all
+            head tensors and device -> host copy of the detections inside the timed region)
+  cpu_baseline  the CPU oracle port of the reference path on a bounded sample, all host threads
+--impl reference: the reference's own CPU implementation is Python and cannot travel to the GPU
+box, so the oracle port (oracle/yolo_ref.py: same torch CPU ops in the same order, pinned
+bit-exactly to the reference by tests/golden) is timed on the host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from object_detectors_b200 import synthetic as syn  # noqa: E402
+
+METRIC = "images/sec decode+NMS, YOLOv3-608 COCO b64"
+IMG, NUM_CLASSES, BATCH = 608, 80, 64
+CONF_THR, NMS_THR = 0.1, 0.6
+MAX_DET = 256          # kept-detection capacity per image in the exchanged message
+CAPACITY = 4096        # candidate slab rows per image (overflow is reported, never silent)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_heads(seed: int, batch: int):
+    return syn.yolo_heads(seed, batch, IMG, NUM_CLASSES, syn.COCO_ANCHORS, "clustered")
+
+
+def load_idf():
+    return torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "idf_coco_smooth.npy")))
+
+
+# ----------------------------------------------------------------------------------------- CPU
+def cpu_reference_pass(heads_cpu, idf):
+    """The reference's eval post-process (oracle port, torch CPU ops): decode -> xyxy -> filter ->
+    nms_majority.  Returns the number of kept detections."""
+    from oracle import yolo_ref
+    recs = yolo_ref.postprocess(heads_cpu, syn.COCO_ANCHORS, IMG, NUM_CLASSES, idf, True, CONF_THR, NMS_THR)
+    return sum(int(r["keep"].numel()) for r in recs)
+
+
+def time_cpu(sample_batch: int, reps: int, warm: int = 1):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    heads = [torch.from_numpy(h) for h in make_heads(1000, sample_batch)]
+    idf = load_idf()
+    for _ in range(warm):
+        cpu_reference_pass(heads, idf)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_reference_pass(heads, idf)
+        ts.append(time.perf_counter() - t0)
+    return sample_batch / float(np.median(ts)), cores, ts
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 16
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    heads = [torch.from_numpy(h) for h in make_heads(1000, sample)]
+    idf = load_idf()
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_pass(heads, idf)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_pass(heads, idf)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    desc = f"{sample} images of the {BATCH}-image 608/COCO batch per step (clustered synthetic heads, seed 1000)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "C2: YOLOv3-608 COCO-80 decode + conf filter + nms_majority, 22743 anchors/image",
+                   "sample_batch": sample, "threads": cores, "engine": "oracle port of the reference (torch CPU ops)"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- GPU
+def run_b200(args):
+    import torch.distributed as dist
+    from object_detectors_b200 import _lib, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: object_detectors_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    heads_np = make_heads(1000 + rank, BATCH)
+    heads = [torch.from_numpy(h).to(dev) for h in heads_np]
+    idf = load_idf().to(dev)
+    grids = [h.shape[2] for h in heads]
+    n_anchor = sum(g * g * 3 for g in grids)
+    algo_bytes = BATCH * n_anchor * (5 + NUM_CLASSES) * 4
+    plan = ops.YoloPostprocess(grids, BATCH, syn.COCO_ANCHORS, IMG, NUM_CLASSES, True, CONF_THR, NMS_THR,
+                               ops.NMS_MAJORITY, CAPACITY, MAX_DET, dev)
+    msg_len = BATCH * (1 + MAX_DET * 6)
+    gathered = torch.empty((world * msg_len,), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step():
+        det, keep, anchor, dcnt, ccnt = plan(heads, idf)
+        if world > 1:
+            msg = ops.pack_detections(det, dcnt)
+            dist.all_gather_into_tensor(gathered, msg)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    plan.check_status()
+
+    # per-step events around the fused decode+filter kernel (roofline numerator)
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in k_ev:
+        a.record(); b.record()          # materialise the cudaEvent_t handles
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin.record()
+    for i in range(args.steps):
+        lib.b200_debug_set_decode_events(C.c_void_p(k_ev[i][0].cuda_event), C.c_void_p(k_ev[i][1].cuda_event))
+        step()
+    lib.b200_debug_set_decode_events(None, None)
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t_begin.elapsed_time(t_end)
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    t = torch.tensor([ms_total, k_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, k_ms = float(t[0]), float(t[1])
+    plan.check_status()
+    kept = int(plan.det_count.sum())
+    cands = int(plan.cand_count.sum())
+
+    # ---- e2e through the host-buffer entry point: H2D of every head tensor + D2H of detections --
+    heads_pin = [torch.from_numpy(h).pin_memory() for h in heads_np]
+    idf_host = load_idf()
+    out = (torch.empty((BATCH, MAX_DET, 6), dtype=torch.float32).pin_memory(),
+           torch.empty((BATCH, MAX_DET), dtype=torch.int32).pin_memory(),
+           torch.empty((BATCH,), dtype=torch.int32).pin_memory(),
+           torch.zeros((1,), dtype=torch.int32).pin_memory())
+    e2e_steps = max(2, min(args.steps, 10))
+    for _ in range(2):
+        ops.yolo_postprocess_host(heads_pin, syn.COCO_ANCHORS, IMG, NUM_CLASSES, idf_host, True, CONF_THR, NMS_THR,
+                                  ops.NMS_MAJORITY, CAPACITY, MAX_DET, out)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ops.yolo_postprocess_host(heads_pin, syn.COCO_ANCHORS, IMG, NUM_CLASSES, idf_host, True, CONF_THR, NMS_THR,
+                                  ops.NMS_MAJORITY, CAPACITY, MAX_DET, out)
+    e2e_s = time.perf_counter() - t0
+    assert int(out[3][0]) == 0, "e2e slab overflow"
+    assert int(out[2].sum()) == kept, "e2e path and device-resident path disagree on kept detections"
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t[0])
+    h2d = sum(h.numel() * 4 for h in heads_pin) + idf_host.numel() * 4
+    d2h = sum(o.numel() * o.element_size() for o in out)
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+        cpu_v, cores, cpu_ts = time_cpu(sample_batch=16, reps=3)
+        line = {
+            "metric": METRIC, "value": world * BATCH * args.steps / (ms_total * 1e-3), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "C2: YOLOv3-608 COCO-80 decode + conf filter + nms_majority, batch 64 per GPU, "
+                                   "22743 anchors/image, softmax classes x IDF, conf 0.1, NMS 0.6",
+                       "batch_per_gpu": BATCH, "global_batch": BATCH * world, "img_size": IMG,
+                       "l2_policy": "inputs (494.9 MB/step) larger than L2 (126 MB), no flush needed",
+                       "candidates_per_step": cands, "kept_per_step": kept,
+                       "exchange": "nccl all_gather of fixed-capacity kept lists" if world > 1 else "none (1 GPU)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_decode_filter", "kernel_ms": k_ms,
+                         "algorithmic_bytes": algo_bytes, "peak_source": peak_src},
+            "cpu_baseline": {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": "16 images of the same 608/COCO workload, 3 timed passes, oracle port "
+                                       "(torch CPU ops, all host threads)"},
+            "e2e": {"value": world * BATCH * e2e_steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": args.steps * (2 + (1 if world > 1 else 0)),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

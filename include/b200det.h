@@ -1,0 +1,237 @@
+/*
+ * b200det.h -- C ABI of libb200det.so: the B200 (sm_100a) detection box-ops hot path.
+ *
+ * The reference (kostas1515/object_detectors) has no FFI: its boundary for this path is a set
+ * of Python call signatures.  Each entry point below names the reference call it replaces
+ * (paths relative to the reference root); the Python shims in object_detectors_b200/ keep the
+ * reference signatures and call these through ctypes.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch / C++ types.  `stream` is a cudaStream_t passed as
+ *    void* (NULL = legacy default stream).  All pointers are DEVICE pointers unless the
+ *    parameter name ends in `_host`.
+ *  - fp32 tensors are contiguous, int32 / int64 as stated.  Inputs are never written.
+ *  - every call is asynchronous on `stream`, allocates nothing and is CUDA-graph capturable
+ *    (except the *_host entry points, which synchronise the stream before returning).
+ *    Scratch memory comes from the caller: query the size with the matching *_workspace_bytes.
+ *  - return value: 0 = B200_OK, negative = error (b200_error_string).  No exceptions cross
+ *    the boundary.  Data-dependent conditions (candidate slab overflow) are reported through
+ *    a device-side status word the caller reads when convenient.
+ *  - there is no CPU fallback: without a CUDA device every compute entry point returns
+ *    B200_ERR_CUDA.
+ */
+#ifndef B200DET_H_
+#define B200DET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+#define B200_MAX_SCALES 4
+#define B200_MAX_ANCHORS 8
+
+enum {
+    B200_OK = 0,
+    B200_ERR_INVALID = -1,  /* bad argument (null pointer, size out of range, unsupported shape) */
+    B200_ERR_CUDA = -2,     /* CUDA runtime error (launch failure, no device) */
+    B200_ERR_WORKSPACE = -3 /* workspace too small / misaligned */
+};
+
+/* NMS flavours -- one arithmetic order per reference implementation */
+enum {
+    /* helper.nms_majority (yolo/utilities/helper.py:280-382): class-agnostic, removes
+     * !(IoU < thr) with thr compared in fp32, IoU = inter/((area_j-inter)+area_i); kept box is
+     * relabelled to the majority class of the boxes it removed with IoU > thr when those hold
+     * more than one distinct class. */
+    B200_NMS_MAJORITY = 0,
+    /* torchvision.ops.nms (call sites yolo/benchmark.py:100, yolo/utilities/telemetry.py:207):
+     * class-agnostic, suppress iff (double)(inter/(area_i+area_j-inter)) > thr. */
+    B200_NMS_TV = 1,
+    /* torchvision.ops.batched_nms, "vanilla" strategy (tvision/rpn.py:272, roi_heads.py:771,
+     * retinanet.py:463, ssd.py:423): as B200_NMS_TV but only equal labels interact. */
+    B200_NMS_TV_CLASS = 2,
+    /* torchvision.ops.batched_nms, "coordinate trick" strategy: boxes are shifted by
+     * label*(max_coordinate+1) in fp32 and suppressed class-agnostically. */
+    B200_NMS_TV_TRICK = 3
+};
+
+/* pairwise IoU flavours of helper.bbox_iou (yolo/utilities/helper.py:221-277) + torchvision */
+enum {
+    B200_IOU = 0,     /* helper.bbox_iou iou_type 0 */
+    B200_GIOU = 1,    /* iou_type 1 (reference default, hydra/yolo/head.yaml:6) */
+    B200_DIOU = 2,    /* iou_type 2 */
+    B200_CIOU = 3,    /* iou_type 3 */
+    B200_IOU_TV = 4   /* torchvision.ops.box_iou: union = (area1 + area2) - inter */
+};
+
+/* Geometry of one multi-scale YOLO head set, i.e. the state YOLOForw.forward rebuilds on every
+ * call (yolo/nets/yolo_forw.py:93-119).  Head s is NCHW fp32 [batch, A*(5+C), grid[s], grid[s]];
+ * flat anchor index inside a scale is n = (h*W + w)*A + a, scales concatenated in order. */
+typedef struct b200_yolo_layout {
+    int32_t num_scales;   /* 1..B200_MAX_SCALES */
+    int32_t num_anchors;  /* A per scale, 1..B200_MAX_ANCHORS */
+    int32_t num_classes;  /* C >= 1 */
+    int32_t batch;        /* B >= 1 */
+    int32_t softmax;      /* 1: cls = softmax(idf*t) (class_loss==1, default); 0: sigmoid(idf*t) */
+    float img_size;       /* YOLOForw.img_size as fp32 */
+    int32_t grid[B200_MAX_SCALES];
+    /* fp32( fp32(a_px / (img_size/grid)) / grid ) per anchor: the reference's `anchor_w`,
+     * `anchor_h` columns of cxypwh (yolo_forw.py:99,108-113), prepared by the host shim with the
+     * reference's rounding (python double division, cast, fp32 division). */
+    float anchor_rel[B200_MAX_SCALES][B200_MAX_ANCHORS][2];
+} b200_yolo_layout;
+
+int b200_abi_version(void);
+const char* b200_error_string(int code);
+/* number of SMs / device name of the current device (diagnostics for bench.py) */
+int b200_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * YOLO decode
+ * ---------------------------------------------------------------------------------------- */
+
+/* Replaces YOLOForw.forward(input, targets=None) (yolo/nets/yolo_forw.py:81-119,163-176).
+ * out: [B, N, 5+C] fp32, rows xc,yc,w,h (pixels), objectness, class probabilities.
+ * idf: [C] fp32 class scale (`idf_logits`) or NULL for 1. */
+int b200_yolo_decode_dense(const b200_yolo_layout* layout, const float* const* heads,
+                           const float* idf, float* out, void* stream);
+
+size_t b200_yolo_workspace_bytes(const b200_yolo_layout* layout, int32_t capacity);
+
+/* Replaces the decode -> get_abs_coord -> score -> mask -> per-image gather sequence of
+ * test_one_epoch (yolo/procedures/test_one_epoch.py:22-28,35) without materialising [B,N,5+C].
+ * Per image b, candidates with conf*max_c(cls) > conf_thr in ascending anchor index:
+ *   cand_box    [B, capacity, 4] fp32 x1,y1,x2,y2
+ *   cand_score  [B, capacity]    fp32
+ *   cand_label  [B, capacity]    int32 argmax class (first maximum)
+ *   cand_anchor [B, capacity]    int32 flat anchor index n
+ *   cand_count  [B]              int32 TRUE number of candidates (may exceed capacity: then
+ *                                only the `capacity` lowest-slot ones are stored and status |= 1)
+ * status: int32 device word, OR-ed with 1 on overflow (caller zeroes it). */
+int b200_yolo_decode_filter(const b200_yolo_layout* layout, const float* const* heads,
+                            const float* idf, float conf_thr, int32_t capacity,
+                            float* cand_box, float* cand_score, int32_t* cand_label,
+                            int32_t* cand_anchor, int32_t* cand_count, int32_t* status,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* The whole eval post-process of test_one_epoch.py:22-36 in one call: decode + filter +
+ * compaction + NMS.  nms_mode B200_NMS_MAJORITY reproduces helper.nms_majority (the active
+ * reference path), B200_NMS_TV / _TV_CLASS the torchvision variants (test_one_epoch.py:30,
+ * benchmark.py:94-101).  Outputs per image, kept detections in descending score:
+ *   det       [B, max_det, 6] fp32 x1,y1,x2,y2,score,label (label after majority relabel)
+ *   det_keep  [B, max_det]    int32 index of the kept box in the image's candidate list
+ *                             (ascending-anchor order == the reference's pred_conf order)
+ *   det_anchor[B, max_det]    int32 flat anchor index of the kept box (may be NULL)
+ *   det_count [B]             int32 number kept (clipped to max_det, status |= 2 if clipped)
+ *   cand_count[B]             int32 number of candidates (may be NULL) */
+int b200_yolo_postprocess(const b200_yolo_layout* layout, const float* const* heads,
+                          const float* idf, float conf_thr, double nms_thr, int32_t nms_mode,
+                          int32_t capacity, int32_t max_det, float* det, int32_t* det_keep,
+                          int32_t* det_anchor, int32_t* det_count, int32_t* cand_count,
+                          int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* End-to-end variant with HOST buffers: copies the heads host->device (pinned or pageable),
+ * runs b200_yolo_postprocess and copies det / det_count back.  Device staging comes from an
+ * internal pool sized on first use; synchronises before returning.
+ * heads_host[s] : [B, A*(5+C), grid, grid] fp32 on the host
+ * det_host      : [B, max_det, 6], det_count_host: [B] */
+int b200_yolo_postprocess_host(const b200_yolo_layout* layout, const float* const* heads_host,
+                               const float* idf_host, float conf_thr, double nms_thr,
+                               int32_t nms_mode, int32_t capacity, int32_t max_det,
+                               float* det_host, int32_t* det_keep_host, int32_t* det_count_host,
+                               int32_t* status_host);
+
+/* Profiling hook (bench.py): two cudaEvent_t (as void*, NULL to disable) that the next
+ * b200_yolo_postprocess / b200_yolo_decode_filter calls record on their stream immediately
+ * before and after the fused decode+filter kernel. */
+int b200_debug_set_decode_events(void* ev_begin, void* ev_end);
+
+/* ------------------------------------------------------------------------------------------
+ * NMS on caller-provided boxes, batched over segments (images, or image x level)
+ * ---------------------------------------------------------------------------------------- */
+
+size_t b200_nms_workspace_bytes(int64_t total_boxes, int32_t num_segments);
+
+/* Replaces helper.nms_majority (helper.py:280), torchvision.ops.nms / batched_nms.
+ *   boxes  [T,4] fp32 xyxy; scores [T] fp32; labels [T] int32 (required unless mode==TV)
+ *   seg_offsets [S+1] int32: segment s owns rows seg_offsets[s] .. seg_offsets[s+1]
+ *   keep      [T] int64: for segment s the kept row indices RELATIVE to the segment start, in
+ *             descending score (ties: lower index first), written at keep[seg_offsets[s] + k]
+ *   keep_count[S] int32
+ *   labels_out[T] int32 or NULL: (MAJORITY) label of the k-th kept box after relabelling,
+ *             written at labels_out[seg_offsets[s] + k]
+ *   iou_thr is a double: MAJORITY rounds it to fp32 like the reference's tensor compare,
+ *   the TV modes compare (double)iou > iou_thr like torchvision. */
+int b200_nms(const float* boxes, const float* scores, const int32_t* labels,
+             const int32_t* seg_offsets, int32_t num_segments, int64_t total_boxes, double iou_thr,
+             int32_t mode, int64_t* keep, int32_t* keep_count, int32_t* labels_out,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * pairwise IoU and IoU-based target matching
+ * ---------------------------------------------------------------------------------------- */
+
+/* Replaces helper.bbox_iou(bb1[M,1,4], bb2[1,N,4], iou_type, xcycwh) (helper.py:221-277) and
+ * torchvision.ops.box_iou (kind B200_IOU_TV, xcycwh must be 0).  out: [M,N] fp32. */
+int b200_box_iou(const float* boxes1, int32_t m, const float* boxes2, int32_t n, int32_t kind,
+                 int32_t xcycwh, float* out, void* stream);
+
+/* element-wise (paired) version: boxes1[K,4] vs boxes2[K,4] -> out[K] (yolo_forw.py:125 shape) */
+int b200_box_iou_paired(const float* boxes1, const float* boxes2, int32_t k, int32_t kind,
+                        int32_t xcycwh, float* out, void* stream);
+
+/* Replaces the IoU + reductions of YOLOForw.get_target (yolo/nets/yolo_forw.py:183-201) for a
+ * whole batch: gt [B, max_gt, 4] fp32 relative xc,yc,w,h (rows >= gt_count[b] ignored),
+ * anchors [N,4] = cxypwh.  Outputs: best_anchor [B, max_gt] int64 (first argmax_n of the IoU
+ * row), noobj [B,N] uint8 = all_m(iou < ignore_thr) with matched anchors cleared.
+ * workspace: b200_iou_match_workspace_bytes(B, max_gt). */
+size_t b200_iou_match_workspace_bytes(int32_t batch, int32_t max_gt);
+int b200_iou_match(const float* gt, const int32_t* gt_count, int32_t batch, int32_t max_gt,
+                   const float* anchors, int32_t n, int32_t kind, float ignore_thr,
+                   int64_t* best_anchor, uint8_t* noobj, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * RPN proposal filter
+ * ---------------------------------------------------------------------------------------- */
+
+size_t b200_rpn_workspace_bytes(int32_t batch, int32_t total_anchors, int32_t num_levels,
+                                int32_t pre_nms_top_n);
+
+/* Replaces BoxCoder.decode + RegionProposalNetwork.filter_proposals
+ * (torchvision_models/tvision/rpn.py:215-280,355; _utils.py:186-223): per-level top-k on raw
+ * objectness, decode of the selected anchors only, sigmoid, clip, small-box and score filters,
+ * per-level NMS, first post_nms_top_n by score.  nms_mode selects which torchvision
+ * batched_nms strategy is reproduced: B200_NMS_TV_CLASS ("vanilla", what torchvision runs for
+ * > 4000 coordinates on CPU / > 100000 on CUDA) or B200_NMS_TV_TRICK (coordinate trick).
+ *   objectness [B, total] fp32, deltas [B, total, 4] fp32, anchors [total, 4] fp32 xyxy,
+ *   level_sizes [L] int32 (host), image_hw [B,2] fp32 (device; h,w)
+ *   out_boxes [B, post_nms_top_n, 4], out_scores [B, post_nms_top_n], out_index [B, post] int32
+ *   (flat anchor index, may be NULL), out_count [B] int32 */
+int b200_rpn_filter(const float* objectness, const float* deltas, const float* anchors,
+                    int32_t batch, int32_t total_anchors, const int32_t* level_sizes_host,
+                    int32_t num_levels, const float* image_hw, int32_t pre_nms_top_n,
+                    int32_t post_nms_top_n, double nms_thr, float score_thr, float min_size,
+                    int32_t nms_mode, float* out_boxes, float* out_scores, int32_t* out_index, int32_t* out_count,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * packing for the multi-GPU exchange (the all-gather itself is NCCL via torch.distributed)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Packs [B,max_det,6] detections + counts into one contiguous fixed-capacity message
+ * [B*(1+max_det*6)] fp32 (count stored as a float bit pattern of the int) so that a single
+ * ncclAllGather moves the variable-length kept lists (replaces the pickle-file merge of
+ * yolo/procedures/eval_results.py:12-31 and detection/utils.py:75-115). */
+int b200_pack_detections(const float* det, const int32_t* det_count, int32_t batch,
+                         int32_t max_det, float* message, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DET_H_ */

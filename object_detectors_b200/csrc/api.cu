@@ -1,0 +1,435 @@
+// api.cu -- the extern "C" boundary of libb200det.so (see include/b200det.h).
+// Host-side only: argument validation, workspace carving, kernel sequencing.  No allocation on
+// the stream-ordered entry points; the *_host convenience entry owns a small device pool.
+#include <mutex>
+
+#include "decode.cuh"
+#include "nms.cuh"
+
+namespace b200 {
+int launch_decode_filter(const DecodeParams& p, bool softmax, cudaStream_t stream);
+int launch_decode_dense(const DecodeParams& p, bool softmax, float* out, cudaStream_t stream);
+int launch_box_iou(const float*, int, const float*, int, int, int, float*, cudaStream_t);
+int launch_box_iou_pair(const float*, const float*, int, int, int, float*, cudaStream_t);
+int launch_iou_match(const float*, const int*, int, int, const float*, int, int, float, long long*,
+                     uint8_t*, unsigned long long*, cudaStream_t);
+int launch_rpn_filter(const float* objectness, const float* deltas, const float* anchors, int batch,
+                      int total, const int* level_sizes_host, int num_levels, const float* image_hw,
+                      int pre_k, int post_k, double nms_thr, float score_thr, float min_size, int nms_mode,
+                      float* out_boxes, float* out_scores, int* out_index, int* out_count,
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t rpn_workspace_bytes(int batch, int total, int num_levels, int pre_k);
+
+namespace {
+
+struct Carver {
+    unsigned char* p;
+    size_t left;
+    bool ok = true;
+    template <typename T>
+    T* take(size_t count) {
+        const size_t bytes = align_up(count * sizeof(T), 256);
+        if (bytes > left) { ok = false; return nullptr; }
+        T* r = reinterpret_cast<T*>(p);
+        p += bytes;
+        left -= bytes;
+        return r;
+    }
+};
+
+struct YoloWs {
+    int* count;
+    Cand* slab;
+    float4* cbox;
+    float* cscore;
+    int* clabel;
+    int* canchor;
+    unsigned long long* gkey;
+    float4* gbox;
+    float* garea;
+    int* glabel;
+    int* gsup;
+    int* gcidx;
+};
+
+size_t yolo_ws_layout(int batch, int cap, void* base, size_t bytes, YoloWs* w) {
+    // base == nullptr: size query
+    const size_t T = (size_t)batch * (size_t)cap;
+    const bool big = cap > kNmsSmemCap;
+    Carver c{reinterpret_cast<unsigned char*>(base), base ? bytes : (size_t)-1};
+    YoloWs tmp;
+    YoloWs& o = w ? *w : tmp;
+    const unsigned char* start = c.p;
+    o.count = c.take<int>((size_t)batch);
+    o.slab = c.take<Cand>(T);
+    o.cbox = c.take<float4>(T);
+    o.cscore = c.take<float>(T);
+    o.clabel = c.take<int>(T);
+    o.canchor = c.take<int>(T);
+    if (big) {
+        o.gkey = c.take<unsigned long long>(2 * T);
+        o.gbox = c.take<float4>(T);
+        o.garea = c.take<float>(T);
+        o.glabel = c.take<int>(T);
+        o.gsup = c.take<int>(T);
+        o.gcidx = c.take<int>(T);
+    } else {
+        o.gkey = nullptr; o.gbox = nullptr; o.garea = nullptr;
+        o.glabel = nullptr; o.gsup = nullptr; o.gcidx = nullptr;
+    }
+    if (!c.ok) return 0;
+    return (size_t)(c.p - start);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+}  // namespace b200
+
+namespace b200 {
+static __global__ void k_pack(const float* __restrict__ det, const int* __restrict__ cnt, int max_det,
+                       float* __restrict__ msg) {
+    const int b = blockIdx.x;
+    const int stride = 1 + max_det * 6;
+    const int n = min(cnt[b], max_det);
+    float* dst = msg + (size_t)b * stride;
+    if (threadIdx.x == 0) dst[0] = __int_as_float(n);
+    for (int i = threadIdx.x; i < max_det * 6; i += blockDim.x)
+        dst[1 + i] = i < n * 6 ? det[(size_t)b * max_det * 6 + i] : 0.f;
+}
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_abi_version(void) { return B200_ABI_VERSION; }
+
+const char* b200_error_string(int code) {
+    switch (code) {
+        case B200_OK: return "ok";
+        case B200_ERR_INVALID: return "invalid argument";
+        case B200_ERR_CUDA: return "CUDA runtime error (no device, launch failure or out of memory)";
+        case B200_ERR_WORKSPACE: return "workspace too small or misaligned";
+        default: return "unknown error";
+    }
+}
+
+int b200_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+    int dev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    B200_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ YOLO
+int b200_yolo_decode_dense(const b200_yolo_layout* layout, const float* const* heads,
+                           const float* idf, float* out, void* stream) {
+    if (!out) return B200_ERR_INVALID;
+    DecodeParams p{};
+    const int rc = make_decode_params(layout, heads, idf, &p);
+    if (rc != B200_OK) return rc;
+    return launch_decode_dense(p, layout->softmax != 0, out, static_cast<cudaStream_t>(stream));
+}
+
+size_t b200_yolo_workspace_bytes(const b200_yolo_layout* layout, int32_t capacity) {
+    if (!layout || capacity < 1 || layout->batch < 1) return 0;
+    return yolo_ws_layout(layout->batch, capacity, nullptr, 0, nullptr) + 256;
+}
+
+// Optional profiling hook (bench.py): events recorded on the call's stream right before / after
+// the fused decode+filter kernel, so its duration can be measured inside a timed region.
+static void* g_ev_decode_begin = nullptr;
+static void* g_ev_decode_end = nullptr;
+int b200_debug_set_decode_events(void* ev_begin, void* ev_end) {
+    g_ev_decode_begin = ev_begin;
+    g_ev_decode_end = ev_end;
+    return B200_OK;
+}
+
+static int yolo_run(const b200_yolo_layout* layout, const float* const* heads, const float* idf,
+                    float conf_thr, int capacity, int* count_buf, NmsParams& np, const YoloWs& w,
+                    cudaStream_t st) {
+    DecodeParams p{};
+    const int rc = make_decode_params(layout, heads, idf, &p);
+    if (rc != B200_OK) return rc;
+    p.thr = conf_thr;
+    p.slab = w.slab;
+    p.cap = capacity;
+    p.count = count_buf;
+    p.status = np.status;
+    B200_CUDA_TRY(cudaMemsetAsync(count_buf, 0, sizeof(int) * (size_t)layout->batch, st));
+    if (g_ev_decode_begin) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(g_ev_decode_begin), st));
+    const int rc2 = launch_decode_filter(p, layout->softmax != 0, st);
+    if (rc2 != B200_OK) return rc2;
+    if (g_ev_decode_end) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(g_ev_decode_end), st));
+    np.slab = w.slab;
+    np.count = count_buf;
+    np.cap = capacity;
+    np.smem_cap = kNmsSmemCap;
+    np.gkey = w.gkey; np.gbox = w.gbox; np.garea = w.garea;
+    np.glabel = w.glabel; np.gsup = w.gsup; np.gcidx = w.gcidx;
+    return launch_nms(np, layout->batch, /*from_slab=*/true, st);
+}
+
+int b200_yolo_decode_filter(const b200_yolo_layout* layout, const float* const* heads,
+                            const float* idf, float conf_thr, int32_t capacity, float* cand_box,
+                            float* cand_score, int32_t* cand_label, int32_t* cand_anchor,
+                            int32_t* cand_count, int32_t* status, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    if (!layout || !cand_box || !cand_score || !cand_label || !cand_anchor || !cand_count || !status ||
+        capacity < 1 || !aligned16(cand_box))
+        return B200_ERR_INVALID;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return B200_ERR_WORKSPACE;
+    YoloWs w;
+    if (!yolo_ws_layout(layout->batch, capacity, workspace, workspace_bytes, &w)) return B200_ERR_WORKSPACE;
+    NmsParams np{};
+    np.mode = -1;
+    np.status = status;
+    np.cbox = reinterpret_cast<float4*>(cand_box);
+    np.cscore = cand_score;
+    np.clabel = cand_label;
+    np.canchor = cand_anchor;
+    // the caller's count array doubles as the atomic slab cursor
+    return yolo_run(layout, heads, idf, conf_thr, capacity, cand_count, np, w, static_cast<cudaStream_t>(stream));
+}
+
+int b200_yolo_postprocess(const b200_yolo_layout* layout, const float* const* heads,
+                          const float* idf, float conf_thr, double nms_thr, int32_t nms_mode,
+                          int32_t capacity, int32_t max_det, float* det, int32_t* det_keep,
+                          int32_t* det_anchor, int32_t* det_count, int32_t* cand_count,
+                          int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!layout || !det || !det_keep || !det_count || !status || capacity < 1 || max_det < 1)
+        return B200_ERR_INVALID;
+    if (nms_mode < B200_NMS_MAJORITY || nms_mode > B200_NMS_TV_TRICK) return B200_ERR_INVALID;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return B200_ERR_WORKSPACE;
+    YoloWs w;
+    if (!yolo_ws_layout(layout->batch, capacity, workspace, workspace_bytes, &w)) return B200_ERR_WORKSPACE;
+    NmsParams np{};
+    np.mode = nms_mode;
+    np.thr_f = (float)nms_thr;
+    np.thr_d = nms_thr;
+    np.fast_reject = nms_mode == B200_NMS_MAJORITY ? (np.thr_f > 0.f) : (nms_thr >= 0.0);
+    np.status = status;
+    np.cbox = w.cbox; np.cscore = w.cscore; np.clabel = w.clabel; np.canchor = w.canchor;
+    np.det = det; np.det_keep = det_keep; np.det_anchor = det_anchor; np.det_count = det_count;
+    np.cand_count_out = cand_count;
+    np.max_det = max_det;
+    return yolo_run(layout, heads, idf, conf_thr, capacity, w.count, np, w, static_cast<cudaStream_t>(stream));
+}
+
+// ----------------------------------------------------------------------------- host-buffer e2e
+namespace {
+struct HostPool {
+    std::mutex mu;
+    void* heads[B200_MAX_SCALES] = {nullptr, nullptr, nullptr, nullptr};
+    size_t head_bytes[B200_MAX_SCALES] = {0, 0, 0, 0};
+    void* idf = nullptr; size_t idf_bytes = 0;
+    void* ws = nullptr; size_t ws_bytes = 0;
+    void* out = nullptr; size_t out_bytes = 0;
+    cudaStream_t copy = nullptr, compute = nullptr;
+    cudaEvent_t ev[64];
+    bool init = false;
+    cudaError_t grow(void** p, size_t* have, size_t want) {
+        if (*have >= want) return cudaSuccess;
+        if (*p) cudaFree(*p);
+        *p = nullptr; *have = 0;
+        cudaError_t e = cudaMalloc(p, want);
+        if (e == cudaSuccess) *have = want;
+        return e;
+    }
+};
+HostPool g_pool;
+}  // namespace
+
+int b200_yolo_postprocess_host(const b200_yolo_layout* layout, const float* const* heads_host,
+                               const float* idf_host, float conf_thr, double nms_thr,
+                               int32_t nms_mode, int32_t capacity, int32_t max_det,
+                               float* det_host, int32_t* det_keep_host, int32_t* det_count_host,
+                               int32_t* status_host) {
+    if (!layout || !heads_host || !det_host || !det_count_host || capacity < 1 || max_det < 1)
+        return B200_ERR_INVALID;
+    HostPool& P = g_pool;
+    std::lock_guard<std::mutex> lock(P.mu);
+    const int B = layout->batch, A = layout->num_anchors, CH = 5 + layout->num_classes;
+    if (!P.init) {
+        B200_CUDA_TRY(cudaStreamCreateWithFlags(&P.copy, cudaStreamNonBlocking));
+        B200_CUDA_TRY(cudaStreamCreateWithFlags(&P.compute, cudaStreamNonBlocking));
+        for (auto& e : P.ev) B200_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        P.init = true;
+    }
+    size_t per_img[B200_MAX_SCALES];
+    for (int s = 0; s < layout->num_scales; ++s) {
+        per_img[s] = (size_t)A * CH * layout->grid[s] * layout->grid[s] * sizeof(float);
+        B200_CUDA_TRY(P.grow(&P.heads[s], &P.head_bytes[s], per_img[s] * B));
+    }
+    // sub-batches: copies of chunk i+1 overlap the kernels of chunk i
+    const int chunk = B >= 16 ? (B + 7) / 8 : B;
+    const int nchunk = (B + chunk - 1) / chunk;
+    if (nchunk > 64) return B200_ERR_INVALID;
+    b200_yolo_layout sub = *layout;
+    sub.batch = chunk;
+    const size_t ws_one = b200_yolo_workspace_bytes(&sub, capacity);
+    B200_CUDA_TRY(P.grow(&P.ws, &P.ws_bytes, ws_one * 2));
+    const size_t det_b = (size_t)B * max_det * 6 * sizeof(float);
+    const size_t keep_b = (size_t)B * max_det * sizeof(int);
+    const size_t cnt_b = align_up((size_t)B * sizeof(int), 256);
+    B200_CUDA_TRY(P.grow(&P.out, &P.out_bytes, det_b + keep_b + cnt_b + 256));
+    float* d_det = reinterpret_cast<float*>(P.out);
+    int* d_keep = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(P.out) + det_b);
+    int* d_cnt = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(P.out) + det_b + keep_b);
+    int* d_status = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(P.out) + det_b + keep_b + cnt_b);
+    const float* d_idf = nullptr;
+    if (idf_host) {
+        B200_CUDA_TRY(P.grow(&P.idf, &P.idf_bytes, sizeof(float) * layout->num_classes));
+        B200_CUDA_TRY(cudaMemcpyAsync(P.idf, idf_host, sizeof(float) * layout->num_classes,
+                                      cudaMemcpyHostToDevice, P.copy));
+        d_idf = reinterpret_cast<const float*>(P.idf);
+    }
+    B200_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int), P.copy));
+    for (int c = 0; c < nchunk; ++c) {
+        const int b0 = c * chunk, nb = (b0 + chunk <= B) ? chunk : B - b0;
+        const float* dev_heads[B200_MAX_SCALES] = {nullptr, nullptr, nullptr, nullptr};
+        for (int s = 0; s < layout->num_scales; ++s) {
+            unsigned char* dst = reinterpret_cast<unsigned char*>(P.heads[s]) + per_img[s] * b0;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(heads_host[s]) + per_img[s] * b0;
+            B200_CUDA_TRY(cudaMemcpyAsync(dst, src, per_img[s] * nb, cudaMemcpyHostToDevice, P.copy));
+            dev_heads[s] = reinterpret_cast<const float*>(dst);
+        }
+        B200_CUDA_TRY(cudaEventRecord(P.ev[c], P.copy));
+        B200_CUDA_TRY(cudaStreamWaitEvent(P.compute, P.ev[c], 0));
+        sub.batch = nb;
+        void* ws = reinterpret_cast<unsigned char*>(P.ws) + ws_one * (c & 1);
+        const int rc = b200_yolo_postprocess(&sub, dev_heads, d_idf, conf_thr, nms_thr, nms_mode, capacity,
+                                             max_det, d_det + (size_t)b0 * max_det * 6,
+                                             d_keep + (size_t)b0 * max_det, nullptr, d_cnt + b0, nullptr,
+                                             d_status, ws, ws_one, P.compute);
+        if (rc != B200_OK) return rc;
+    }
+    B200_CUDA_TRY(cudaMemcpyAsync(det_host, d_det, det_b, cudaMemcpyDeviceToHost, P.compute));
+    if (det_keep_host) B200_CUDA_TRY(cudaMemcpyAsync(det_keep_host, d_keep, keep_b, cudaMemcpyDeviceToHost, P.compute));
+    B200_CUDA_TRY(cudaMemcpyAsync(det_count_host, d_cnt, sizeof(int) * B, cudaMemcpyDeviceToHost, P.compute));
+    if (status_host) B200_CUDA_TRY(cudaMemcpyAsync(status_host, d_status, sizeof(int), cudaMemcpyDeviceToHost, P.compute));
+    B200_CUDA_TRY(cudaStreamSynchronize(P.compute));
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------- NMS
+size_t b200_nms_workspace_bytes(int64_t total_boxes, int32_t num_segments) {
+    (void)num_segments;
+    if (total_boxes < 0) return 0;
+    const size_t T = (size_t)(total_boxes > 0 ? total_boxes : 1);
+    return align_up(16 * T, 256) + align_up(16 * T, 256) + 4 * align_up(4 * T, 256) + 256;
+}
+
+int b200_nms(const float* boxes, const float* scores, const int32_t* labels, const int32_t* seg_offsets,
+             int32_t num_segments, int64_t total_boxes, double iou_thr, int32_t mode, int64_t* keep,
+             int32_t* keep_count, int32_t* labels_out, void* workspace, size_t workspace_bytes,
+             void* stream) {
+    if (num_segments < 0 || total_boxes < 0) return B200_ERR_INVALID;
+    if (num_segments == 0) return B200_OK;
+    if (!seg_offsets || !keep_count) return B200_ERR_INVALID;
+    if (total_boxes > 0 && (!boxes || !scores || !keep || !aligned16(boxes))) return B200_ERR_INVALID;
+    if (mode < B200_NMS_MAJORITY || mode > B200_NMS_TV_TRICK) return B200_ERR_INVALID;
+    if (mode != B200_NMS_TV && !labels && total_boxes > 0) return B200_ERR_INVALID;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u) ||
+        workspace_bytes < b200_nms_workspace_bytes(total_boxes, num_segments))
+        return B200_ERR_WORKSPACE;
+    const size_t T = (size_t)(total_boxes > 0 ? total_boxes : 1);
+    Carver c{reinterpret_cast<unsigned char*>(workspace), workspace_bytes};
+    NmsParams np{};
+    np.gkey = c.take<unsigned long long>(2 * T);
+    np.gbox = c.take<float4>(T);
+    np.garea = c.take<float>(T);
+    np.glabel = c.take<int>(T);
+    np.gsup = c.take<int>(T);
+    np.gcidx = c.take<int>(T);
+    if (!c.ok) return B200_ERR_WORKSPACE;
+    np.boxes = boxes; np.scores = scores; np.labels = labels; np.seg_offsets = seg_offsets;
+    np.keep = reinterpret_cast<long long*>(keep); np.keep_count = keep_count; np.labels_out = labels_out;
+    np.mode = mode;
+    np.thr_f = (float)iou_thr;
+    np.thr_d = iou_thr;
+    np.fast_reject = mode == B200_NMS_MAJORITY ? (np.thr_f > 0.f) : (iou_thr >= 0.0);
+    np.smem_cap = kNmsSmemCap;
+    return launch_nms(np, num_segments, /*from_slab=*/false, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------- IoU
+int b200_box_iou(const float* boxes1, int32_t m, const float* boxes2, int32_t n, int32_t kind,
+                 int32_t xcycwh, float* out, void* stream) {
+    if (m < 0 || n < 0 || kind < B200_IOU || kind > B200_IOU_TV) return B200_ERR_INVALID;
+    if (m == 0 || n == 0) return B200_OK;
+    if (!boxes1 || !boxes2 || !out || !aligned16(boxes1) || !aligned16(boxes2)) return B200_ERR_INVALID;
+    if (kind == B200_IOU_TV && xcycwh) return B200_ERR_INVALID;
+    return launch_box_iou(boxes1, m, boxes2, n, kind, xcycwh, out, static_cast<cudaStream_t>(stream));
+}
+
+int b200_box_iou_paired(const float* boxes1, const float* boxes2, int32_t k, int32_t kind,
+                        int32_t xcycwh, float* out, void* stream) {
+    if (k < 0 || kind < B200_IOU || kind > B200_IOU_TV) return B200_ERR_INVALID;
+    if (k == 0) return B200_OK;
+    if (!boxes1 || !boxes2 || !out || !aligned16(boxes1) || !aligned16(boxes2)) return B200_ERR_INVALID;
+    return launch_box_iou_pair(boxes1, boxes2, k, kind, xcycwh, out, static_cast<cudaStream_t>(stream));
+}
+
+size_t b200_iou_match_workspace_bytes(int32_t batch, int32_t max_gt) {
+    if (batch < 1 || max_gt < 1) return 0;
+    return align_up(sizeof(unsigned long long) * (size_t)batch * max_gt, 256);
+}
+
+int b200_iou_match(const float* gt, const int32_t* gt_count, int32_t batch, int32_t max_gt,
+                   const float* anchors, int32_t n, int32_t kind, float ignore_thr, int64_t* best_anchor,
+                   uint8_t* noobj, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!gt || !gt_count || !anchors || !best_anchor || !noobj || batch < 1 || max_gt < 1 || n < 1)
+        return B200_ERR_INVALID;
+    if (kind < B200_IOU || kind > B200_CIOU || !aligned16(gt) || !aligned16(anchors)) return B200_ERR_INVALID;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u) ||
+        workspace_bytes < b200_iou_match_workspace_bytes(batch, max_gt))
+        return B200_ERR_WORKSPACE;
+    return launch_iou_match(gt, gt_count, batch, max_gt, anchors, n, kind, ignore_thr,
+                            reinterpret_cast<long long*>(best_anchor), noobj,
+                            reinterpret_cast<unsigned long long*>(workspace), static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------- RPN
+size_t b200_rpn_workspace_bytes(int32_t batch, int32_t total_anchors, int32_t num_levels,
+                                int32_t pre_nms_top_n) {
+    if (batch < 1 || total_anchors < 1 || num_levels < 1 || pre_nms_top_n < 1) return 0;
+    return rpn_workspace_bytes(batch, total_anchors, num_levels, pre_nms_top_n);
+}
+
+int b200_rpn_filter(const float* objectness, const float* deltas, const float* anchors, int32_t batch,
+                    int32_t total_anchors, const int32_t* level_sizes_host, int32_t num_levels,
+                    const float* image_hw, int32_t pre_nms_top_n, int32_t post_nms_top_n, double nms_thr,
+                    float score_thr, float min_size, int32_t nms_mode, float* out_boxes, float* out_scores,
+                    int32_t* out_index, int32_t* out_count, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+    if (!objectness || !deltas || !anchors || !level_sizes_host || !image_hw || !out_boxes || !out_scores ||
+        !out_count || batch < 1 || total_anchors < 1 || num_levels < 1 || num_levels > 16 ||
+        pre_nms_top_n < 1 || post_nms_top_n < 1)
+        return B200_ERR_INVALID;
+    if (nms_mode != B200_NMS_TV_CLASS && nms_mode != B200_NMS_TV_TRICK) return B200_ERR_INVALID;
+    if (!aligned16(deltas) || !aligned16(anchors) || !aligned16(out_boxes)) return B200_ERR_INVALID;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u) ||
+        workspace_bytes < b200_rpn_workspace_bytes(batch, total_anchors, num_levels, pre_nms_top_n))
+        return B200_ERR_WORKSPACE;
+    return launch_rpn_filter(objectness, deltas, anchors, batch, total_anchors, level_sizes_host, num_levels,
+                             image_hw, pre_nms_top_n, post_nms_top_n, nms_thr, score_thr, min_size, nms_mode,
+                             out_boxes, out_scores, out_index, out_count, workspace, workspace_bytes,
+                             static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------ pack
+int b200_pack_detections(const float* det, const int32_t* det_count, int32_t batch, int32_t max_det,
+                         float* message, void* stream) {
+    if (!det || !det_count || !message || batch < 1 || max_det < 1) return B200_ERR_INVALID;
+    b200::k_pack<<<batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(det, det_count, max_det, message);
+    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+// iou.cu -- pairwise IoU family and IoU-based target matching (sm_100a).
+//
+//  k_box_iou       : [M,N] matrix of helper.bbox_iou (IoU/GIoU/DIoU/CIoU) or torchvision box_iou.
+//  k_box_iou_pair  : element-wise version for the loss-side call (yolo_forw.py:125).
+//  k_iou_match     : YOLOForw.get_target's IoU + reductions (yolo_forw.py:186-201) without ever
+//                    writing the [M,N] matrix: every thread keeps a few anchors in registers,
+//                    walks the image's ground-truth boxes (staged in shared memory), tracks
+//                    "all IoUs below the ignore threshold" per anchor and feeds a per-GT first
+//                    argmax through redux.sync -> shared 64-bit atomicMax -> global atomicMax.
+//  k_match_finish  : unpacks the argmax keys and clears the matched anchors in the mask.
+// Bound: SM issue rate (about 35 fp32 lane-ops per GIoU pair), not memory.
+#include "common.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ Box load_box(const float* p, int xcycwh) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    if (xcycwh) return abs_coord(v.x, v.y, v.z, v.w);
+    return Box{v.x, v.y, v.z, v.w};
+}
+
+__global__ void __launch_bounds__(256)
+k_box_iou(const float* __restrict__ b1, int M, const float* __restrict__ b2, int N, int kind,
+          int xcycwh, float* __restrict__ out) {
+    __shared__ Box rows[16];
+    const int m0 = blockIdx.y * 16;
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (threadIdx.x < 16 && m0 + threadIdx.x < M) rows[threadIdx.x] = load_box(b1 + 4 * (size_t)(m0 + threadIdx.x), xcycwh);
+    __syncthreads();
+    if (n >= N) return;
+    const Box q = load_box(b2 + 4 * (size_t)n, xcycwh);
+    const int mr = min(16, M - m0);
+    for (int r = 0; r < mr; ++r) out[(size_t)(m0 + r) * N + n] = pair_iou(rows[r], q, kind);
+}
+
+__global__ void __launch_bounds__(256)
+k_box_iou_pair(const float* __restrict__ b1, const float* __restrict__ b2, int K, int kind,
+               int xcycwh, float* __restrict__ out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= K) return;
+    out[i] = pair_iou(load_box(b1 + 4 * (size_t)i, xcycwh), load_box(b2 + 4 * (size_t)i, xcycwh), kind);
+}
+
+static constexpr int kMatchThreads = 256;
+static constexpr int kMatchItems = 4;    // anchors per thread
+static constexpr int kGtChunk = 128;     // ground-truth boxes staged per pass
+
+__global__ void __launch_bounds__(kMatchThreads)
+k_iou_match(const float* __restrict__ gt, const int* __restrict__ gt_count, int max_gt,
+            const float* __restrict__ anchors, int N, int kind, float ignore_thr,
+            unsigned long long* __restrict__ best_key, uint8_t* __restrict__ noobj) {
+    __shared__ Box sgt[kGtChunk];
+    __shared__ unsigned long long sbest[kGtChunk];
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int M = min(gt_count[b], max_gt);
+    const int n0 = blockIdx.x * (kMatchThreads * kMatchItems);
+
+    Box anc[kMatchItems];
+    bool valid[kMatchItems], free_[kMatchItems];
+#pragma unroll
+    for (int k = 0; k < kMatchItems; ++k) {
+        const int n = n0 + k * kMatchThreads + tid;
+        valid[k] = n < N;
+        free_[k] = true;
+        anc[k] = valid[k] ? load_box(anchors + 4 * (size_t)n, 1) : Box{0.f, 0.f, 0.f, 0.f};
+    }
+
+    for (int mc = 0; mc < M; mc += kGtChunk) {
+        const int mm = min(kGtChunk, M - mc);
+        __syncthreads();
+        for (int i = tid; i < mm; i += kMatchThreads) {
+            sgt[i] = load_box(gt + ((size_t)b * max_gt + mc + i) * 4, 1);
+            sbest[i] = 0ull;
+        }
+        __syncthreads();
+        for (int i = 0; i < mm; ++i) {
+            const Box g = sgt[i];
+            unsigned bk = 0u;          // orderable(best iou) over this thread's anchors
+            unsigned bn = 0xffffffffu; // its anchor index
+#pragma unroll
+            for (int k = 0; k < kMatchItems; ++k) {
+                if (valid[k]) {
+                    const float v = pair_iou(g, anc[k], kind);
+                    free_[k] = free_[k] && (v < ignore_thr);
+                    const unsigned ok = orderable(v);
+                    if (ok > bk) { bk = ok; bn = (unsigned)(n0 + k * kMatchThreads + tid); }  // ascending n: first max
+                }
+            }
+            const unsigned wmax = __reduce_max_sync(kFullMask, bk);
+            const unsigned wn = __reduce_min_sync(kFullMask, bk == wmax ? bn : 0xffffffffu);
+            if (lane == 0 && wn != 0xffffffffu)
+                atomicMax(&sbest[i], ((unsigned long long)wmax << 32) | (unsigned long long)(~wn));
+        }
+        __syncthreads();
+        for (int i = tid; i < mm; i += kMatchThreads)
+            if (sbest[i]) atomicMax(best_key + (size_t)b * max_gt + mc + i, sbest[i]);
+    }
+#pragma unroll
+    for (int k = 0; k < kMatchItems; ++k) {
+        const int n = n0 + k * kMatchThreads + tid;
+        if (valid[k]) noobj[(size_t)b * N + n] = free_[k] ? 1 : 0;
+    }
+}
+
+__global__ void k_match_finish(const unsigned long long* __restrict__ best_key,
+                               const int* __restrict__ gt_count, int max_gt, int N,
+                               long long* __restrict__ best_anchor, uint8_t* __restrict__ noobj) {
+    const int b = blockIdx.x;
+    const int M = min(gt_count[b], max_gt);
+    for (int m = threadIdx.x; m < max_gt; m += blockDim.x) {
+        long long idx = 0;
+        if (m < M) {
+            idx = (long long)(~(unsigned)(best_key[(size_t)b * max_gt + m] & 0xffffffffull));
+            if (idx >= 0 && idx < N) noobj[(size_t)b * N + idx] = 0;   // yolo_forw.py:201
+        }
+        best_anchor[(size_t)b * max_gt + m] = idx;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+int launch_box_iou(const float* b1, int m, const float* b2, int n, int kind, int xcycwh, float* out,
+                   cudaStream_t stream) {
+    if (m <= 0 || n <= 0) return B200_OK;
+    dim3 grid(cdiv(n, 256), cdiv(m, 16));
+    k_box_iou<<<grid, 256, 0, stream>>>(b1, m, b2, n, kind, xcycwh, out);
+    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
+
+int launch_box_iou_pair(const float* b1, const float* b2, int k, int kind, int xcycwh, float* out,
+                        cudaStream_t stream) {
+    if (k <= 0) return B200_OK;
+    k_box_iou_pair<<<cdiv(k, 256), 256, 0, stream>>>(b1, b2, k, kind, xcycwh, out);
+    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
+
+int launch_iou_match(const float* gt, const int* gt_count, int batch, int max_gt, const float* anchors,
+                     int n, int kind, float ignore_thr, long long* best_anchor, uint8_t* noobj,
+                     unsigned long long* best_key, cudaStream_t stream) {
+    if (cudaMemsetAsync(best_key, 0, sizeof(unsigned long long) * (size_t)batch * max_gt, stream) != cudaSuccess)
+        return B200_ERR_CUDA;
+    dim3 grid(cdiv(n, kMatchThreads * kMatchItems), batch);
+    k_iou_match<<<grid, kMatchThreads, 0, stream>>>(gt, gt_count, max_gt, anchors, n, kind, ignore_thr,
+                                                    best_key, noobj);
+    k_match_finish<<<batch, 128, 0, stream>>>(best_key, gt_count, max_gt, n, best_anchor, noobj);
+    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
+
+}  // namespace b200

@@ -1,0 +1,337 @@
+"""Tensor-level front end of libb200det.so: validates CUDA tensors, owns scratch buffers and
+passes raw device pointers + the current CUDA stream through the C ABI.  Everything here is
+plumbing; the arithmetic lives in csrc/*.cu.  CUDA tensors only -- there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (CIOU, DIOU, GIOU, IOU, IOU_TV, NMS_MAJORITY, NMS_TV, NMS_TV_CLASS,  # noqa: F401
+                   NMS_TV_TRICK)
+
+Tensor = torch.Tensor
+
+_scratch: Dict[Tuple[int, str], Tensor] = {}
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(t: Tensor, name: str, dtype=None) -> Tensor:
+    if not isinstance(t, Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (object_detectors_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def workspace(nbytes: int, device: torch.device, tag: str = "ws") -> Tensor:
+    """Grow-only byte buffer per (device, tag); torch's allocator returns >= 512 B alignment."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+# --------------------------------------------------------------------------------------- YOLO
+def make_layout(grids: Sequence[int], batch: int, anchors, img_size: float, num_classes: int,
+                softmax: bool) -> _lib.YoloLayout:
+    """Host-side geometry with the reference's roundings (yolo_forw.py:97-99,108-113):
+    ``scaled = fp32(a / (img/grid))`` (python double division, then cast), ``rel = scaled/grid``
+    as an fp32 division."""
+    if len(grids) != len(anchors) or not 1 <= len(grids) <= _lib.MAX_SCALES:
+        raise RuntimeError("anchors must hold one list per head tensor (<= 4 scales)")
+    na = len(anchors[0])
+    if any(len(a) != na for a in anchors) or not 1 <= na <= _lib.MAX_ANCHORS:
+        raise RuntimeError("every scale must use the same number of anchors (1..8)")
+    lay = _lib.YoloLayout()
+    lay.num_scales, lay.num_anchors, lay.num_classes = len(grids), na, int(num_classes)
+    lay.batch, lay.softmax, lay.img_size = int(batch), int(bool(softmax)), float(img_size)
+    for s, g in enumerate(grids):
+        lay.grid[s] = int(g)
+        stride = img_size / g
+        for a, (aw, ah) in enumerate(anchors[s]):
+            lay.anchor_rel[s][a][0] = float(np.float32(aw / stride) / np.float32(g))
+            lay.anchor_rel[s][a][1] = float(np.float32(ah / stride) / np.float32(g))
+    return lay
+
+
+def _heads_args(heads: Sequence[Tensor], anchors, img_size, num_classes, softmax):
+    hs = [_need_cuda(h, f"heads[{i}]", torch.float32) for i, h in enumerate(heads)]
+    b = hs[0].shape[0]
+    na = len(anchors[0])
+    grids = []
+    for h in hs:
+        if h.dim() != 4 or h.shape[0] != b or h.shape[1] != na * (5 + num_classes) or h.shape[2] != h.shape[3]:
+            raise RuntimeError(f"head tensor of shape {tuple(h.shape)} is not [B, A*(5+C), G, G] "
+                               f"with A={na}, C={num_classes}")
+        grids.append(h.shape[2])
+    lay = make_layout(grids, b, anchors, img_size, num_classes, softmax)
+    arr = (C.c_void_p * len(hs))(*[h.data_ptr() for h in hs])
+    n_total = sum(g * g * na for g in grids)
+    return hs, lay, arr, n_total
+
+
+def _idf_arg(idf: Optional[Tensor], num_classes: int, device) -> Optional[Tensor]:
+    if idf is None:
+        return None
+    idf = torch.as_tensor(idf, dtype=torch.float32, device=device).contiguous()
+    if idf.numel() == 1:          # the reference's `idf_logits = tensor(1)` scalar (yolo_forw.py:38)
+        idf = idf.reshape(1).expand(num_classes).contiguous()
+    if idf.numel() != num_classes:
+        raise RuntimeError("idf must hold one weight per class")
+    return idf
+
+
+def yolo_decode_dense(heads, anchors, img_size, num_classes, idf=None, softmax=True) -> Tensor:
+    """-> [B, N, 5+C]  (YOLOForw.forward inference branch)."""
+    lib = _lib.load()
+    hs, lay, arr, n = _heads_args(heads, anchors, img_size, num_classes, softmax)
+    idf = _idf_arg(idf, num_classes, hs[0].device)
+    out = torch.empty((lay.batch, n, 5 + num_classes), dtype=torch.float32, device=hs[0].device)
+    _lib.check(lib.b200_yolo_decode_dense(C.byref(lay), arr, _ptr(idf), _ptr(out), _stream()),
+               "b200_yolo_decode_dense")
+    return out
+
+
+def yolo_decode_filter(heads, anchors, img_size, num_classes, idf=None, softmax=True,
+                       conf_thr: float = 0.1, capacity: Optional[int] = None):
+    """-> dict(box [B,cap,4], score [B,cap], label [B,cap] i32, anchor [B,cap] i32, count [B] i32)."""
+    lib = _lib.load()
+    hs, lay, arr, n = _heads_args(heads, anchors, img_size, num_classes, softmax)
+    dev = hs[0].device
+    idf = _idf_arg(idf, num_classes, dev)
+    cap = int(capacity or n)
+    b = lay.batch
+    box = torch.empty((b, cap, 4), dtype=torch.float32, device=dev)
+    score = torch.empty((b, cap), dtype=torch.float32, device=dev)
+    label = torch.empty((b, cap), dtype=torch.int32, device=dev)
+    anchor = torch.empty((b, cap), dtype=torch.int32, device=dev)
+    count = torch.empty((b,), dtype=torch.int32, device=dev)
+    status = torch.zeros((1,), dtype=torch.int32, device=dev)
+    nbytes = lib.b200_yolo_workspace_bytes(C.byref(lay), cap)
+    ws = workspace(nbytes, dev, "yolo")
+    _lib.check(lib.b200_yolo_decode_filter(C.byref(lay), arr, _ptr(idf), float(np.float32(conf_thr)), cap,
+                                           _ptr(box), _ptr(score), _ptr(label), _ptr(anchor), _ptr(count),
+                                           _ptr(status), _ptr(ws), ws.numel(), _stream()),
+               "b200_yolo_decode_filter")
+    return {"box": box, "score": score, "label": label, "anchor": anchor, "count": count, "status": status}
+
+
+class YoloPostprocess:
+    """Reusable plan for b200_yolo_postprocess: owns outputs + workspace so repeated calls
+    (benchmark loop, CUDA-graph capture) allocate nothing."""
+
+    def __init__(self, grids, batch, anchors, img_size, num_classes, softmax=True, conf_thr=0.1,
+                 nms_thr=0.6, nms_mode=NMS_MAJORITY, capacity=None, max_det=None, device="cuda"):
+        self.lib = _lib.load()
+        self.dev = torch.device(device)
+        self.lay = make_layout(grids, batch, anchors, img_size, num_classes, softmax)
+        self.num_classes = num_classes
+        na = len(anchors[0])
+        self.head_shapes = [(batch, na * (5 + num_classes), g, g) for g in grids]
+        self.n = sum(g * g * na for g in grids)
+        self.cap = int(capacity or self.n)
+        self.max_det = int(max_det or self.cap)
+        self.conf_thr = float(np.float32(conf_thr))
+        self.nms_thr = float(nms_thr)   # double: MAJORITY rounds to fp32 in C, TV modes compare in double
+        self.nms_mode = int(nms_mode)
+        b = batch
+        self.det = torch.empty((b, self.max_det, 6), dtype=torch.float32, device=self.dev)
+        self.det_keep = torch.empty((b, self.max_det), dtype=torch.int32, device=self.dev)
+        self.det_anchor = torch.empty((b, self.max_det), dtype=torch.int32, device=self.dev)
+        self.det_count = torch.zeros((b,), dtype=torch.int32, device=self.dev)
+        self.cand_count = torch.zeros((b,), dtype=torch.int32, device=self.dev)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=self.dev)
+        self.ws_bytes = self.lib.b200_yolo_workspace_bytes(C.byref(self.lay), self.cap)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.dev)
+
+    def __call__(self, heads: Sequence[Tensor], idf: Optional[Tensor] = None):
+        for h, shp in zip(heads, self.head_shapes):
+            if tuple(h.shape) != shp or not h.is_cuda or h.dtype != torch.float32 or not h.is_contiguous():
+                raise RuntimeError(f"head tensor {tuple(h.shape)} does not match the plan {shp} "
+                                   "(CUDA, fp32, contiguous)")
+        arr = (C.c_void_p * len(heads))(*[h.data_ptr() for h in heads])
+        idf = _idf_arg(idf, self.num_classes, self.dev)
+        _lib.check(self.lib.b200_yolo_postprocess(
+            C.byref(self.lay), arr, _ptr(idf), self.conf_thr, self.nms_thr, self.nms_mode, self.cap,
+            self.max_det, _ptr(self.det), _ptr(self.det_keep), _ptr(self.det_anchor), _ptr(self.det_count),
+            _ptr(self.cand_count), _ptr(self.status), _ptr(self.ws), self.ws_bytes, _stream()),
+            "b200_yolo_postprocess")
+        return self.det, self.det_keep, self.det_anchor, self.det_count, self.cand_count
+
+    def check_status(self):
+        st = int(self.status.item())
+        if st & 1:
+            raise RuntimeError("candidate slab overflow: raise `capacity`")
+        if st & 2:
+            raise RuntimeError("more detections than `max_det`")
+
+
+def yolo_postprocess(heads, anchors, img_size, num_classes, idf=None, softmax=True, conf_thr=0.1,
+                     nms_thr=0.6, nms_mode=NMS_MAJORITY, capacity=None, max_det=None):
+    hs, lay, arr, n = _heads_args(heads, anchors, img_size, num_classes, softmax)
+    plan = YoloPostprocess([h.shape[2] for h in hs], lay.batch, anchors, img_size, num_classes, softmax,
+                           conf_thr, nms_thr, nms_mode, capacity, max_det, hs[0].device)
+    out = plan(hs, idf)
+    plan.check_status()
+    return out
+
+
+def yolo_postprocess_host(heads_host: Sequence[Tensor], anchors, img_size, num_classes, idf_host=None,
+                          softmax=True, conf_thr=0.1, nms_thr=0.6, nms_mode=NMS_MAJORITY,
+                          capacity=None, max_det=300, out=None):
+    """End-to-end entry with HOST tensors (pinned recommended): H2D, decode+NMS, D2H."""
+    lib = _lib.load()
+    b = heads_host[0].shape[0]
+    na = len(anchors[0])
+    grids = [h.shape[2] for h in heads_host]
+    for h in heads_host:
+        if h.is_cuda or h.dtype != torch.float32 or not h.is_contiguous():
+            raise RuntimeError("yolo_postprocess_host expects contiguous fp32 HOST tensors")
+    lay = make_layout(grids, b, anchors, img_size, num_classes, softmax)
+    n = sum(g * g * na for g in grids)
+    cap = int(capacity or n)
+    if out is None:
+        out = (torch.empty((b, max_det, 6), dtype=torch.float32).pin_memory(),
+               torch.empty((b, max_det), dtype=torch.int32).pin_memory(),
+               torch.empty((b,), dtype=torch.int32).pin_memory(),
+               torch.zeros((1,), dtype=torch.int32).pin_memory())
+    det, keep, cnt, status = out
+    arr = (C.c_void_p * len(heads_host))(*[h.data_ptr() for h in heads_host])
+    idf_p = C.c_void_p(0)
+    if idf_host is not None:
+        idf_host = torch.as_tensor(idf_host, dtype=torch.float32).contiguous()
+        idf_p = C.c_void_p(idf_host.data_ptr())
+    _lib.check(lib.b200_yolo_postprocess_host(C.byref(lay), arr, idf_p, float(np.float32(conf_thr)),
+                                              float(nms_thr), int(nms_mode), cap, int(max_det),
+                                              _ptr(det), _ptr(keep), _ptr(cnt), _ptr(status)),
+               "b200_yolo_postprocess_host")
+    return det, keep, cnt, status
+
+
+# ---------------------------------------------------------------------------------------- NMS
+def nms_segments(boxes: Tensor, scores: Tensor, labels: Optional[Tensor], seg_offsets: Tensor,
+                 iou_thr: float, mode: int):
+    """Batched NMS.  -> (keep int64 [T], keep_count int32 [S], labels_out int32 [T])."""
+    lib = _lib.load()
+    boxes = _need_cuda(boxes, "boxes", torch.float32)
+    scores = _need_cuda(scores, "scores", torch.float32)
+    seg_offsets = _need_cuda(seg_offsets, "seg_offsets", torch.int32)
+    t = boxes.shape[0]
+    s = seg_offsets.numel() - 1
+    if labels is not None:
+        labels = _need_cuda(labels, "labels").to(torch.int32).contiguous()
+    dev = boxes.device
+    keep = torch.empty((max(t, 1),), dtype=torch.int64, device=dev)
+    keep_count = torch.zeros((max(s, 1),), dtype=torch.int32, device=dev)
+    labels_out = torch.empty((max(t, 1),), dtype=torch.int32, device=dev) if mode == NMS_MAJORITY else None
+    nbytes = lib.b200_nms_workspace_bytes(t, s)
+    ws = workspace(nbytes, dev, "nms")
+    if boxes.data_ptr() % 16:
+        boxes = boxes.clone()
+    _lib.check(lib.b200_nms(_ptr(boxes), _ptr(scores), _ptr(labels), _ptr(seg_offsets), s, t, float(iou_thr),
+                            int(mode), _ptr(keep), _ptr(keep_count), _ptr(labels_out), _ptr(ws), ws.numel(),
+                            _stream()), "b200_nms")
+    return keep, keep_count, labels_out
+
+
+# ---------------------------------------------------------------------------------------- IoU
+def box_iou(b1: Tensor, b2: Tensor, kind: int = IOU, xcycwh: bool = False) -> Tensor:
+    lib = _lib.load()
+    b1 = _need_cuda(b1, "boxes1", torch.float32)
+    b2 = _need_cuda(b2, "boxes2", torch.float32)
+    m, n = b1.shape[0], b2.shape[0]
+    out = torch.empty((m, n), dtype=torch.float32, device=b1.device)
+    if b1.data_ptr() % 16:
+        b1 = b1.clone()
+    if b2.data_ptr() % 16:
+        b2 = b2.clone()
+    _lib.check(lib.b200_box_iou(_ptr(b1), m, _ptr(b2), n, int(kind), int(bool(xcycwh)), _ptr(out), _stream()),
+               "b200_box_iou")
+    return out
+
+
+def box_iou_paired(b1: Tensor, b2: Tensor, kind: int = IOU, xcycwh: bool = False) -> Tensor:
+    lib = _lib.load()
+    b1 = _need_cuda(b1, "boxes1", torch.float32)
+    b2 = _need_cuda(b2, "boxes2", torch.float32)
+    if b1.shape != b2.shape:
+        raise RuntimeError("paired IoU needs equal shapes")
+    k = b1.shape[0]
+    out = torch.empty((k,), dtype=torch.float32, device=b1.device)
+    if b1.data_ptr() % 16:
+        b1 = b1.clone()
+    if b2.data_ptr() % 16:
+        b2 = b2.clone()
+    _lib.check(lib.b200_box_iou_paired(_ptr(b1), _ptr(b2), k, int(kind), int(bool(xcycwh)), _ptr(out),
+                                       _stream()), "b200_box_iou_paired")
+    return out
+
+
+def iou_match(gt: Tensor, gt_count: Tensor, anchors: Tensor, kind: int = GIOU, ignore_thr: float = 0.5):
+    """gt [B, Mmax, 4] rel xc,yc,w,h; gt_count [B] i32; anchors [N,4] (cxypwh).
+    -> best_anchor int64 [B, Mmax], noobj bool [B, N]."""
+    lib = _lib.load()
+    gt = _need_cuda(gt, "gt", torch.float32)
+    gt_count = _need_cuda(gt_count, "gt_count", torch.int32)
+    anchors = _need_cuda(anchors, "anchors", torch.float32)
+    b, mmax = gt.shape[0], gt.shape[1]
+    n = anchors.shape[0]
+    dev = gt.device
+    best = torch.empty((b, mmax), dtype=torch.int64, device=dev)
+    noobj = torch.empty((b, n), dtype=torch.uint8, device=dev)
+    nbytes = lib.b200_iou_match_workspace_bytes(b, mmax)
+    ws = workspace(nbytes, dev, "match")
+    _lib.check(lib.b200_iou_match(_ptr(gt), _ptr(gt_count), b, mmax, _ptr(anchors), n, int(kind),
+                                  float(np.float32(ignore_thr)), _ptr(best), _ptr(noobj), _ptr(ws), ws.numel(),
+                                  _stream()), "b200_iou_match")
+    return best, noobj.view(torch.bool)
+
+
+# ---------------------------------------------------------------------------------------- RPN
+def rpn_filter(objectness: Tensor, deltas: Tensor, anchors: Tensor, level_sizes: Sequence[int],
+               image_hw: Tensor, pre_nms_top_n: int, post_nms_top_n: int, nms_thr: float = 0.7,
+               score_thr: float = 0.0, min_size: float = 1e-3, nms_mode: int = NMS_TV_CLASS):
+    """-> boxes [B,post,4], scores [B,post], index [B,post] i32, count [B] i32."""
+    lib = _lib.load()
+    objectness = _need_cuda(objectness, "objectness", torch.float32)
+    deltas = _need_cuda(deltas, "deltas", torch.float32)
+    anchors = _need_cuda(anchors, "anchors", torch.float32)
+    image_hw = _need_cuda(image_hw, "image_hw", torch.float32)
+    b, total = objectness.shape
+    dev = objectness.device
+    lv = (C.c_int32 * len(level_sizes))(*[int(v) for v in level_sizes])
+    boxes = torch.zeros((b, post_nms_top_n, 4), dtype=torch.float32, device=dev)
+    scores = torch.zeros((b, post_nms_top_n), dtype=torch.float32, device=dev)
+    index = torch.zeros((b, post_nms_top_n), dtype=torch.int32, device=dev)
+    count = torch.zeros((b,), dtype=torch.int32, device=dev)
+    nbytes = lib.b200_rpn_workspace_bytes(b, total, len(level_sizes), pre_nms_top_n)
+    ws = workspace(nbytes, dev, "rpn")
+    _lib.check(lib.b200_rpn_filter(_ptr(objectness), _ptr(deltas), _ptr(anchors), b, total, lv,
+                                   len(level_sizes), _ptr(image_hw), int(pre_nms_top_n), int(post_nms_top_n),
+                                   float(nms_thr), float(np.float32(score_thr)),
+                                   float(np.float32(min_size)), int(nms_mode), _ptr(boxes), _ptr(scores),
+                                   _ptr(index), _ptr(count), _ptr(ws), ws.numel(), _stream()),
+               "b200_rpn_filter")
+    return boxes, scores, index, count
+
+
+def pack_detections(det: Tensor, det_count: Tensor) -> Tensor:
+    lib = _lib.load()
+    b, max_det = det.shape[0], det.shape[1]
+    msg = torch.empty((b * (1 + max_det * 6),), dtype=torch.float32, device=det.device)
+    _lib.check(lib.b200_pack_detections(_ptr(det), _ptr(det_count), b, max_det, _ptr(msg), _stream()),
+               "b200_pack_detections")
+    return msg
