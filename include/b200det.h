@@ -155,7 +155,9 @@ int b200_debug_set_decode_events(void* ev_begin, void* ev_end);
  * NMS on caller-provided boxes, batched over segments (images, or image x level)
  * ---------------------------------------------------------------------------------------- */
 
-size_t b200_nms_workspace_bytes(int64_t total_boxes, int32_t num_segments);
+/* max_segment: host-known upper bound of any segment length (0 = total_boxes).  The scratch holds a
+ * suppression bitmask of num_segments * max_segment * ceil(max_segment/64) * 8 bytes. */
+size_t b200_nms_workspace_bytes(int64_t total_boxes, int32_t num_segments, int32_t max_segment);
 
 /* Replaces helper.nms_majority (helper.py:280), torchvision.ops.nms / batched_nms.
  *   boxes  [T,4] fp32 xyxy; scores [T] fp32; labels [T] int32 (required unless mode==TV)
@@ -168,8 +170,8 @@ size_t b200_nms_workspace_bytes(int64_t total_boxes, int32_t num_segments);
  *   iou_thr is a double: MAJORITY rounds it to fp32 like the reference's tensor compare,
  *   the TV modes compare (double)iou > iou_thr like torchvision. */
 int b200_nms(const float* boxes, const float* scores, const int32_t* labels,
-             const int32_t* seg_offsets, int32_t num_segments, int64_t total_boxes, double iou_thr,
-             int32_t mode, int64_t* keep, int32_t* keep_count, int32_t* labels_out,
+             const int32_t* seg_offsets, int32_t num_segments, int64_t total_boxes,
+             int32_t max_segment, double iou_thr, int32_t mode, int64_t* keep, int32_t* keep_count, int32_t* labels_out,
              void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -40,8 +40,8 @@ SIGNATURES = {
                                         _p, _sz, _p]),
     "b200_yolo_postprocess_host": (C.c_int, [_LP, _PP, _p, _f32, _f64, _i32, _i32, _i32, _p, _p, _p, _p]),
     "b200_debug_set_decode_events": (C.c_int, [_p, _p]),
-    "b200_nms_workspace_bytes": (_sz, [_i64, _i32]),
-    "b200_nms": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _f64, _i32, _p, _p, _p, _p, _sz, _p]),
+    "b200_nms_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "b200_nms": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _f64, _i32, _p, _p, _p, _p, _sz, _p]),
     "b200_box_iou": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _p, _p]),
     "b200_box_iou_paired": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
     "b200_iou_match_workspace_bytes": (_sz, [_i32, _i32]),

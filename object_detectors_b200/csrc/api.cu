@@ -44,18 +44,13 @@ struct YoloWs {
     float* cscore;
     int* clabel;
     int* canchor;
-    unsigned long long* gkey;
-    float4* gbox;
-    float* garea;
-    int* glabel;
-    int* gsup;
-    int* gcidx;
+    void* nms;          // scratch of the NMS kernels (nms_carve_scratch)
+    size_t nms_bytes;
 };
 
 size_t yolo_ws_layout(int batch, int cap, void* base, size_t bytes, YoloWs* w) {
     // base == nullptr: size query
     const size_t T = (size_t)batch * (size_t)cap;
-    const bool big = cap > kNmsSmemCap;
     Carver c{reinterpret_cast<unsigned char*>(base), base ? bytes : (size_t)-1};
     YoloWs tmp;
     YoloWs& o = w ? *w : tmp;
@@ -66,17 +61,8 @@ size_t yolo_ws_layout(int batch, int cap, void* base, size_t bytes, YoloWs* w) {
     o.cscore = c.take<float>(T);
     o.clabel = c.take<int>(T);
     o.canchor = c.take<int>(T);
-    if (big) {
-        o.gkey = c.take<unsigned long long>(2 * T);
-        o.gbox = c.take<float4>(T);
-        o.garea = c.take<float>(T);
-        o.glabel = c.take<int>(T);
-        o.gsup = c.take<int>(T);
-        o.gcidx = c.take<int>(T);
-    } else {
-        o.gkey = nullptr; o.gbox = nullptr; o.garea = nullptr;
-        o.glabel = nullptr; o.gsup = nullptr; o.gcidx = nullptr;
-    }
+    o.nms_bytes = nms_scratch_bytes(T, (size_t)batch, (size_t)cap);
+    o.nms = c.take<unsigned char>(o.nms_bytes);
     if (!c.ok) return 0;
     return (size_t)(c.p - start);
 }
@@ -167,13 +153,15 @@ static int yolo_run(const b200_yolo_layout* layout, const float* const* heads, c
     const int rc2 = launch_decode_filter(p, layout->softmax != 0, st);
     if (rc2 != B200_OK) return rc2;
     if (g_ev_decode_end) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(g_ev_decode_end), st));
+    if (!nms_carve_scratch(&np, (size_t)layout->batch * capacity, (size_t)layout->batch, (size_t)capacity,
+                           w.nms, w.nms_bytes))
+        return B200_ERR_WORKSPACE;
     np.slab = w.slab;
     np.count = count_buf;
     np.cap = capacity;
-    np.smem_cap = kNmsSmemCap;
-    np.gkey = w.gkey; np.gbox = w.gbox; np.garea = w.garea;
-    np.glabel = w.glabel; np.gsup = w.gsup; np.gcidx = w.gcidx;
-    return launch_nms(np, layout->batch, /*from_slab=*/true, st);
+    np.from_slab = 1;
+    np.max_seg = capacity;
+    return launch_nms(np, layout->batch, st);
 }
 
 int b200_yolo_decode_filter(const b200_yolo_layout* layout, const float* const* heads,
@@ -213,7 +201,6 @@ int b200_yolo_postprocess(const b200_yolo_layout* layout, const float* const* he
     np.mode = nms_mode;
     np.thr_f = (float)nms_thr;
     np.thr_d = nms_thr;
-    np.fast_reject = nms_mode == B200_NMS_MAJORITY ? (np.thr_f > 0.f) : (nms_thr >= 0.0);
     np.status = status;
     np.cbox = w.cbox; np.cscore = w.cscore; np.clabel = w.clabel; np.canchor = w.canchor;
     np.det = det; np.det_keep = det_keep; np.det_anchor = det_anchor; np.det_count = det_count;
@@ -319,44 +306,34 @@ int b200_yolo_postprocess_host(const b200_yolo_layout* layout, const float* cons
 }
 
 // ------------------------------------------------------------------------------------------- NMS
-size_t b200_nms_workspace_bytes(int64_t total_boxes, int32_t num_segments) {
-    (void)num_segments;
-    if (total_boxes < 0) return 0;
-    const size_t T = (size_t)(total_boxes > 0 ? total_boxes : 1);
-    return align_up(16 * T, 256) + align_up(16 * T, 256) + 4 * align_up(4 * T, 256) + 256;
+size_t b200_nms_workspace_bytes(int64_t total_boxes, int32_t num_segments, int32_t max_segment) {
+    if (total_boxes < 0 || num_segments < 0 || max_segment < 0) return 0;
+    const size_t ms = max_segment > 0 ? (size_t)max_segment : (size_t)total_boxes;
+    return nms_scratch_bytes((size_t)total_boxes, (size_t)num_segments, ms) + 256;
 }
 
 int b200_nms(const float* boxes, const float* scores, const int32_t* labels, const int32_t* seg_offsets,
-             int32_t num_segments, int64_t total_boxes, double iou_thr, int32_t mode, int64_t* keep,
-             int32_t* keep_count, int32_t* labels_out, void* workspace, size_t workspace_bytes,
+             int32_t num_segments, int64_t total_boxes, int32_t max_segment, double iou_thr, int32_t mode,
+             int64_t* keep, int32_t* keep_count, int32_t* labels_out, void* workspace, size_t workspace_bytes,
              void* stream) {
-    if (num_segments < 0 || total_boxes < 0) return B200_ERR_INVALID;
+    if (num_segments < 0 || total_boxes < 0 || max_segment < 0) return B200_ERR_INVALID;
     if (num_segments == 0) return B200_OK;
     if (!seg_offsets || !keep_count) return B200_ERR_INVALID;
     if (total_boxes > 0 && (!boxes || !scores || !keep || !aligned16(boxes))) return B200_ERR_INVALID;
     if (mode < B200_NMS_MAJORITY || mode > B200_NMS_TV_TRICK) return B200_ERR_INVALID;
     if (mode != B200_NMS_TV && !labels && total_boxes > 0) return B200_ERR_INVALID;
-    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u) ||
-        workspace_bytes < b200_nms_workspace_bytes(total_boxes, num_segments))
-        return B200_ERR_WORKSPACE;
-    const size_t T = (size_t)(total_boxes > 0 ? total_boxes : 1);
-    Carver c{reinterpret_cast<unsigned char*>(workspace), workspace_bytes};
+    const size_t ms = max_segment > 0 ? (size_t)max_segment : (size_t)total_boxes;
     NmsParams np{};
-    np.gkey = c.take<unsigned long long>(2 * T);
-    np.gbox = c.take<float4>(T);
-    np.garea = c.take<float>(T);
-    np.glabel = c.take<int>(T);
-    np.gsup = c.take<int>(T);
-    np.gcidx = c.take<int>(T);
-    if (!c.ok) return B200_ERR_WORKSPACE;
+    if (!nms_carve_scratch(&np, (size_t)total_boxes, (size_t)num_segments, ms, workspace, workspace_bytes))
+        return B200_ERR_WORKSPACE;
     np.boxes = boxes; np.scores = scores; np.labels = labels; np.seg_offsets = seg_offsets;
     np.keep = reinterpret_cast<long long*>(keep); np.keep_count = keep_count; np.labels_out = labels_out;
     np.mode = mode;
     np.thr_f = (float)iou_thr;
     np.thr_d = iou_thr;
-    np.fast_reject = mode == B200_NMS_MAJORITY ? (np.thr_f > 0.f) : (iou_thr >= 0.0);
-    np.smem_cap = kNmsSmemCap;
-    return launch_nms(np, num_segments, /*from_slab=*/false, static_cast<cudaStream_t>(stream));
+    np.from_slab = 0;
+    np.max_seg = (int)ms;
+    return launch_nms(np, num_segments, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------- IoU

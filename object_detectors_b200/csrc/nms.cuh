@@ -1,4 +1,4 @@
-// nms.cuh -- parameter block of the per-segment NMS kernel (see nms.cu).
+// nms.cuh -- parameter block of the segmented NMS kernels (see nms.cu).
 #pragma once
 #include "common.cuh"
 
@@ -20,12 +20,12 @@ struct NmsParams {
     const Cand* slab;        // [S, cap]
     const int* count;        // [S] true candidate counts
     int cap;
-    float4* cbox;            // [S, cap] canonical (ascending anchor) candidate arrays
-    float* cscore;
+    float4* cbox;            // [S, cap] canonical (ascending anchor) candidate arrays, written
+    float* cscore;           //          only by the canonicalise-only mode (mode < 0)
     int* clabel;
     int* canchor;
     float* det;              // [S, max_det, 6]
-    int* det_keep;           // [S, max_det]
+    int* det_keep;           // [S, max_det] or nullptr
     int* det_anchor;         // [S, max_det] or nullptr
     int* det_count;          // [S]
     int* cand_count_out;     // [S] or nullptr
@@ -35,20 +35,28 @@ struct NmsParams {
     int mode;                // B200_NMS_* ; < 0 = canonicalise the slab only
     float thr_f;             // MAJORITY: threshold rounded to fp32 (tensor-vs-scalar compare)
     double thr_d;            // TV modes: compared against (double)iou
-    int fast_reject;         // inter == 0 can never suppress (thr > 0 resp. >= 0)
-    int smem_cap;            // power of two; larger segments use the global scratch below
-    // ---- global scratch for oversized segments ------------------------------------------------
-    unsigned long long* gkey;  // [2*T]
-    float4* gbox;              // [T]
-    float* garea;
-    int* glabel;
-    int* gsup;
-    int* gcidx;
+    int from_slab;
+    int max_seg;             // upper bound of any segment length (host-known)
+    int max_words;           // cdiv(max_seg, 64): row stride of the dominator bitmask
+    // ---- global scratch ---------------------------------------------------------------------
+    unsigned long long* gkey;   // [2*T] sort keys when a sort does not fit in shared memory
+    int* gval;                  // [2*T] sort payload
+    unsigned long long* dom;    // [S * max_seg * max_words]: bit j of row i = "j precedes i in
+                                //  (score desc, index asc) order and suppresses it"
+    float* shift_unit;          // [S] coordinate-trick offset unit (max coordinate + 1)
+    int* tile_prefix;           // [S+1] exclusive prefix of 64x64 pair tiles per segment
+    int* work_counter;          // [1] tile queue cursor
+    int num_segments;
+    int* gsup;                  // [T] first suppressor | vote flag (MAJORITY)
+    int* gklist;                // [T] kept positions
+    int* gnewlab;               // [T] label of each kept box after the majority vote
 };
 
-static constexpr int kNmsSmemCap = 4096;
+// scratch bytes needed for T boxes in S segments of at most max_seg boxes each
+size_t nms_scratch_bytes(size_t total, size_t segments, size_t max_seg);
+// carve the scratch block (256 B aligned) into the pointers above; returns false if too small
+bool nms_carve_scratch(NmsParams* P, size_t total, size_t segments, size_t max_seg, void* base, size_t bytes);
 
-size_t nms_smem_bytes(int smem_cap);
-int launch_nms(const NmsParams& P, int num_segments, bool from_slab, cudaStream_t stream);
+int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream);
 
 }  // namespace b200

@@ -258,10 +258,17 @@ struct RpnWs {
     float4* box; float* score; int* label; int* aidx;
     int* seg_start; int* seg_count; int* img_start; int* img_count;
     long long* keep; int* keep_count;
-    unsigned long long* gkey; float4* gbox; float* garea; int* glabel; int* gsup; int* gcidx;
+    void* nms; size_t nms_bytes;
 };
-size_t rpn_carve(int batch, int ktot, int levels, void* base, size_t bytes, RpnWs* w) {
-    const size_t T = (size_t)batch * ktot;
+// NMS scratch must serve either strategy: (B*L segments of <= pre_k) or (B segments of <= L*pre_k)
+size_t rpn_nms_bytes(int batch, int levels, int pre_k) {
+    const size_t T = (size_t)batch * levels * pre_k;
+    const size_t a = nms_scratch_bytes(T, (size_t)batch * levels, (size_t)pre_k);
+    const size_t b = nms_scratch_bytes(T, (size_t)batch, (size_t)levels * pre_k);
+    return a > b ? a : b;
+}
+size_t rpn_carve(int batch, int levels, int pre_k, void* base, size_t bytes, RpnWs* w) {
+    const size_t T = (size_t)batch * levels * pre_k;   // worst case rows (>= B*Ktot)
     unsigned char* p = reinterpret_cast<unsigned char*>(base);
     size_t used = 0;
     auto take = [&](size_t b) { b = align_up(b, 256); void* r = base ? p + used : nullptr; used += b; return r; };
@@ -270,8 +277,8 @@ size_t rpn_carve(int batch, int ktot, int levels, void* base, size_t bytes, RpnW
     t.seg_start = (int*)take(4 * (size_t)batch * levels); t.seg_count = (int*)take(4 * (size_t)batch * levels);
     t.img_start = (int*)take(4 * (size_t)batch); t.img_count = (int*)take(4 * (size_t)batch);
     t.keep = (long long*)take(8 * T); t.keep_count = (int*)take(4 * (size_t)batch * levels);
-    t.gkey = (unsigned long long*)take(16 * T); t.gbox = (float4*)take(16 * T); t.garea = (float*)take(4 * T);
-    t.glabel = (int*)take(4 * T); t.gsup = (int*)take(4 * T); t.gcidx = (int*)take(4 * T);
+    t.nms_bytes = rpn_nms_bytes(batch, levels, pre_k);
+    t.nms = take(t.nms_bytes);
     if (base && used > bytes) return 0;
     if (w) *w = t;
     return used;
@@ -280,7 +287,7 @@ size_t rpn_carve(int batch, int ktot, int levels, void* base, size_t bytes, RpnW
 
 size_t rpn_workspace_bytes(int batch, int total, int num_levels, int pre_k) {
     (void)total;
-    return rpn_carve(batch, num_levels * pre_k, num_levels, nullptr, 0, nullptr) + 256;
+    return rpn_carve(batch, num_levels, pre_k, nullptr, 0, nullptr) + 256;
 }
 
 int launch_rpn_filter(const float* objectness, const float* deltas, const float* anchors, int batch,
@@ -306,8 +313,7 @@ int launch_rpn_filter(const float* objectness, const float* deltas, const float*
     P.Ktot = koff;
     if (koff > 16384 || kmax > 8192) return B200_ERR_INVALID;   // shared-memory sort capacity
     RpnWs w;
-    // the workspace is carved with the worst case num_levels*pre_k >= Ktot rows per image
-    if (!rpn_carve(batch, num_levels * pre_k, num_levels, workspace, workspace_bytes, &w)) return B200_ERR_WORKSPACE;
+    if (!rpn_carve(batch, num_levels, pre_k, workspace, workspace_bytes, &w)) return B200_ERR_WORKSPACE;
     P.box = w.box; P.score = w.score; P.label = w.label; P.aidx = w.aidx;
     P.seg_start = w.seg_start; P.seg_count = w.seg_count; P.img_start = w.img_start; P.img_count = w.img_count;
     P.keep = w.keep; P.keep_count = w.keep_count;
@@ -324,22 +330,25 @@ int launch_rpn_filter(const float* objectness, const float* deltas, const float*
     k_rpn_select<<<dim3(num_levels, batch), kSelThreads, sel_smem, stream>>>(P);
 
     NmsParams np{};
+    const size_t T = (size_t)batch * P.Ktot;
+    const bool trick = nms_mode == B200_NMS_TV_TRICK;
+    const int nseg = trick ? batch : batch * num_levels;
+    const int max_seg = trick ? P.Ktot : kmax;
+    if (!nms_carve_scratch(&np, T, (size_t)nseg, (size_t)max_seg, w.nms, w.nms_bytes)) return B200_ERR_WORKSPACE;
     np.boxes = reinterpret_cast<const float*>(w.box); np.scores = w.score; np.labels = w.label;
     np.keep = w.keep; np.labels_out = nullptr; np.keep_count = w.keep_count;
-    np.thr_f = (float)nms_thr; np.thr_d = nms_thr; np.fast_reject = nms_thr >= 0.0;
-    np.smem_cap = kNmsSmemCap;
-    np.gkey = w.gkey; np.gbox = w.gbox; np.garea = w.garea; np.glabel = w.glabel; np.gsup = w.gsup; np.gcidx = w.gcidx;
-    int rc;
-    if (nms_mode == B200_NMS_TV_TRICK) {
+    np.thr_f = (float)nms_thr; np.thr_d = nms_thr;
+    np.from_slab = 0;
+    np.max_seg = max_seg;
+    if (trick) {
         k_rpn_concat<<<batch, 1024, 0, stream>>>(P);
         np.seg_offsets = w.img_start; np.seg_counts = w.img_count; np.mode = B200_NMS_TV_TRICK;
-        rc = launch_nms(np, batch, false, stream);
         P.segs_per_img = 1;
     } else {
         np.seg_offsets = w.seg_start; np.seg_counts = w.seg_count; np.mode = B200_NMS_TV;  // one level per segment
-        rc = launch_nms(np, batch * num_levels, false, stream);
         P.segs_per_img = num_levels;
     }
+    const int rc = launch_nms(np, nseg, stream);
     if (rc != B200_OK) return rc;
     int fp = 1;
     while (fp < P.Ktot) fp <<= 1;

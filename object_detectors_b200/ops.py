@@ -17,6 +17,11 @@ Tensor = torch.Tensor
 
 _scratch: Dict[Tuple[int, str], Tensor] = {}
 
+# Candidate rows kept per image unless the caller says otherwise.  The reference has no cap; a slab
+# overflow is never silent (device status word -> RuntimeError) and the drop-ins retry with the
+# worst case N.  The NMS bitmask scratch grows with capacity^2/8 bytes per image.
+DEFAULT_CAPACITY = 4096
+
 
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -112,7 +117,7 @@ def yolo_decode_filter(heads, anchors, img_size, num_classes, idf=None, softmax=
     hs, lay, arr, n = _heads_args(heads, anchors, img_size, num_classes, softmax)
     dev = hs[0].device
     idf = _idf_arg(idf, num_classes, dev)
-    cap = int(capacity or n)
+    cap = int(capacity or min(n, DEFAULT_CAPACITY))
     b = lay.batch
     box = torch.empty((b, cap, 4), dtype=torch.float32, device=dev)
     score = torch.empty((b, cap), dtype=torch.float32, device=dev)
@@ -142,7 +147,7 @@ class YoloPostprocess:
         na = len(anchors[0])
         self.head_shapes = [(batch, na * (5 + num_classes), g, g) for g in grids]
         self.n = sum(g * g * na for g in grids)
-        self.cap = int(capacity or self.n)
+        self.cap = int(capacity or min(self.n, DEFAULT_CAPACITY))
         self.max_det = int(max_det or self.cap)
         self.conf_thr = float(np.float32(conf_thr))
         self.nms_thr = float(nms_thr)   # double: MAJORITY rounds to fp32 in C, TV modes compare in double
@@ -202,7 +207,7 @@ def yolo_postprocess_host(heads_host: Sequence[Tensor], anchors, img_size, num_c
             raise RuntimeError("yolo_postprocess_host expects contiguous fp32 HOST tensors")
     lay = make_layout(grids, b, anchors, img_size, num_classes, softmax)
     n = sum(g * g * na for g in grids)
-    cap = int(capacity or n)
+    cap = int(capacity or min(n, DEFAULT_CAPACITY))
     if out is None:
         out = (torch.empty((b, max_det, 6), dtype=torch.float32).pin_memory(),
                torch.empty((b, max_det), dtype=torch.int32).pin_memory(),
@@ -223,8 +228,9 @@ def yolo_postprocess_host(heads_host: Sequence[Tensor], anchors, img_size, num_c
 
 # ---------------------------------------------------------------------------------------- NMS
 def nms_segments(boxes: Tensor, scores: Tensor, labels: Optional[Tensor], seg_offsets: Tensor,
-                 iou_thr: float, mode: int):
-    """Batched NMS.  -> (keep int64 [T], keep_count int32 [S], labels_out int32 [T])."""
+                 iou_thr: float, mode: int, max_segment: int = 0):
+    """Batched NMS.  -> (keep int64 [T], keep_count int32 [S], labels_out int32 [T]).
+    ``max_segment``: host-known bound of the largest segment (0 = T); it sizes the bitmask."""
     lib = _lib.load()
     boxes = _need_cuda(boxes, "boxes", torch.float32)
     scores = _need_cuda(scores, "scores", torch.float32)
@@ -237,13 +243,13 @@ def nms_segments(boxes: Tensor, scores: Tensor, labels: Optional[Tensor], seg_of
     keep = torch.empty((max(t, 1),), dtype=torch.int64, device=dev)
     keep_count = torch.zeros((max(s, 1),), dtype=torch.int32, device=dev)
     labels_out = torch.empty((max(t, 1),), dtype=torch.int32, device=dev) if mode == NMS_MAJORITY else None
-    nbytes = lib.b200_nms_workspace_bytes(t, s)
+    nbytes = lib.b200_nms_workspace_bytes(t, s, int(max_segment))
     ws = workspace(nbytes, dev, "nms")
     if boxes.data_ptr() % 16:
         boxes = boxes.clone()
-    _lib.check(lib.b200_nms(_ptr(boxes), _ptr(scores), _ptr(labels), _ptr(seg_offsets), s, t, float(iou_thr),
-                            int(mode), _ptr(keep), _ptr(keep_count), _ptr(labels_out), _ptr(ws), ws.numel(),
-                            _stream()), "b200_nms")
+    _lib.check(lib.b200_nms(_ptr(boxes), _ptr(scores), _ptr(labels), _ptr(seg_offsets), s, t, int(max_segment),
+                            float(iou_thr), int(mode), _ptr(keep), _ptr(keep_count), _ptr(labels_out), _ptr(ws),
+                            ws.numel(), _stream()), "b200_nms")
     return keep, keep_count, labels_out
 
 

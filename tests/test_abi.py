@@ -53,7 +53,7 @@ def test_layout_struct_matches_header(lib):
 
 
 def test_invalid_arguments_are_rejected_without_touching_the_gpu(lib):
-    assert lib.b200_nms(None, None, None, None, -1, 0, 0.5, 1, None, None, None, None, 0, None) == -1
+    assert lib.b200_nms(None, None, None, None, -1, 0, 0, 0.5, 1, None, None, None, None, 0, None) == -1
     assert lib.b200_box_iou(None, 3, None, 3, 9, 0, None, None) == -1
     assert lib.b200_yolo_workspace_bytes(None, 16) == 0
 
