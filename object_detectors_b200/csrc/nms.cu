@@ -2,22 +2,25 @@
 // A segment is one image (YOLO post-process, torchvision nms / coordinate-trick batched_nms) or
 // one image x level (RPN).
 //
-// Greedy NMS in (score desc, index asc) order has a unique characterisation that needs no serial
-// walk: box i is kept  <=>  no KEPT box that precedes i suppresses it.  So
+// Greedy NMS in (score desc, index asc) order has a characterisation that needs no serial walk:
+// box i is kept  <=>  no KEPT box that precedes i suppresses it.  Pipeline per batch:
 //
-//  k_nms_pairs   (all SMs) builds the "dominator" bitmask on the boxes in whatever order they
-//                arrive: bit j of row i is set iff j precedes i and suppresses it.  64x64 tiles of
-//                unordered pairs, each pair evaluated once with the roles (picked S / remaining T)
-//                chosen by comparing (score, index) keys, the IoU arithmetic reproduced operation
-//                by operation per flavour (appendix A.3).  The IEEE division is only executed when
-//                inter is within 1e-6 (relative) of thr*union; outside that band the comparison of
-//                the rounded quotient with the threshold is already decided.
-//  k_nms_resolve (one CTA per segment) iterates the fixed point in parallel rounds over bitsets in
-//                shared memory (a box becomes KEPT when all its dominators are removed, REMOVED as
-//                soon as one of them is kept; the number of rounds is the depth of the suppression
-//                chains, a handful in practice), then sorts only the KEPT boxes by score, finds
-//                each removed box's first suppressor, applies the majority relabel
-//                (helper.py:368-375) and emits.
+//  k_nms_plan    (one CTA per segment) counting-sorts the boxes into (size class, y band) bins so
+//                that 64 consecutive positions are spatially coherent, summarises every 64-tile
+//                (union box, area range), zeroes the bitmask rows and emits only those tile pairs
+//                that can contain a suppressing pair (union boxes intersect and the area ranges
+//                allow IoU >= thr) into a global work list.
+//  k_nms_pairs   (all SMs, persistent CTAs popping the work list) builds the "dominator" bitmask:
+//                bit q of row p is set iff q precedes p and suppresses it.  Each unordered pair is
+//                evaluated once, roles (picked S / remaining T) chosen by comparing (score, index)
+//                keys, IoU arithmetic reproduced operation by operation per flavour (appendix
+//                A.3).  The IEEE division is only executed when inter is within 1e-6 (relative) of
+//                thr*union; outside that band the comparison of the rounded quotient is decided.
+//  k_nms_resolve (one CTA per segment) brings boxes and mask rows into shared memory and iterates
+//                the fixed point in parallel rounds over bitsets (KEPT when every dominator is
+//                removed, REMOVED as soon as one is kept; rounds = depth of the suppression chains),
+//                sorts only the KEPT boxes by score, finds each removed box's first suppressor,
+//                applies the majority relabel (helper.py:368-375) and emits.
 //  k_nms_canon   (YOLO stage API only) sorts the unordered candidate slab by flat anchor index and
 //                writes the reference's ascending-anchor candidate list (test_one_epoch.py:27-28).
 #include "decode.cuh"
@@ -27,12 +30,16 @@ namespace b200 {
 
 static constexpr int kCanonThreads = 512;
 static constexpr int kSortSmemKeys = 4096;
+static constexpr int kPlanThreads = 512;
+static constexpr int kPlanTiles = 512;          // tile summaries kept in shared memory (n <= 32768)
+static constexpr int kBins = 128;               // 8 size classes x 16 y bands
 static constexpr int kPairThreads = 256;
 static constexpr int kResolveThreads = 512;
 static constexpr int kResolveWarps = kResolveThreads / 32;
-static constexpr int kKeptSmem = 2048;          // kept boxes sorted in shared memory up to this many
+static constexpr int kKeptSmem = 2048;          // slow path: kept boxes sorted in shared memory
 static constexpr int kVoteFlag = 1 << 30;
 static constexpr int kVoteListCap = 128;
+static constexpr size_t kResolveSmem = 200 * 1024;
 
 __device__ __forceinline__ int next_pow2(int n) {
     int p = 1;
@@ -64,8 +71,9 @@ struct Item {
     int label;
 };
 
+// by index i inside the segment
 template <bool SLAB>
-__device__ __forceinline__ Item load_item(const NmsParams& P, long long off, int i, float unit) {
+__device__ __forceinline__ Item load_raw(const NmsParams& P, long long off, int i, float unit) {
     Item it;
     float score;
     unsigned tie;
@@ -91,12 +99,16 @@ __device__ __forceinline__ Item load_item(const NmsParams& P, long long off, int
     it.key = ((unsigned long long)(~orderable(score)) << 32) | tie;
     return it;
 }
+// by binned position p
+template <bool SLAB>
+__device__ __forceinline__ Item load_item(const NmsParams& P, long long off, int p, float unit) {
+    return load_raw<SLAB>(P, off, P.gperm[off + p], unit);
+}
 
-// S = the box that precedes (picked), T = the later one (remaining).  exact: always divide.
-template <int MODE, bool EXACT>
-__device__ __forceinline__ bool suppresses(const NmsParams& P, const float4& bs, float as, int ls,
-                                           const float4& bt, float at, int lt, bool* vote) {
-    if (MODE == B200_NMS_TV_CLASS && ls != lt) return false;
+// exact test, S = the box that precedes (picked), T = the later one (remaining)
+template <int MODE>
+__device__ __forceinline__ bool suppresses_exact(const NmsParams& P, const float4& bs, float as, const float4& bt,
+                                                 float at, bool* vote) {
     float w = __fsub_rn(fminf(bs.z, bt.z), fmaxf(bs.x, bt.x));
     float h = __fsub_rn(fminf(bs.w, bt.w), fmaxf(bs.y, bt.y));
     w = fmaxf(w, 0.f);
@@ -105,21 +117,42 @@ __device__ __forceinline__ bool suppresses(const NmsParams& P, const float4& bs,
     // helper.py:361-366  union = (area_T - inter) + area_S ;  torchvision: (area_i + area_j) - inter
     const float den = MODE == B200_NMS_MAJORITY ? __fadd_rn(__fsub_rn(at, inter), as)
                                                 : __fsub_rn(__fadd_rn(as, at), inter);
-    if (!EXACT) {
-        // fl(inter/den) differs from inter/den by < 2^-24 relative: outside a 1e-6 band around
-        // thr*den the threshold comparison is decided without dividing.
-        const float t = __fmul_rn(den, P.thr_f);
-        if (den > 1e-30f) {
-            if (inter > __fmul_rn(t, 1.000001f)) return true;
-            if (inter < __fmul_rn(t, 0.999999f)) return false;
-        }
-    }
     const float iou = __fdiv_rn(inter, den);
     if (MODE == B200_NMS_MAJORITY) {
         if (vote) *vote = iou > P.thr_f;                 // helper.py:369
         return !(iou < P.thr_f);                         // helper.py:368 (NaN and == thr are removed)
     }
     return (double)iou > P.thr_d;                        // torchvision: double threshold
+}
+
+// Unordered pair test.  The intersection is symmetric; only the MAJORITY union
+// (area_T - inter) + area_S depends on which box comes first.
+template <int MODE>
+__device__ __forceinline__ bool pair_hit(const NmsParams& P, const float4& bi, float ai, int li,
+                                         const float4& bj, float aj, int lj, bool i_first) {
+    if (MODE == B200_NMS_TV_CLASS && li != lj) return false;
+    float w = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x));
+    float h = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
+    w = fmaxf(w, 0.f);
+    h = fmaxf(h, 0.f);
+    const float inter = __fmul_rn(w, h);
+    float den;
+    if (MODE == B200_NMS_MAJORITY) {
+        const float as = i_first ? ai : aj, at = i_first ? aj : ai;
+        den = __fadd_rn(__fsub_rn(at, inter), as);
+    } else {
+        den = __fsub_rn(__fadd_rn(ai, aj), inter);
+    }
+    // fl(inter/den) differs from inter/den by < 2^-24 relative: outside a 1e-6 band around thr*den
+    // the threshold comparison is decided without dividing.
+    const float t = __fmul_rn(den, P.thr_f);
+    if (den > 1e-30f) {
+        if (inter > __fmul_rn(t, 1.000001f)) return true;
+        if (inter < __fmul_rn(t, 0.999999f)) return false;
+    }
+    const float iou = __fdiv_rn(inter, den);
+    if (MODE == B200_NMS_MAJORITY) return !(iou < P.thr_f);
+    return (double)iou > P.thr_d;
 }
 
 // ascending bitonic sort of key[0..P) (+ optional payload), P a power of two, whole CTA
@@ -139,6 +172,26 @@ __device__ void bitonic_sort(unsigned long long* key, int* val, int P) {
             __syncthreads();
         }
     }
+}
+
+// exclusive rank of a flag over the CTA (NW warps); `running` accumulates the total
+template <int NW>
+__device__ __forceinline__ int block_rank(bool flag, int* scratch, int& running) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(kFullMask, flag);
+    if (lane == 0) scratch[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const int c = scratch[w];
+        if (w < warp) before += c;
+        total += c;
+    }
+    const int rank = running + before + __popc(bal & ((1u << lane) - 1u));
+    running += total;
+    __syncthreads();
+    return rank;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -169,135 +222,213 @@ k_nms_canon(const __grid_constant__ NmsParams P) {
     }
 }
 
-// coordinate trick: per-segment max coordinate + 1
+// ------------------------------------------------------------------------------------------
+// plan: spatial binning, tile summaries, pruned work list
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, red[w]);
+    return r;
+}
+
+__device__ __forceinline__ int box_bin(const Item& it, float ymin, float yscale) {
+    const bool ok = it.area > 0.f && it.area < 3.0e38f;
+    if (!ok) return 0;
+    const int e = ((__float_as_int(it.area) >> 23) & 0xff) - 127;       // floor(log2(area))
+    const int cls = min(max((e - 6) >> 1, 0), 7);                       // 2 octaves of area per class
+    const float cy = 0.5f * (it.b.y + it.b.w);
+    int yb = (int)((cy - ymin) * yscale);
+    yb = min(max(yb, 0), 15);
+    return cls * 16 + yb;
+}
+
 template <bool SLAB>
-__global__ void __launch_bounds__(256)
-k_nms_trick_prep(const __grid_constant__ NmsParams P) {
-    __shared__ float red[8];
-    const int seg = blockIdx.x, tid = threadIdx.x;
+__global__ void __launch_bounds__(kPlanThreads)
+k_nms_plan(const __grid_constant__ NmsParams P) {
+    __shared__ float red[kPlanThreads / 32];
+    __shared__ int hist[kBins];
+    __shared__ float4 tbox[kPlanTiles];
+    __shared__ float2 tarea[kPlanTiles];
+    __shared__ unsigned char tbad[kPlanTiles];
+    __shared__ int s_scan[kPlanThreads / 32];
+    __shared__ int s_base;
+    const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     long long off;
     int n, n_true;
     segment_range(P, seg, off, n, n_true);
-    float mx = -INFINITY;
-    for (int i = tid; i < n; i += 256) {
-        const float4 b = SLAB ? reinterpret_cast<const float4*>(P.slab + off + i)[0]
-                              : reinterpret_cast<const float4*>(P.boxes)[off + i];
-        mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, o));
-    if ((tid & 31) == 0) red[tid >> 5] = mx;
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
-        P.shift_unit[seg] = __fadd_rn(mx, 1.0f);
-    }
-}
+    if (n == 0) return;
 
-// ------------------------------------------------------------------------------------------
-// dominator bitmask: 64x64 tiles of unordered pairs, dynamically scheduled over all SMs
-// ------------------------------------------------------------------------------------------
-// Unordered pair test.  The intersection is symmetric; only the MAJORITY union
-// (area_T - inter) + area_S depends on which box comes first.
-template <int MODE>
-__device__ __forceinline__ bool pair_hit(const NmsParams& P, const float4& bi, float ai, int li,
-                                         const float4& bj, float aj, int lj, bool i_first) {
-    if (MODE == B200_NMS_TV_CLASS && li != lj) return false;
-    float w = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x));
-    float h = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
-    w = fmaxf(w, 0.f);
-    h = fmaxf(h, 0.f);
-    const float inter = __fmul_rn(w, h);
-    float den;
-    if (MODE == B200_NMS_MAJORITY) {
-        const float as = i_first ? ai : aj, at = i_first ? aj : ai;
-        den = __fadd_rn(__fsub_rn(at, inter), as);
-    } else {
-        den = __fsub_rn(__fadd_rn(ai, aj), inter);
-    }
-    const float t = __fmul_rn(den, P.thr_f);
-    if (den > 1e-30f) {
-        if (inter > __fmul_rn(t, 1.000001f)) return true;
-        if (inter < __fmul_rn(t, 0.999999f)) return false;
-    }
-    const float iou = __fdiv_rn(inter, den);
-    if (MODE == B200_NMS_MAJORITY) return !(iou < P.thr_f);
-    return (double)iou > P.thr_d;
-}
-
-// one CTA (1024 threads): tiles per segment -> exclusive prefix, and the work counter reset
-__global__ void __launch_bounds__(1024)
-k_nms_plan(const __grid_constant__ NmsParams P) {
-    __shared__ int warp_sum[32];
-    __shared__ int carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { carry = 0; *P.work_counter = 0; }
-    __syncthreads();
-    for (int s0 = 0; s0 < P.num_segments; s0 += 1024) {
-        const int s = s0 + tid;
-        int tiles = 0;
-        if (s < P.num_segments) {
-            long long off; int n, n_true;
-            segment_range(P, s, off, n, n_true);
-            const int nt = cdiv(n, 64);
-            tiles = nt * (nt + 1) / 2;
+    // ---- coordinate-trick unit, y range of the box centres ------------------------------------
+    float unit = 0.f;
+    if (P.mode == B200_NMS_TV_TRICK) {
+        float mx = -INFINITY;
+        for (int i = tid; i < n; i += kPlanThreads) {
+            const float4 b = SLAB ? reinterpret_cast<const float4*>(P.slab + off + i)[0]
+                                  : reinterpret_cast<const float4*>(P.boxes)[off + i];
+            mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
         }
-        int incl = tiles;
+        unit = __fadd_rn(block_reduce_max(mx, red), 1.0f);
+        if (tid == 0) P.shift_unit[seg] = unit;
+    }
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = tid; i < n; i += kPlanThreads) {
+        const Item it = load_raw<SLAB>(P, off, i, unit);
+        const float cy = 0.5f * (it.b.y + it.b.w);
+        if (cy == cy) { lo = fminf(lo, cy); hi = fmaxf(hi, cy); }
+    }
+    const float ymax = block_reduce_max(hi, red);
+    const float ymin = -block_reduce_max(-lo, red);
+    const float range = ymax - ymin;
+    const float yscale = range > 0.f && range < 3.0e38f ? 16.0f / range : 0.f;
+
+    // ---- counting sort into (size class, y band) bins -> gperm ----------------------------------
+    for (int b = tid; b < kBins; b += kPlanThreads) hist[b] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kPlanThreads) atomicAdd(&hist[box_bin(load_raw<SLAB>(P, off, i, unit), ymin, yscale)], 1);
+    __syncthreads();
+    if (warp == 0) {                      // exclusive scan of 128 bins, 4 per lane
+        int v[4], sum = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFullMask, incl, o); if (lane >= o) incl += v; }
-        if (lane == 31) warp_sum[warp] = incl;
+        for (int k = 0; k < 4; ++k) { v[k] = hist[lane * 4 + k]; sum += v[k]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(kFullMask, incl, o); if (lane >= o) incl += u; }
+        int run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { hist[lane * 4 + k] = run; run += v[k]; }
+    }
+    __syncthreads();
+    int* perm = P.gperm + off;
+    for (int i = tid; i < n; i += kPlanThreads)
+        perm[atomicAdd(&hist[box_bin(load_raw<SLAB>(P, off, i, unit), ymin, yscale)], 1)] = i;
+    __syncthreads();
+
+    // ---- tile summaries + zeroed bitmask rows -----------------------------------------------------
+    const int nt = cdiv(n, 64);
+    const bool summarise = nt <= kPlanTiles && P.thr_f > 0.f;
+    if (summarise) {
+        for (int t = warp; t < nt; t += kPlanThreads / 32) {
+            float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY, amin = INFINITY, amax = -INFINITY;
+            bool bad = false;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int p = t * 64 + h * 32 + lane;
+                if (p < n) {
+                    const Item it = load_raw<SLAB>(P, off, perm[p], unit);
+                    x1 = fminf(x1, it.b.x); y1 = fminf(y1, it.b.y); x2 = fmaxf(x2, it.b.z); y2 = fmaxf(y2, it.b.w);
+                    amin = fminf(amin, it.area); amax = fmaxf(amax, it.area);
+                    // degenerate boxes can yield NaN IoU (removed by the majority rule): never prune them
+                    bad |= !(it.area > 0.f) || !(it.area < 3.0e38f) || !(it.b.x == it.b.x) || !(it.b.y == it.b.y) ||
+                           !(it.b.z == it.b.z) || !(it.b.w == it.b.w);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                x1 = fminf(x1, __shfl_xor_sync(kFullMask, x1, o)); y1 = fminf(y1, __shfl_xor_sync(kFullMask, y1, o));
+                x2 = fmaxf(x2, __shfl_xor_sync(kFullMask, x2, o)); y2 = fmaxf(y2, __shfl_xor_sync(kFullMask, y2, o));
+                amin = fminf(amin, __shfl_xor_sync(kFullMask, amin, o)); amax = fmaxf(amax, __shfl_xor_sync(kFullMask, amax, o));
+            }
+            bad = __any_sync(kFullMask, bad);
+            if (lane == 0) { tbox[t] = make_float4(x1, y1, x2, y2); tarea[t] = make_float2(amin, amax); tbad[t] = bad ? 1 : 0; }
+        }
+    }
+    // rows of up to 64 words keep a per-row "non-zero word" mask and are never read where it is clear;
+    // longer rows (slow resolve path) are cleared in full
+    if (nt <= 64) {
+        for (int p = tid; p < n; p += kPlanThreads) P.nzmask[off + p] = 0ull;
+    } else {
+        unsigned long long* dom = P.dom + (size_t)seg * (size_t)P.max_seg * (size_t)P.max_words;
+        for (long long e = tid; e < (long long)n * nt; e += kPlanThreads) {
+            const long long p = e / nt;
+            dom[(size_t)p * P.max_words + (size_t)(e - p * nt)] = 0ull;
+        }
+    }
+    __syncthreads();
+
+    // ---- work list: diagonal tiles always, off-diagonal tiles unless provably empty --------------
+    const int total = nt * (nt + 1) / 2;
+    const float slack = 0.99f * P.thr_f;
+    for (int t0 = 0; t0 < total; t0 += kPlanThreads) {
+        const int t = t0 + tid;
+        bool keep = false;
+        int rt = 0, ct = 0;
+        if (t < total) {
+            // row-major upper triangle: prefix(r) = r*nt - r*(r-1)/2
+            const float fb = (float)(2 * nt + 1);
+            rt = (int)((fb - sqrtf(fmaxf(fb * fb - 8.0f * (float)t, 0.f))) * 0.5f);
+            rt = min(max(rt, 0), nt - 1);
+            while (rt > 0 && rt * nt - rt * (rt - 1) / 2 > t) --rt;
+            while ((rt + 1) * nt - (rt + 1) * rt / 2 <= t) ++rt;
+            ct = rt + (t - (rt * nt - rt * (rt - 1) / 2));
+            keep = true;
+            if (summarise && rt != ct && !tbad[rt] && !tbad[ct]) {
+                const float4 a = tbox[rt], b = tbox[ct];
+                const float2 ra = tarea[rt], rb = tarea[ct];
+                const bool disjoint = a.z <= b.x || b.z <= a.x || a.w <= b.y || b.w <= a.y;   // inter == 0
+                const bool mismatch = ra.y < slack * rb.x || rb.y < slack * ra.x;             // IoU <= min/max area
+                keep = !(disjoint || mismatch);
+            }
+        }
+        int running = 0;
+        const int k = block_rank<kPlanThreads / 32>(keep, s_scan, running);
+        if (tid == 0) s_base = running > 0 ? atomicAdd(&P.work_count[0], running) : 0;
         __syncthreads();
-        int before = carry;
-        for (int w = 0; w < warp; ++w) before += warp_sum[w];
-        if (s < P.num_segments) P.tile_prefix[s] = before + incl - tiles;
-        __syncthreads();
-        if (tid == 1023) carry = before + incl;
+        if (keep) P.work[s_base + k] = make_int2(seg, (rt << 16) | ct);
         __syncthreads();
     }
-    if (tid == 0) P.tile_prefix[P.num_segments] = carry;
 }
+
+// ------------------------------------------------------------------------------------------
+// dominator bitmask: 64x64 tiles of unordered pairs
+// ------------------------------------------------------------------------------------------
+struct PairSmem {
+    float4 rb[64], cb[64];
+    float ra[64], ca[64];
+    unsigned long long rk[64], ck[64];
+    unsigned trans[128];      // transposed hits, 32-bit halves (native shared-memory atomics)
+    int rl[64], cl[64];
+};
 
 template <int MODE, bool SLAB>
-__device__ __forceinline__ void pair_tile(const NmsParams& P, int seg, int local, float4* rb, float4* cb, float* ra,
-                                          float* ca, unsigned long long* rk, unsigned long long* ck,
-                                          unsigned long long* trans, int* rl, int* cl) {
+__device__ __forceinline__ void pair_tile(const NmsParams& P, int seg, int rt, int ct, PairSmem& S) {
     long long off;
     int n, n_true;
     segment_range(P, seg, off, n, n_true);
     const float unit = P.mode == B200_NMS_TV_TRICK ? P.shift_unit[seg] : 0.f;
-    const int nt = cdiv(n, 64);
-    int rt = 0, rem = local;
-    while (rem >= nt - rt) { rem -= nt - rt; ++rt; }
-    const int ct = rt + rem;
     const int tid = threadIdx.x;
     const int r = tid >> 2, cg = tid & 3;
     unsigned long long* dom = P.dom + (size_t)seg * (size_t)P.max_seg * (size_t)P.max_words;
     if (tid < 64) {
         const int i = rt * 64 + tid;
-        if (i < n) { const Item it = load_item<SLAB>(P, off, i, unit); rb[tid] = it.b; ra[tid] = it.area; rk[tid] = it.key; rl[tid] = it.label; }
+        if (i < n) { const Item it = load_item<SLAB>(P, off, i, unit); S.rb[tid] = it.b; S.ra[tid] = it.area; S.rk[tid] = it.key; S.rl[tid] = it.label; }
     } else if (tid < 128) {
         const int j = ct * 64 + tid - 64;
-        if (j < n) { const Item it = load_item<SLAB>(P, off, j, unit); cb[tid - 64] = it.b; ca[tid - 64] = it.area; ck[tid - 64] = it.key; cl[tid - 64] = it.label; }
-    } else if (tid < 192) {
-        trans[tid - 128] = 0ull;
+        if (j < n) { const Item it = load_item<SLAB>(P, off, j, unit); S.cb[tid - 64] = it.b; S.ca[tid - 64] = it.area; S.ck[tid - 64] = it.key; S.cl[tid - 64] = it.label; }
+    } else {
+        S.trans[tid - 128] = 0u;
     }
     __syncthreads();
     const int i = rt * 64 + r;
     unsigned long long bits = 0ull;
     if (i < n) {
-        const float4 bi = rb[r];
-        const float ai = ra[r];
-        const unsigned long long ki = rk[r];
-        const int li = rl[r];
+        const float4 bi = S.rb[r];
+        const float ai = S.ra[r];
+        const unsigned long long ki = S.rk[r];
+        const int li = S.rl[r];
 #pragma unroll 4
         for (int c = 0; c < 16; ++c) {
             const int cc = c * 4 + cg;            // the 4 threads of a row read adjacent columns
             const int j = ct * 64 + cc;
             if (j < n && (rt != ct || cc > r)) {
-                const bool i_first = ki < ck[cc];
-                if (pair_hit<MODE>(P, bi, ai, li, cb[cc], ca[cc], cl[cc], i_first)) {
-                    if (i_first) atomicOr(&trans[cc], 1ull << r);   // i dominates j
-                    else bits |= 1ull << cc;                        // j dominates i
+                const bool i_first = ki < S.ck[cc];
+                if (pair_hit<MODE>(P, bi, ai, li, S.cb[cc], S.ca[cc], S.cl[cc], i_first)) {
+                    if (i_first) atomicOr(&S.trans[2 * cc + (r >> 5)], 1u << (r & 31));   // i dominates j
+                    else bits |= 1ull << cc;                                              // j dominates i
                 }
             }
         }
@@ -305,119 +436,368 @@ __device__ __forceinline__ void pair_tile(const NmsParams& P, int seg, int local
     bits |= __shfl_xor_sync(kFullMask, bits, 1);
     bits |= __shfl_xor_sync(kFullMask, bits, 2);
     __syncthreads();
+    const bool track = n <= 64 * 64;          // rows of <= 64 words: maintain the non-zero word mask
+    unsigned long long* nzm = P.nzmask + off;
     if (rt == ct) {
-        if (cg == 0 && i < n) dom[(size_t)i * P.max_words + ct] = bits | trans[r];
+        if (cg == 0 && i < n) {
+            const unsigned long long word = bits | ((unsigned long long)S.trans[2 * r + 1] << 32) | S.trans[2 * r];
+            if (word) {
+                dom[(size_t)i * P.max_words + ct] = word;
+                if (track) atomicOr(&nzm[i], 1ull << ct);
+            }
+        }
     } else {
-        if (cg == 0 && i < n) dom[(size_t)i * P.max_words + ct] = bits;
-        if (tid < 64 && ct * 64 + tid < n) dom[(size_t)(ct * 64 + tid) * P.max_words + rt] = trans[tid];
+        if (cg == 0 && i < n && bits) {
+            dom[(size_t)i * P.max_words + ct] = bits;
+            if (track) atomicOr(&nzm[i], 1ull << ct);
+        }
+        if (tid < 64 && ct * 64 + tid < n) {
+            const unsigned long long word = ((unsigned long long)S.trans[2 * tid + 1] << 32) | S.trans[2 * tid];
+            if (word) {
+                dom[(size_t)(ct * 64 + tid) * P.max_words + rt] = word;
+                if (track) atomicOr(&nzm[ct * 64 + tid], 1ull << rt);
+            }
+        }
     }
 }
 
 template <bool SLAB>
 __global__ void __launch_bounds__(kPairThreads)
 k_nms_pairs(const __grid_constant__ NmsParams P) {
-    __shared__ float4 rb[64], cb[64];
-    __shared__ float ra[64], ca[64];
-    __shared__ unsigned long long rk[64], ck[64], trans[64];
-    __shared__ int rl[64], cl[64];
+    __shared__ PairSmem S;
     __shared__ int s_work;
-    const int total = P.tile_prefix[P.num_segments];
+    const int total = P.work_count[0];
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_work = atomicAdd(P.work_counter, 1);
+        if (threadIdx.x == 0) s_work = atomicAdd(&P.work_count[1], 1);
         __syncthreads();
         const int t = s_work;
         if (t >= total) break;
-        int lo = 0, hi = P.num_segments - 1;          // last segment with tile_prefix[seg] <= t
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (P.tile_prefix[mid] <= t) lo = mid; else hi = mid - 1;
-        }
-        const int local = t - P.tile_prefix[lo];
+        const int2 w = P.work[t];
+        const int rt = w.y >> 16, ct = w.y & 0xffff;
         switch (P.mode) {
-            case B200_NMS_MAJORITY: pair_tile<B200_NMS_MAJORITY, SLAB>(P, lo, local, rb, cb, ra, ca, rk, ck, trans, rl, cl); break;
-            case B200_NMS_TV_CLASS: pair_tile<B200_NMS_TV_CLASS, SLAB>(P, lo, local, rb, cb, ra, ca, rk, ck, trans, rl, cl); break;
-            default:                pair_tile<B200_NMS_TV, SLAB>(P, lo, local, rb, cb, ra, ca, rk, ck, trans, rl, cl); break;
+            case B200_NMS_MAJORITY: pair_tile<B200_NMS_MAJORITY, SLAB>(P, w.x, rt, ct, S); break;
+            case B200_NMS_TV_CLASS: pair_tile<B200_NMS_TV_CLASS, SLAB>(P, w.x, rt, ct, S); break;
+            default:                pair_tile<B200_NMS_TV, SLAB>(P, w.x, rt, ct, S); break;   // TV, TV_TRICK
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// resolve + order the kept boxes + vote + emit
+// resolve, fast path: the segment lives in shared memory
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int block_rank(bool flag, int* scratch, int& running) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned bal = __ballot_sync(kFullMask, flag);
-    if (lane == 0) scratch[warp] = __popc(bal);
-    __syncthreads();
-    int before = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kResolveWarps; ++w) {
-        const int c = scratch[w];
-        if (w < warp) before += c;
-        total += c;
-    }
-    const int rank = running + before + __popc(bal & ((1u << lane) - 1u));
-    running += total;
-    __syncthreads();
-    return rank;
+struct FastSmem {
+    float4* box;                 // [n]
+    float* area;                 // [n]
+    unsigned long long* key;     // [n]
+    unsigned long long* nz;      // [n]   which words of the box's dominator row are non-zero
+    int* lab;                    // [n]
+    int* sup;                    // [n]   first suppressor | vote flag
+    int* voff;                   // [n+1] voter list offsets
+    int* vlab;                   // [n]   voter labels
+    int* newlab;                 // [n]
+    int* klist;                  // [n]
+    unsigned long long* Kset;    // [nw]  kept bitset
+    unsigned long long* Rset;    // [nw]  removed bitset
+    int* scan;                   // [32]
+    unsigned char* u;            // union: compact mask rows [4n] | sort keys + payload [P2]
+};
+static constexpr int kCompactWords = 4;   // non-zero row words cached per box (spatial binning keeps rows sparse)
+__host__ __device__ inline size_t fast_fixed_bytes(int n, int nw) {
+    return 16 * 14 + 60 * (size_t)n + 4 + 16 * (size_t)nw + 128;
 }
+__device__ __forceinline__ void fast_carve(FastSmem& f, unsigned char* base, int n, int nw) {
+    size_t o = 0;
+    auto take = [&](size_t bytes) { unsigned char* r = base + o; o += align_up(bytes, 16); return r; };
+    f.box = reinterpret_cast<float4*>(take(16 * (size_t)n));
+    f.area = reinterpret_cast<float*>(take(4 * (size_t)n));
+    f.key = reinterpret_cast<unsigned long long*>(take(8 * (size_t)n));
+    f.nz = reinterpret_cast<unsigned long long*>(take(8 * (size_t)n));
+    f.lab = reinterpret_cast<int*>(take(4 * (size_t)n));
+    f.sup = reinterpret_cast<int*>(take(4 * (size_t)n));
+    f.voff = reinterpret_cast<int*>(take(4 * ((size_t)n + 1)));
+    f.vlab = reinterpret_cast<int*>(take(4 * (size_t)n));
+    f.newlab = reinterpret_cast<int*>(take(4 * (size_t)n));
+    f.klist = reinterpret_cast<int*>(take(4 * (size_t)n));
+    f.Kset = reinterpret_cast<unsigned long long*>(take(8 * (size_t)nw));
+    f.Rset = reinterpret_cast<unsigned long long*>(take(8 * (size_t)nw));
+    f.scan = reinterpret_cast<int*>(take(4 * 32));
+    f.u = base + o;
+}
+
+// in-place exclusive scan of a[0..n) (whole CTA), returns the total
+__device__ __forceinline__ int block_exclusive_scan(int* a, int n, int* scratch) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int carry = 0;
+    for (int base = 0; base < n; base += kResolveThreads) {
+        const int i = base + tid;
+        const int v = i < n ? a[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(kFullMask, incl, o); if (lane >= o) incl += u; }
+        if (lane == 31) scratch[warp] = incl;
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kResolveWarps; ++w) { const int c = scratch[w]; if (w < warp) before += c; total += c; }
+        if (i < n) a[i] = carry + before + incl - v;
+        carry += total;
+        __syncthreads();
+    }
+    return carry;
+}
+
+__device__ __forceinline__ void set_bit(unsigned long long* set, int p) {
+    atomicOr(reinterpret_cast<unsigned*>(set) + (p >> 5), 1u << (p & 31));   // little endian halves
+}
+__device__ __forceinline__ bool get_bit(const unsigned long long* set, int p) {
+    return (set[p >> 6] >> (p & 63)) & 1ull;
+}
+
+// word w of the dominator row of box p: from the compact cache when it is there, else from global
+struct RowReader {
+    const unsigned long long* cw;     // [kCompactWords * n] or nullptr
+    const unsigned long long* dom;
+    size_t stride;
+    __device__ __forceinline__ unsigned long long get(int p, unsigned long long nz, int w) const {
+        const int k = __popcll(nz & ((1ull << w) - 1ull));      // rank of word w among the non-zero ones
+        if (cw && k < kCompactWords) return cw[(size_t)p * kCompactWords + k];
+        return dom[(size_t)p * stride + w];
+    }
+};
 
 template <int MODE, bool SLAB>
-__device__ void resolve_body(const NmsParams& P, int seg, unsigned char* smem_raw, int* sm_scan, int* sm_vote,
-                             unsigned long long* skey, int* sval) {
+__device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, unsigned char* smem_raw, bool compact) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    long long off;
-    int n, n_true;
-    segment_range(P, seg, off, n, n_true);
-    if (tid == 0 && SLAB && P.cand_count_out) P.cand_count_out[seg] = n_true;
-    if (n == 0) {
-        if (tid == 0) {
-            if (P.keep_count) P.keep_count[seg] = 0;
-            if (P.det_count) P.det_count[seg] = 0;
-        }
-        return;
-    }
+    const int nw = cdiv(n, 64);      // <= 64 on this path
+    FastSmem f;
+    fast_carve(f, smem_raw, n, nw);
     const float unit = P.mode == B200_NMS_TV_TRICK ? P.shift_unit[seg] : 0.f;
-    const int nw = cdiv(n, 64);
-    unsigned long long* Kset = reinterpret_cast<unsigned long long*>(smem_raw);   // [max_words]
-    unsigned long long* Rset = Kset + P.max_words;                                // [max_words]
     const unsigned long long* dom = P.dom + (size_t)seg * (size_t)P.max_seg * (size_t)P.max_words;
-    for (int w = tid; w < nw; w += kResolveThreads) { Kset[w] = 0ull; Rset[w] = 0ull; }
-    __syncthreads();
+    unsigned long long* cw = compact ? reinterpret_cast<unsigned long long*>(f.u) : nullptr;
+    const int* perm = P.gperm + off;
 
-    // ---- fixed point: kept <=> every dominator removed ; removed <=> some dominator kept ---------
+    for (int w = tid; w < nw; w += kResolveThreads) { f.Kset[w] = 0ull; f.Rset[w] = 0ull; }
+    __syncthreads();
+    // ---- A. stage boxes and the non-zero structure of the mask rows --------------------------------
+    for (int p = tid; p < n; p += kResolveThreads) {
+        const Item it = load_raw<SLAB>(P, off, perm[p], unit);
+        f.box[p] = it.b; f.area[p] = it.area; f.key[p] = it.key; f.lab[p] = it.label;
+        const unsigned long long* row = dom + (size_t)p * P.max_words;
+        const unsigned long long nz = P.nzmask[off + p];
+        if (cw && nz) {
+            // first kCompactWords non-zero words, loads issued together
+            int wi[kCompactWords];
+            unsigned long long it2 = nz;
+#pragma unroll
+            for (int k = 0; k < kCompactWords; ++k) {
+                wi[k] = it2 ? __ffsll((long long)it2) - 1 : -1;
+                it2 &= it2 - 1ull;
+            }
+            unsigned long long d[kCompactWords];
+#pragma unroll
+            for (int k = 0; k < kCompactWords; ++k) d[k] = wi[k] >= 0 ? row[wi[k]] : 0ull;
+#pragma unroll
+            for (int k = 0; k < kCompactWords; ++k) cw[(size_t)p * kCompactWords + k] = d[k];
+        }
+        f.nz[p] = nz;
+        if (!nz) atomicOr(reinterpret_cast<unsigned*>(f.Kset) + (p >> 5), 1u << (p & 31));   // no dominator: kept
+    }
+    __syncthreads();
+    const RowReader R{cw, dom, (size_t)P.max_words};
+
+    // ---- B. fixed point over bitsets ----------------------------------------------------------------
     int pending;
     do {
         int undecided = 0;
-        for (int i = tid; i < n; i += kResolveThreads) {
-            const int wi = i >> 6;
-            const unsigned long long bit = 1ull << (i & 63);
-            if ((Kset[wi] | Rset[wi]) & bit) continue;
-            const unsigned long long* row = dom + (size_t)i * P.max_words;
-            bool any_kept = false, all_removed = true;
-            for (int w = 0; w < nw; ++w) {
-                const unsigned long long d = row[w];
-                if (d) {
-                    if (d & Kset[w]) { any_kept = true; break; }
-                    if (d & ~Rset[w]) all_removed = false;
-                }
+        for (int p = tid; p < n; p += kResolveThreads) {
+            if (get_bit(f.Kset, p) || get_bit(f.Rset, p)) continue;
+            const unsigned long long nz = f.nz[p];
+            unsigned long long hitK = 0ull, alive = 0ull, it = nz;
+            while (it) {
+                const int w = __ffsll((long long)it) - 1;
+                it &= it - 1ull;
+                const unsigned long long d = R.get(p, nz, w);
+                hitK |= d & f.Kset[w];
+                alive |= d & ~f.Rset[w];
             }
-            if (any_kept) atomicOr(&Rset[wi], bit);
-            else if (all_removed) atomicOr(&Kset[wi], bit);
+            if (hitK) set_bit(f.Rset, p);
+            else if (!alive) set_bit(f.Kset, p);
             else ++undecided;
         }
         pending = __syncthreads_count(undecided > 0);
     } while (pending > 0);
 
-    // ---- kept boxes, ordered by (score desc, canonical index asc) ------------------------------------
+    if (MODE == B200_NMS_MAJORITY) {
+        // ---- C. first suppressor + vote (helper.py:368-369), voters gathered per kept box ---------
+        for (int p = tid; p <= n; p += kResolveThreads) f.voff[p] = 0;
+        __syncthreads();
+        for (int j = tid; j < n; j += kResolveThreads) {
+            int s = -1;
+            if (get_bit(f.Rset, j)) {
+                const unsigned long long nz = f.nz[j];
+                unsigned long long best = ~0ull, it = nz;
+                int besti = -1;
+                while (it) {
+                    const int w = __ffsll((long long)it) - 1;
+                    it &= it - 1ull;
+                    unsigned long long d = R.get(j, nz, w) & f.Kset[w];
+                    while (d) {
+                        const int i = w * 64 + __ffsll((long long)d) - 1;
+                        d &= d - 1ull;
+                        if (f.key[i] < best) { best = f.key[i]; besti = i; }
+                    }
+                }
+                bool vote = false;
+                suppresses_exact<MODE>(P, f.box[besti], f.area[besti], f.box[j], f.area[j], &vote);
+                s = besti | (vote ? kVoteFlag : 0);
+                if (vote) atomicAdd(&f.voff[besti], 1);
+            }
+            f.sup[j] = s;
+        }
+        __syncthreads();
+        block_exclusive_scan(f.voff, n + 1, f.scan);
+        for (int p = tid; p < n; p += kResolveThreads) f.klist[p] = f.voff[p];    // fill cursors
+        __syncthreads();
+        for (int j = tid; j < n; j += kResolveThreads) {
+            const int s = f.sup[j];
+            if (s >= 0 && (s & kVoteFlag)) f.vlab[atomicAdd(&f.klist[s & ~kVoteFlag], 1)] = f.lab[j];
+        }
+        __syncthreads();
+        // majority relabel (helper.py:370-375): one warp per kept box that has at least two voters
+        for (int p = warp; p < n; p += kResolveWarps) {
+            if (!get_bit(f.Kset, p)) continue;
+            const int v0 = f.voff[p], L = f.voff[p + 1] - v0;
+            int label = f.lab[p];
+            if (L >= 2) {
+                int best_cnt = 0, best_lab = 0x7fffffff;
+                for (int a = lane; a < L; a += 32) {
+                    const int la = f.vlab[v0 + a];
+                    int cnt = 0;
+                    for (int b = 0; b < L; ++b) cnt += (f.vlab[v0 + b] == la);
+                    if (cnt > best_cnt || (cnt == best_cnt && la < best_lab)) { best_cnt = cnt; best_lab = la; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const int oc = __shfl_xor_sync(kFullMask, best_cnt, o);
+                    const int ol = __shfl_xor_sync(kFullMask, best_lab, o);
+                    if (oc > best_cnt || (oc == best_cnt && ol < best_lab)) { best_cnt = oc; best_lab = ol; }
+                }
+                if (best_cnt < L) label = best_lab;   // more than one distinct class among the voters
+            }
+            if (lane == 0) f.newlab[p] = label;
+        }
+        __syncthreads();
+    }
+
+    // ---- D. kept boxes in (score desc, canonical index asc) order ------------------------------------
+    int running = 0;
+    for (int p0 = 0; p0 < n; p0 += kResolveThreads) {
+        const int p = p0 + tid;
+        const bool kept = p < n && get_bit(f.Kset, p);
+        const int k = block_rank<kResolveWarps>(kept, f.scan, running);
+        if (kept) f.klist[k] = p;
+    }
+    const int K = running;
+    const int Pk = next_pow2(K);
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(f.u);      // compact rows are dead now
+    int* sval = reinterpret_cast<int*>(skey + Pk);
+    __syncthreads();
+    for (int t = tid; t < Pk; t += kResolveThreads) {
+        skey[t] = t < K ? f.key[f.klist[t]] : ~0ull;
+        sval[t] = t < K ? f.klist[t] : -1;
+    }
+    __syncthreads();
+    bitonic_sort(skey, sval, Pk);
+
+    // ---- E. emit -----------------------------------------------------------------------------------------
+    const int Kout = SLAB ? min(K, P.max_det) : K;
+    if (SLAB && P.det_keep) {
+        // index in the reference's candidate list = rank of the flat anchor index among all candidates
+        // one warp per kept box, lanes sweep consecutive candidates (conflict-free shared reads)
+        for (int t = warp; t < Kout; t += kResolveWarps) {
+            const unsigned anchor = (unsigned)f.key[sval[t]];
+            int cnt = 0;
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int j = j0 + lane;
+                cnt += __popc(__ballot_sync(kFullMask, j < n && (unsigned)f.key[j] < anchor));
+            }
+            if (lane == 0) P.det_keep[(size_t)seg * P.max_det + t] = cnt;
+        }
+    }
+    for (int t = tid; t < Kout; t += kResolveThreads) {
+        const int p = sval[t];
+        const int i = perm[p];
+        const int lab = MODE == B200_NMS_MAJORITY ? f.newlab[p] : f.lab[p];
+        if (SLAB) {
+            const float4 b = reinterpret_cast<const float4*>(P.slab + off + i)[0];   // unshifted box
+            float* d = P.det + ((size_t)seg * P.max_det + t) * 6;
+            d[0] = b.x; d[1] = b.y; d[2] = b.z; d[3] = b.w;
+            d[4] = from_orderable(~(unsigned)(f.key[p] >> 32));
+            d[5] = (float)lab;
+            if (P.det_anchor) P.det_anchor[(size_t)seg * P.max_det + t] = (int)(unsigned)f.key[p];
+        } else {
+            P.keep[off + t] = i;
+            if (P.labels_out) P.labels_out[off + t] = lab;
+        }
+    }
+    if (tid == 0) {
+        if (SLAB) {
+            P.det_count[seg] = Kout;
+            if (K > P.max_det && P.status) atomicOr(P.status, 2);
+        } else {
+            P.keep_count[seg] = K;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// resolve, slow path: segments too large for shared memory work on global scratch
+// ------------------------------------------------------------------------------------------
+template <int MODE, bool SLAB>
+__device__ void resolve_slow(const NmsParams& P, int seg, long long off, int n, unsigned char* smem_raw) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float unit = P.mode == B200_NMS_TV_TRICK ? P.shift_unit[seg] : 0.f;
+    const int nw = cdiv(n, 64);
+    unsigned char* q = smem_raw;
+    unsigned long long* Kset = reinterpret_cast<unsigned long long*>(q); q += sizeof(unsigned long long) * P.max_words;
+    unsigned long long* Rset = reinterpret_cast<unsigned long long*>(q); q += sizeof(unsigned long long) * P.max_words;
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(q); q += sizeof(unsigned long long) * kKeptSmem;
+    int* sval = reinterpret_cast<int*>(q);                               q += sizeof(int) * kKeptSmem;
+    int* sm_vote = reinterpret_cast<int*>(q);                            q += sizeof(int) * kResolveWarps * kVoteListCap;
+    int* sm_scan = reinterpret_cast<int*>(q);
+    const unsigned long long* dom = P.dom + (size_t)seg * (size_t)P.max_seg * (size_t)P.max_words;
+    const int* perm = P.gperm + off;
+    for (int w = tid; w < nw; w += kResolveThreads) { Kset[w] = 0ull; Rset[w] = 0ull; }
+    __syncthreads();
+
+    int pending;
+    do {
+        int undecided = 0;
+        for (int p = tid; p < n; p += kResolveThreads) {
+            if (get_bit(Kset, p) || get_bit(Rset, p)) continue;
+            const unsigned long long* row = dom + (size_t)p * P.max_words;
+            const unsigned long long nz = nw <= 64 ? P.nzmask[off + p] : ~0ull;   // short rows: only flagged words are valid
+            unsigned long long hitK = 0ull, alive = 0ull;
+            for (int w = 0; w < nw; ++w) {
+                const unsigned long long d = (nw > 64 || ((nz >> w) & 1ull)) ? row[w] : 0ull;
+                hitK |= d & Kset[w];
+                alive |= d & ~Rset[w];
+            }
+            if (hitK) set_bit(Rset, p);
+            else if (!alive) set_bit(Kset, p);
+            else ++undecided;
+        }
+        pending = __syncthreads_count(undecided > 0);
+    } while (pending > 0);
+
     int running = 0;
     int* klist = P.gklist + off;
-    for (int i0 = 0; i0 < n; i0 += kResolveThreads) {
-        const int i = i0 + tid;
-        const bool kept = i < n && ((Kset[i >> 6] >> (i & 63)) & 1ull);
-        const int k = block_rank(kept, sm_scan, running);
-        if (kept) klist[k] = i;
+    for (int p0 = 0; p0 < n; p0 += kResolveThreads) {
+        const int p = p0 + tid;
+        const bool kept = p < n && get_bit(Kset, p);
+        const int k = block_rank<kResolveWarps>(kept, sm_scan, running);
+        if (kept) klist[k] = p;
     }
     const int K = running;
     __syncthreads();
@@ -425,30 +805,24 @@ __device__ void resolve_body(const NmsParams& P, int seg, unsigned char* smem_ra
     unsigned long long* key = Pk <= kKeptSmem ? skey : P.gkey + 2 * off;   // Pk < 2K <= 2n
     int* val = Pk <= kKeptSmem ? sval : P.gval + 2 * off;
     for (int t = tid; t < Pk; t += kResolveThreads) {
-        if (t < K) {
-            const int i = klist[t];
-            key[t] = load_item<SLAB>(P, off, i, unit).key;
-            val[t] = i;
-        } else {
-            key[t] = ~0ull;
-            val[t] = -1;
-        }
+        if (t < K) { key[t] = load_item<SLAB>(P, off, klist[t], unit).key; val[t] = klist[t]; }
+        else       { key[t] = ~0ull; val[t] = -1; }
     }
     __syncthreads();
     bitonic_sort(key, val, Pk);
 
     int* newlab = P.gnewlab + off;   // indexed by position
     if (MODE == B200_NMS_MAJORITY) {
-        // ---- first suppressor of every removed box = its kept dominator that comes first ----------
         int* sup = P.gsup + off;
         for (int j = tid; j < n; j += kResolveThreads) {
             int s = -1;
-            if ((Rset[j >> 6] >> (j & 63)) & 1ull) {
+            if (get_bit(Rset, j)) {
                 const unsigned long long* row = dom + (size_t)j * P.max_words;
+                const unsigned long long nz = nw <= 64 ? P.nzmask[off + j] : ~0ull;
                 unsigned long long best = ~0ull;
                 int besti = -1;
                 for (int w = 0; w < nw; ++w) {
-                    unsigned long long d = row[w] & Kset[w];
+                    unsigned long long d = (nw > 64 || ((nz >> w) & 1ull)) ? (row[w] & Kset[w]) : 0ull;
                     while (d) {
                         const int i = w * 64 + __ffsll((long long)d) - 1;
                         d &= d - 1ull;
@@ -456,18 +830,15 @@ __device__ void resolve_body(const NmsParams& P, int seg, unsigned char* smem_ra
                         if (k < best) { best = k; besti = i; }
                     }
                 }
-                if (besti >= 0) {
-                    const Item S = load_item<SLAB>(P, off, besti, unit);
-                    const Item T = load_item<SLAB>(P, off, j, unit);
-                    bool vote = false;
-                    suppresses<MODE, true>(P, S.b, S.area, S.label, T.b, T.area, T.label, &vote);
-                    s = besti | (vote ? kVoteFlag : 0);
-                }
+                const Item S = load_item<SLAB>(P, off, besti, unit);
+                const Item T = load_item<SLAB>(P, off, j, unit);
+                bool vote = false;
+                suppresses_exact<MODE>(P, S.b, S.area, T.b, T.area, &vote);
+                s = besti | (vote ? kVoteFlag : 0);
             }
             sup[j] = s;
         }
         __syncthreads();
-        // ---- majority relabel (helper.py:368-375): one warp per kept box ----------------------------
         int* list = sm_vote + warp * kVoteListCap;
         for (int t = warp; t < K; t += kResolveWarps) {
             const int i = klist[t];
@@ -510,7 +881,7 @@ __device__ void resolve_body(const NmsParams& P, int seg, unsigned char* smem_ra
                     const int ol = __shfl_xor_sync(kFullMask, best_lab, o);
                     if (oc > best_cnt || (oc == best_cnt && ol < best_lab)) { best_cnt = oc; best_lab = ol; }
                 }
-                if (best_cnt < L) label = best_lab;   // more than one distinct class among the voters
+                if (best_cnt < L) label = best_lab;
             }
             if (lane == 0) newlab[i] = label;
             __syncwarp();
@@ -518,19 +889,18 @@ __device__ void resolve_body(const NmsParams& P, int seg, unsigned char* smem_ra
         __syncthreads();
     }
 
-    // ---- emit in score order -----------------------------------------------------------------------------
     for (int t = tid; t < K; t += kResolveThreads) {
-        const int i = val[t];
+        const int p = val[t];
+        const int i = perm[p];
         if (SLAB) {
             if (t < P.max_det) {
                 const Cand c = P.slab[off + i];
                 float* d = P.det + ((size_t)seg * P.max_det + t) * 6;
                 d[0] = c.x1; d[1] = c.y1; d[2] = c.x2; d[3] = c.y2;
                 d[4] = c.score;
-                d[5] = (float)(MODE == B200_NMS_MAJORITY ? newlab[i] : c.label);
+                d[5] = (float)(MODE == B200_NMS_MAJORITY ? newlab[p] : c.label);
                 if (P.det_anchor) P.det_anchor[(size_t)seg * P.max_det + t] = c.anchor;
                 if (P.det_keep) {
-                    // index in the reference's candidate list = rank of the flat anchor index
                     int rank = 0;
                     for (int j = 0; j < n; ++j) rank += (P.slab[off + j].anchor < c.anchor);
                     P.det_keep[(size_t)seg * P.max_det + t] = rank;
@@ -538,7 +908,7 @@ __device__ void resolve_body(const NmsParams& P, int seg, unsigned char* smem_ra
             }
         } else {
             P.keep[off + t] = i;
-            if (P.labels_out) P.labels_out[off + t] = MODE == B200_NMS_MAJORITY ? newlab[i] : (P.labels ? P.labels[off + i] : 0);
+            if (P.labels_out) P.labels_out[off + t] = MODE == B200_NMS_MAJORITY ? newlab[p] : (P.labels ? P.labels[off + i] : 0);
         }
     }
     if (tid == 0) {
@@ -551,268 +921,40 @@ __device__ void resolve_body(const NmsParams& P, int seg, unsigned char* smem_ra
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// fast resolve: the whole segment lives in shared memory (n <= kFastN boxes, <= kFastE edges)
-// ------------------------------------------------------------------------------------------
-static constexpr int kFastN = 2048;
-static constexpr int kFastE = 40960;
-
-struct FastSmem {
-    float4* box;               // [kFastN]
-    float* area;               // [kFastN]
-    unsigned long long* key;   // [kFastN]
-    int* lab;                  // [kFastN]
-    int* off;                  // [kFastN+1] dominator list offsets
-    unsigned short* edge;      // [kFastE]   dominator indices; later reused as sort keys + payload
-    unsigned char* state;      // [kFastN]   0 undecided, 1 kept, 2 removed
-    int* sup;                  // [kFastN]   first suppressor | vote flag
-    int* voff;                 // [kFastN+1] voter list offsets
-    int* vlab;                 // [kFastN]   voter labels
-    int* newlab;               // [kFastN]
-    int* klist;                // [kFastN]
-    int* scan;                 // [32]
-};
-__host__ __device__ inline size_t fast_smem_carve(FastSmem* f, unsigned char* base) {
-    size_t o = 0;
-    auto take = [&](size_t bytes) { unsigned char* r = base ? base + o : nullptr; o += align_up(bytes, 16); return r; };
-    unsigned char* p;
-    p = take(16 * kFastN);       if (f) f->box = reinterpret_cast<float4*>(p);
-    p = take(4 * kFastN);        if (f) f->area = reinterpret_cast<float*>(p);
-    p = take(8 * kFastN);        if (f) f->key = reinterpret_cast<unsigned long long*>(p);
-    p = take(4 * kFastN);        if (f) f->lab = reinterpret_cast<int*>(p);
-    p = take(4 * (kFastN + 1));  if (f) f->off = reinterpret_cast<int*>(p);
-    p = take(2 * kFastE);        if (f) f->edge = reinterpret_cast<unsigned short*>(p);
-    p = take(kFastN);            if (f) f->state = p;
-    p = take(4 * kFastN);        if (f) f->sup = reinterpret_cast<int*>(p);
-    p = take(4 * (kFastN + 1));  if (f) f->voff = reinterpret_cast<int*>(p);
-    p = take(4 * kFastN);        if (f) f->vlab = reinterpret_cast<int*>(p);
-    p = take(4 * kFastN);        if (f) f->newlab = reinterpret_cast<int*>(p);
-    p = take(4 * kFastN);        if (f) f->klist = reinterpret_cast<int*>(p);
-    p = take(4 * 32);            if (f) f->scan = reinterpret_cast<int*>(p);
-    return o;
-}
-
-// in-place exclusive scan of a[0..n) (whole CTA), returns the total
-__device__ __forceinline__ int block_exclusive_scan(int* a, int n, int* scratch) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int carry = 0;
-    for (int base = 0; base < n; base += kResolveThreads) {
-        const int i = base + tid;
-        const int v = i < n ? a[i] : 0;
-        int incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(kFullMask, incl, o); if (lane >= o) incl += u; }
-        if (lane == 31) scratch[warp] = incl;
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < kResolveWarps; ++w) { const int c = scratch[w]; if (w < warp) before += c; total += c; }
-        if (i < n) a[i] = carry + before + incl - v;
-        carry += total;
-        __syncthreads();
-    }
-    return carry;
-}
-
-// returns false (before touching any output) when the dominator lists do not fit -> slow path
-template <int MODE, bool SLAB>
-__device__ bool resolve_fast(const NmsParams& P, int seg, long long off, int n, unsigned char* smem_raw) {
-    FastSmem f;
-    fast_smem_carve(&f, smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float unit = P.mode == B200_NMS_TV_TRICK ? P.shift_unit[seg] : 0.f;
-    const int nw = cdiv(n, 64);
-    const unsigned long long* dom = P.dom + (size_t)seg * (size_t)P.max_seg * (size_t)P.max_words;
-
-    // ---- A. boxes + in-degree ---------------------------------------------------------------------
-    for (int i = tid; i < n; i += kResolveThreads) {
-        const Item it = load_item<SLAB>(P, off, i, unit);
-        f.box[i] = it.b; f.area[i] = it.area; f.key[i] = it.key; f.lab[i] = it.label;
-        f.state[i] = 0;
-        const unsigned long long* row = dom + (size_t)i * P.max_words;
-        int deg = 0;
-        for (int w = 0; w < nw; ++w) deg += __popcll(row[w]);
-        f.off[i] = deg;
-    }
-    if (tid == 0) f.off[n] = 0;
-    __syncthreads();
-    const int E = block_exclusive_scan(f.off, n + 1, f.scan);
-    if (E > kFastE) return false;
-    // ---- B. dominator index lists -----------------------------------------------------------------
-    for (int i = tid; i < n; i += kResolveThreads) {
-        const unsigned long long* row = dom + (size_t)i * P.max_words;
-        int e = f.off[i];
-        if (f.off[i + 1] == e) continue;
-        for (int w = 0; w < nw; ++w) {
-            unsigned long long d = row[w];
-            while (d) {
-                f.edge[e++] = (unsigned short)(w * 64 + __ffsll((long long)d) - 1);
-                d &= d - 1ull;
-            }
-        }
-    }
-    __syncthreads();
-    // ---- C. fixed point ---------------------------------------------------------------------------
-    int pending;
-    do {
-        int undecided = 0;
-        for (int i = tid; i < n; i += kResolveThreads) {
-            if (f.state[i]) continue;
-            bool any_kept = false, all_removed = true;
-            for (int e = f.off[i], e1 = f.off[i + 1]; e < e1; ++e) {
-                const int s = f.state[f.edge[e]];
-                if (s == 1) { any_kept = true; break; }
-                if (s == 0) all_removed = false;
-            }
-            if (any_kept) f.state[i] = 2;
-            else if (all_removed) f.state[i] = 1;
-            else ++undecided;
-        }
-        pending = __syncthreads_count(undecided > 0);
-    } while (pending > 0);
-
-    if (MODE == B200_NMS_MAJORITY) {
-        // ---- D. first suppressor + vote (helper.py:368-369), voters gathered per kept box ---------
-        for (int i = tid; i <= n; i += kResolveThreads) f.voff[i] = 0;
-        __syncthreads();
-        for (int j = tid; j < n; j += kResolveThreads) {
-            int s = -1;
-            if (f.state[j] == 2) {
-                unsigned long long best = ~0ull;
-                int besti = -1;
-                for (int e = f.off[j], e1 = f.off[j + 1]; e < e1; ++e) {
-                    const int i = f.edge[e];
-                    if (f.state[i] == 1 && f.key[i] < best) { best = f.key[i]; besti = i; }
-                }
-                bool vote = false;
-                suppresses<MODE, true>(P, f.box[besti], f.area[besti], 0, f.box[j], f.area[j], 0, &vote);
-                s = besti | (vote ? kVoteFlag : 0);
-                if (vote) atomicAdd(&f.voff[besti], 1);
-            }
-            f.sup[j] = s;
-        }
-        __syncthreads();
-        block_exclusive_scan(f.voff, n + 1, f.scan);
-        for (int i = tid; i < n; i += kResolveThreads) f.klist[i] = f.voff[i];    // fill cursors
-        __syncthreads();
-        for (int j = tid; j < n; j += kResolveThreads) {
-            const int s = f.sup[j];
-            if (s >= 0 && (s & kVoteFlag)) f.vlab[atomicAdd(&f.klist[s & ~kVoteFlag], 1)] = f.lab[j];
-        }
-        __syncthreads();
-        // majority relabel (helper.py:370-375): one warp per kept box
-        for (int i = warp; i < n; i += kResolveWarps) {
-            if (f.state[i] != 1) continue;
-            const int v0 = f.voff[i], L = f.voff[i + 1] - v0;
-            int label = f.lab[i];
-            if (L >= 2) {
-                int best_cnt = 0, best_lab = 0x7fffffff;
-                for (int a = lane; a < L; a += 32) {
-                    const int la = f.vlab[v0 + a];
-                    int cnt = 0;
-                    for (int b = 0; b < L; ++b) cnt += (f.vlab[v0 + b] == la);
-                    if (cnt > best_cnt || (cnt == best_cnt && la < best_lab)) { best_cnt = cnt; best_lab = la; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const int oc = __shfl_xor_sync(kFullMask, best_cnt, o);
-                    const int ol = __shfl_xor_sync(kFullMask, best_lab, o);
-                    if (oc > best_cnt || (oc == best_cnt && ol < best_lab)) { best_cnt = oc; best_lab = ol; }
-                }
-                if (best_cnt < L) label = best_lab;   // more than one distinct class among the voters
-            }
-            if (lane == 0) f.newlab[i] = label;
-        }
-        __syncthreads();
-    }
-
-    // ---- E. kept boxes in (score desc, canonical index asc) order ------------------------------------
-    int running = 0;
-    for (int i0 = 0; i0 < n; i0 += kResolveThreads) {
-        const int i = i0 + tid;
-        const bool kept = i < n && f.state[i] == 1;
-        const int k = block_rank(kept, f.scan, running);
-        if (kept) f.klist[k] = i;
-    }
-    const int K = running;
-    const int Pk = next_pow2(K);
-    unsigned long long* skey = reinterpret_cast<unsigned long long*>(f.edge);      // edges are dead now
-    int* sval = reinterpret_cast<int*>(skey + kFastN);
-    for (int t = tid; t < Pk; t += kResolveThreads) {
-        skey[t] = t < K ? f.key[f.klist[t]] : ~0ull;
-        sval[t] = t < K ? f.klist[t] : -1;
-    }
-    __syncthreads();
-    bitonic_sort(skey, sval, Pk);
-
-    // ---- F. emit -------------------------------------------------------------------------------------
-    for (int t = tid; t < K; t += kResolveThreads) {
-        const int i = sval[t];
-        const int lab = MODE == B200_NMS_MAJORITY ? f.newlab[i] : f.lab[i];
-        if (SLAB) {
-            if (t < P.max_det) {
-                const float4 b = reinterpret_cast<const float4*>(P.slab + off + i)[0];   // unshifted box
-                const unsigned anchor = (unsigned)f.key[i];
-                float* d = P.det + ((size_t)seg * P.max_det + t) * 6;
-                d[0] = b.x; d[1] = b.y; d[2] = b.z; d[3] = b.w;
-                d[4] = from_orderable(~(unsigned)(f.key[i] >> 32));
-                d[5] = (float)lab;
-                if (P.det_anchor) P.det_anchor[(size_t)seg * P.max_det + t] = (int)anchor;
-                if (P.det_keep) {
-                    // index in the reference's candidate list = rank of the flat anchor index
-                    int rank = 0;
-                    for (int j = 0; j < n; ++j) rank += ((unsigned)f.key[j] < anchor);
-                    P.det_keep[(size_t)seg * P.max_det + t] = rank;
-                }
-            }
-        } else {
-            P.keep[off + t] = i;
-            if (P.labels_out) P.labels_out[off + t] = lab;
-        }
-    }
-    if (tid == 0) {
-        if (SLAB) {
-            P.det_count[seg] = min(K, P.max_det);
-            if (K > P.max_det && P.status) atomicOr(P.status, 2);
-        } else {
-            P.keep_count[seg] = K;
-        }
-    }
-    return true;
-}
-
-// dynamic shared memory: max(fast layout, slow layout)
 __host__ __device__ inline size_t slow_smem_bytes(int max_words) {
-    return align_up(sizeof(unsigned long long) * 2 * (size_t)max_words, 16) + sizeof(unsigned long long) * kKeptSmem +
+    return sizeof(unsigned long long) * 2 * (size_t)max_words + sizeof(unsigned long long) * kKeptSmem +
            sizeof(int) * kKeptSmem + sizeof(int) * kResolveWarps * kVoteListCap + sizeof(int) * 32;
 }
 
 template <bool SLAB>
 __global__ void __launch_bounds__(kResolveThreads, 1)
-k_nms_resolve(const __grid_constant__ NmsParams P) {
+k_nms_resolve(const __grid_constant__ NmsParams P, const unsigned smem_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int seg = blockIdx.x;
     long long off;
     int n, n_true;
     segment_range(P, seg, off, n, n_true);
-    if (n > 0 && n <= kFastN) {
-        const bool done = P.mode == B200_NMS_MAJORITY ? resolve_fast<B200_NMS_MAJORITY, SLAB>(P, seg, off, n, smem_raw)
-                                                      : resolve_fast<B200_NMS_TV, SLAB>(P, seg, off, n, smem_raw);
-        if (done) {
-            if (threadIdx.x == 0 && SLAB && P.cand_count_out) P.cand_count_out[seg] = n_true;
-            return;
+    if (threadIdx.x == 0 && SLAB && P.cand_count_out) P.cand_count_out[seg] = n_true;
+    if (n == 0) {
+        if (threadIdx.x == 0) {
+            if (P.keep_count) P.keep_count[seg] = 0;
+            if (P.det_count) P.det_count[seg] = 0;
         }
-        __syncthreads();
+        return;
     }
-    unsigned char* q = smem_raw + align_up(sizeof(unsigned long long) * 2 * (size_t)P.max_words, 16);
-    unsigned long long* skey = reinterpret_cast<unsigned long long*>(q); q += sizeof(unsigned long long) * kKeptSmem;
-    int* sval = reinterpret_cast<int*>(q);                                q += sizeof(int) * kKeptSmem;
-    int* sm_vote = reinterpret_cast<int*>(q);                             q += sizeof(int) * kResolveWarps * kVoteListCap;
-    int* sm_scan = reinterpret_cast<int*>(q);
-    if (P.mode == B200_NMS_MAJORITY)
-        resolve_body<B200_NMS_MAJORITY, SLAB>(P, seg, smem_raw, sm_scan, sm_vote, skey, sval);
-    else
-        resolve_body<B200_NMS_TV, SLAB>(P, seg, smem_raw, sm_scan, sm_vote, skey, sval);
+    const int nw = cdiv(n, 64);
+    const size_t fixed = fast_fixed_bytes(n, nw);
+    const size_t sort_bytes = 12 * (size_t)next_pow2(n);
+    const size_t cw_bytes = 8 * (size_t)kCompactWords * (size_t)n;
+    const bool fast = nw <= 64 && fixed + sort_bytes <= smem_bytes;
+    const bool staged = fast && fixed + (cw_bytes > sort_bytes ? cw_bytes : sort_bytes) <= smem_bytes;
+    if (P.mode == B200_NMS_MAJORITY) {
+        if (fast) resolve_fast<B200_NMS_MAJORITY, SLAB>(P, seg, off, n, smem_raw, staged);
+        else      resolve_slow<B200_NMS_MAJORITY, SLAB>(P, seg, off, n, smem_raw);
+    } else {
+        if (fast) resolve_fast<B200_NMS_TV, SLAB>(P, seg, off, n, smem_raw, staged);
+        else      resolve_slow<B200_NMS_TV, SLAB>(P, seg, off, n, smem_raw);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -835,17 +977,20 @@ size_t carve_all(NmsParams* P, size_t T, size_t S, size_t max_seg, void* base, b
     if (S == 0) S = 1;
     if (max_seg == 0) max_seg = 1;
     const size_t words = (max_seg + 63) / 64;
+    const size_t tiles = words * (words + 1) / 2;
     Carve c{reinterpret_cast<unsigned char*>(base), 0, query};
     NmsParams tmp{};
     NmsParams& o = P ? *P : tmp;
     o.gkey = (unsigned long long*)c.take(16 * T);
     o.gval = (int*)c.take(8 * T);
+    o.gperm = (int*)c.take(4 * T);
+    o.nzmask = (unsigned long long*)c.take(8 * T);
     o.gsup = (int*)c.take(4 * T);
     o.gklist = (int*)c.take(4 * T);
     o.gnewlab = (int*)c.take(4 * T);
     o.shift_unit = (float*)c.take(4 * S);
-    o.tile_prefix = (int*)c.take(4 * (S + 1));
-    o.work_counter = (int*)c.take(4);
+    o.work_count = (int*)c.take(8);
+    o.work = (int2*)c.take(8 * S * tiles);
     o.dom = (unsigned long long*)c.take(8 * S * max_seg * words);
     return c.used;
 }
@@ -867,14 +1012,13 @@ int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
     if (num_segments > 65535) return B200_ERR_INVALID;
     if (P.max_seg < 1) P.max_seg = 1;
     P.max_words = cdiv(P.max_seg, 64);
+    if (P.max_words > 65535) return B200_ERR_INVALID;      // tile coordinates are packed in 16 bits
+    P.max_tiles = P.max_words * (P.max_words + 1) / 2;
+    P.num_segments = num_segments;
     if (P.mode < 0) {
         if (!P.from_slab) return B200_ERR_INVALID;
         k_nms_canon<<<num_segments, kCanonThreads, 0, stream>>>(P);
         return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
-    }
-    if (P.mode == B200_NMS_TV_TRICK) {
-        if (P.from_slab) k_nms_trick_prep<true><<<num_segments, 256, 0, stream>>>(P);
-        else             k_nms_trick_prep<false><<<num_segments, 256, 0, stream>>>(P);
     }
     static int sms = 0;
     if (sms == 0) {
@@ -885,16 +1029,16 @@ int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
         else
             sms = 148;
     }
-    P.num_segments = num_segments;
-    k_nms_plan<<<1, 1024, 0, stream>>>(P);
+    if (cudaMemsetAsync(P.work_count, 0, 2 * sizeof(int), stream) != cudaSuccess) return B200_ERR_CUDA;
+    if (P.from_slab) k_nms_plan<true><<<num_segments, kPlanThreads, 0, stream>>>(P);
+    else             k_nms_plan<false><<<num_segments, kPlanThreads, 0, stream>>>(P);
     const int pair_ctas = 8 * sms;                       // 8 x 256 threads per SM, tiles pulled from a queue
     if (P.from_slab) k_nms_pairs<true><<<pair_ctas, kPairThreads, 0, stream>>>(P);
     else             k_nms_pairs<false><<<pair_ctas, kPairThreads, 0, stream>>>(P);
 
-    const size_t fast_bytes = fast_smem_carve(nullptr, nullptr);
     const size_t slow_bytes = slow_smem_bytes(P.max_words);
-    const size_t smem = fast_bytes > slow_bytes ? fast_bytes : slow_bytes;
-    if (smem > 227 * 1024) return B200_ERR_INVALID;   // max_seg beyond ~700k boxes
+    const size_t smem = kResolveSmem > slow_bytes ? kResolveSmem : slow_bytes;
+    if (smem > 227 * 1024) return B200_ERR_INVALID;   // max_seg beyond ~1.4M boxes
     static size_t attr_bytes[2] = {0, 0};
     if (smem > attr_bytes[P.from_slab ? 1 : 0]) {
         const cudaError_t e = P.from_slab
@@ -903,8 +1047,8 @@ int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
         if (e != cudaSuccess) return B200_ERR_CUDA;
         attr_bytes[P.from_slab ? 1 : 0] = smem;
     }
-    if (P.from_slab) k_nms_resolve<true><<<num_segments, kResolveThreads, smem, stream>>>(P);
-    else             k_nms_resolve<false><<<num_segments, kResolveThreads, smem, stream>>>(P);
+    if (P.from_slab) k_nms_resolve<true><<<num_segments, kResolveThreads, smem, stream>>>(P, (unsigned)smem);
+    else             k_nms_resolve<false><<<num_segments, kResolveThreads, smem, stream>>>(P, (unsigned)smem);
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }
 

@@ -36,20 +36,24 @@ struct NmsParams {
     float thr_f;             // MAJORITY: threshold rounded to fp32 (tensor-vs-scalar compare)
     double thr_d;            // TV modes: compared against (double)iou
     int from_slab;
+    int num_segments;
     int max_seg;             // upper bound of any segment length (host-known)
     int max_words;           // cdiv(max_seg, 64): row stride of the dominator bitmask
+    int max_tiles;           // nt*(nt+1)/2 with nt = max_words: work items per segment at most
     // ---- global scratch ---------------------------------------------------------------------
     unsigned long long* gkey;   // [2*T] sort keys when a sort does not fit in shared memory
     int* gval;                  // [2*T] sort payload
-    unsigned long long* dom;    // [S * max_seg * max_words]: bit j of row i = "j precedes i in
-                                //  (score desc, index asc) order and suppresses it"
+    int* gperm;                 // [T] binned position -> index inside the segment
+    unsigned long long* dom;    // [S * max_seg * max_words]: bit q of row p = "the box at position q
+                                //  precedes the box at position p in (score desc, index asc) order
+                                //  and suppresses it"
+    unsigned long long* nzmask; // [T] per row (segments of <= 4096 boxes): which words of the row are non-zero
     float* shift_unit;          // [S] coordinate-trick offset unit (max coordinate + 1)
-    int* tile_prefix;           // [S+1] exclusive prefix of 64x64 pair tiles per segment
-    int* work_counter;          // [1] tile queue cursor
-    int num_segments;
-    int* gsup;                  // [T] first suppressor | vote flag (MAJORITY)
-    int* gklist;                // [T] kept positions
-    int* gnewlab;               // [T] label of each kept box after the majority vote
+    int2* work;                 // [S * max_tiles] (segment, row_tile << 16 | col_tile)
+    int* work_count;            // [2] number of work items, queue cursor
+    int* gsup;                  // [T] first suppressor | vote flag (MAJORITY, slow path)
+    int* gklist;                // [T] kept positions (slow path)
+    int* gnewlab;               // [T] label of each kept box after the majority vote (slow path)
 };
 
 // scratch bytes needed for T boxes in S segments of at most max_seg boxes each
