@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -188,21 +188,41 @@ def run_b200(args):
     grids = [h.shape[2] for h in heads]
     n_anchor = sum(g * g * 3 for g in grids)
     algo_bytes = BATCH * n_anchor * (5 + NUM_CLASSES) * 4
-    plan = ops.YoloPostprocess(grids, BATCH, syn.COCO_ANCHORS, IMG, NUM_CLASSES, True, CONF_THR, NMS_THR,
-                               ops.NMS_MAJORITY, CAPACITY, MAX_DET, dev)
+    # Two independent plans (own outputs + workspace) on two streams: the latency-bound NMS kernels of
+    # step i overlap the HBM-bound decode kernel of step i+1.  Every step's work completes inside the
+    # timed region (the end event waits for both streams).
+    n_streams = max(1, args.streams)
+    plans = [ops.YoloPostprocess(grids, BATCH, syn.COCO_ANCHORS, IMG, NUM_CLASSES, True, CONF_THR, NMS_THR,
+                                 ops.NMS_MAJORITY, CAPACITY, MAX_DET, dev) for _ in range(n_streams)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
     msg_len = BATCH * (1 + MAX_DET * 6)
-    gathered = torch.empty((world * msg_len,), dtype=torch.float32, device=dev) if world > 1 else None
+    gathered = [torch.empty((world * msg_len,), dtype=torch.float32, device=dev) for _ in range(n_streams)] if world > 1 else None
 
-    def step():
-        det, keep, anchor, dcnt, ccnt = plan(heads, idf)
-        if world > 1:
-            msg = ops.pack_detections(det, dcnt)
-            dist.all_gather_into_tensor(gathered, msg)
+    def step(i):
+        k = i % n_streams
+        with torch.cuda.stream(streams[k]):
+            det, keep, anchor, dcnt, ccnt = plans[k](heads, idf)
+            if world > 1:
+                msg = ops.pack_detections(det, dcnt)
+                dist.all_gather_into_tensor(gathered[k], msg)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    def fence_in():
+        ev = torch.cuda.Event()
+        ev.record()
+        for st in streams:
+            st.wait_event(ev)
+
+    def fence_out():
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
+
+    fence_in()
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    fence_out()
     torch.cuda.synchronize()
-    plan.check_status()
+    for pl in plans:
+        pl.check_status()
 
     # per-step events around the fused decode+filter kernel (roofline numerator)
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -218,10 +238,12 @@ def run_b200(args):
         sampler.start()
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin.record()
+    fence_in()
     for i in range(args.steps):
         lib.b200_debug_set_decode_events(C.c_void_p(k_ev[i][0].cuda_event), C.c_void_p(k_ev[i][1].cuda_event))
-        step()
+        step(i)
     lib.b200_debug_set_decode_events(None, None)
+    fence_out()
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -233,7 +255,9 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, k_ms = float(t[0]), float(t[1])
-    plan.check_status()
+    for pl in plans:
+        pl.check_status()
+    plan = plans[0]
     kept = int(plan.det_count.sum())
     cands = int(plan.cand_count.sum())
 
@@ -278,7 +302,7 @@ def run_b200(args):
                                    "22743 anchors/image, softmax classes x IDF, conf 0.1, NMS 0.6",
                        "batch_per_gpu": BATCH, "global_batch": BATCH * world, "img_size": IMG,
                        "l2_policy": "inputs (494.9 MB/step) larger than L2 (126 MB), no flush needed",
-                       "candidates_per_step": cands, "kept_per_step": kept,
+                       "candidates_per_step": cands, "kept_per_step": kept, "streams": n_streams,
                        "exchange": "nccl all_gather of fixed-capacity kept lists" if world > 1 else "none (1 GPU)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "k_decode_filter", "kernel_ms": k_ms,
@@ -288,7 +312,7 @@ def run_b200(args):
                                        "(torch CPU ops, all host threads)"},
             "e2e": {"value": world * BATCH * e2e_steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-            "gpu_launches": args.steps * (2 + (1 if world > 1 else 0)),
+            "gpu_launches": args.steps * (4 + (1 if world > 1 else 0)),
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -299,9 +323,10 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=3, help="software pipeline depth (independent plans on own streams)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -125,7 +125,7 @@ int b200_yolo_decode_filter(const b200_yolo_layout* layout, const float* const* 
  * benchmark.py:94-101).  Outputs per image, kept detections in descending score:
  *   det       [B, max_det, 6] fp32 x1,y1,x2,y2,score,label (label after majority relabel)
  *   det_keep  [B, max_det]    int32 index of the kept box in the image's candidate list
- *                             (ascending-anchor order == the reference's pred_conf order)
+ *                             (ascending-anchor order == the reference's pred_conf order; may be NULL)
  *   det_anchor[B, max_det]    int32 flat anchor index of the kept box (may be NULL)
  *   det_count [B]             int32 number kept (clipped to max_det, status |= 2 if clipped)
  *   cand_count[B]             int32 number of candidates (may be NULL) */

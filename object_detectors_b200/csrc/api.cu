@@ -160,6 +160,7 @@ static int yolo_run(const b200_yolo_layout* layout, const float* const* heads, c
     np.count = count_buf;
     np.cap = capacity;
     np.from_slab = 1;
+    np.anchor_space = p.N;
     np.max_seg = capacity;
     return launch_nms(np, layout->batch, st);
 }
@@ -191,7 +192,7 @@ int b200_yolo_postprocess(const b200_yolo_layout* layout, const float* const* he
                           int32_t capacity, int32_t max_det, float* det, int32_t* det_keep,
                           int32_t* det_anchor, int32_t* det_count, int32_t* cand_count,
                           int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
-    if (!layout || !det || !det_keep || !det_count || !status || capacity < 1 || max_det < 1)
+    if (!layout || !det || !det_count || !status || capacity < 1 || max_det < 1)
         return B200_ERR_INVALID;
     if (nms_mode < B200_NMS_MAJORITY || nms_mode > B200_NMS_TV_TRICK) return B200_ERR_INVALID;
     if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return B200_ERR_WORKSPACE;

@@ -34,7 +34,7 @@ static constexpr int kPlanThreads = 512;
 static constexpr int kPlanTiles = 512;          // tile summaries kept in shared memory (n <= 32768)
 static constexpr int kBins = 128;               // 8 size classes x 16 y bands
 static constexpr int kPairThreads = 256;
-static constexpr int kResolveThreads = 512;
+static constexpr int kResolveThreads = 1024;
 static constexpr int kResolveWarps = kResolveThreads / 32;
 static constexpr int kKeptSmem = 2048;          // slow path: kept boxes sorted in shared memory
 static constexpr int kVoteFlag = 1 << 30;
@@ -714,15 +714,38 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
     const int Kout = SLAB ? min(K, P.max_det) : K;
     if (SLAB && P.det_keep) {
         // index in the reference's candidate list = rank of the flat anchor index among all candidates
-        // one warp per kept box, lanes sweep consecutive candidates (conflict-free shared reads)
-        for (int t = warp; t < Kout; t += kResolveWarps) {
-            const unsigned anchor = (unsigned)f.key[sval[t]];
-            int cnt = 0;
-            for (int j0 = 0; j0 < n; j0 += 32) {
-                const int j = j0 + lane;
-                cnt += __popc(__ballot_sync(kFullMask, j < n && (unsigned)f.key[j] < anchor));
+        const int abits = P.anchor_space;                          // flat anchor indices are < abits
+        const int awords = cdiv(abits, 32);
+        if (abits > 0 && (size_t)awords * 8 <= 12 * (size_t)n) {
+            // bitmap of the candidates' anchor indices + prefix popcounts: rank = #set bits below mine.
+            // sup / voff / vlab (12n contiguous bytes) are free again.
+            unsigned* bm = reinterpret_cast<unsigned*>(f.sup);
+            int* pre = reinterpret_cast<int*>(bm + awords);
+            for (int w = tid; w < awords; w += kResolveThreads) bm[w] = 0u;
+            __syncthreads();
+            for (int j = tid; j < n; j += kResolveThreads) {
+                const unsigned a = (unsigned)f.key[j];
+                atomicOr(&bm[a >> 5], 1u << (a & 31));
             }
-            if (lane == 0) P.det_keep[(size_t)seg * P.max_det + t] = cnt;
+            __syncthreads();
+            for (int w = tid; w < awords; w += kResolveThreads) pre[w] = __popc(bm[w]);
+            __syncthreads();
+            block_exclusive_scan(pre, awords, f.scan);
+            for (int t = tid; t < Kout; t += kResolveThreads) {
+                const unsigned a = (unsigned)f.key[sval[t]];
+                P.det_keep[(size_t)seg * P.max_det + t] = pre[a >> 5] + __popc(bm[a >> 5] & ((1u << (a & 31)) - 1u));
+            }
+        } else {
+            // one warp per kept box, lanes sweep consecutive candidates (conflict-free shared reads)
+            for (int t = warp; t < Kout; t += kResolveWarps) {
+                const unsigned anchor = (unsigned)f.key[sval[t]];
+                int cnt = 0;
+                for (int j0 = 0; j0 < n; j0 += 32) {
+                    const int j = j0 + lane;
+                    cnt += __popc(__ballot_sync(kFullMask, j < n && (unsigned)f.key[j] < anchor));
+                }
+                if (lane == 0) P.det_keep[(size_t)seg * P.max_det + t] = cnt;
+            }
         }
     }
     for (int t = tid; t < Kout; t += kResolveThreads) {

@@ -36,6 +36,7 @@ struct NmsParams {
     float thr_f;             // MAJORITY: threshold rounded to fp32 (tensor-vs-scalar compare)
     double thr_d;            // TV modes: compared against (double)iou
     int from_slab;
+    int anchor_space;        // slab path: flat anchor indices are < anchor_space (0 = unknown)
     int num_segments;
     int max_seg;             // upper bound of any segment length (host-known)
     int max_words;           // cdiv(max_seg, 64): row stride of the dominator bitmask
