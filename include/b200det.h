@@ -222,6 +222,36 @@ int b200_rpn_filter(const float* objectness, const float* deltas, const float* a
                     int32_t nms_mode, float* out_boxes, float* out_scores, int32_t* out_index, int32_t* out_count,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same filter on boxes that are already decoded: the exact signature-level replacement of
+ * RegionProposalNetwork.filter_proposals(proposals, objectness, image_shapes, num_anchors_per_level)
+ * (rpn.py:230).  proposals [B, total, 4] fp32 xyxy. */
+int b200_rpn_filter_proposals(const float* objectness, const float* proposals, int32_t batch,
+                              int32_t total_anchors, const int32_t* level_sizes_host, int32_t num_levels,
+                              const float* image_hw, int32_t pre_nms_top_n, int32_t post_nms_top_n,
+                              double nms_thr, float score_thr, float min_size, int32_t nms_mode,
+                              float* out_boxes, float* out_scores, int32_t* out_index, int32_t* out_count,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * element-wise pieces of the drop-in surface
+ * ---------------------------------------------------------------------------------------- */
+
+/* helper.get_abs_coord (yolo/utilities/helper.py:203-217): [n,4] xc,yc,w,h -> x1,y1,x2,y2. */
+int b200_abs_coord(const float* boxes, int64_t n, float* out, void* stream);
+
+/* BoxCoder.decode_single (torchvision_models/tvision/_utils.py:186-223): rel_codes [n, 4*k],
+ * boxes [n,4] -> out [n, 4*k]; weights_host = (wx, wy, ww, wh); xform_clip = log(1000/16). */
+int b200_boxcoder_decode(const float* rel_codes, const float* boxes, int64_t n, int32_t boxes_per_row,
+                         const float* weights_host, float xform_clip, float* out, void* stream);
+
+/* Matcher.__call__ (tvision/_utils.py:271-344) on a dense [M,N] quality matrix: matches [N] int64 =
+ * argmax over M (first maximum), -1 below low_thr, -2 between the thresholds; with
+ * allow_low_quality every prediction tying a ground truth's best quality gets its argmax back.
+ * workspace: N * 8 bytes (only read when allow_low_quality). */
+int b200_matcher(const float* quality, int32_t m, int32_t n, float high_thr, float low_thr,
+                 int32_t allow_low_quality, int64_t* matches, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * packing for the multi-GPU exchange (the all-gather itself is NCCL via torch.distributed)
  * ---------------------------------------------------------------------------------------- */

@@ -13,7 +13,12 @@ int launch_box_iou(const float*, int, const float*, int, int, int, float*, cudaS
 int launch_box_iou_pair(const float*, const float*, int, int, int, float*, cudaStream_t);
 int launch_iou_match(const float*, const int*, int, int, const float*, int, int, float, long long*,
                      uint8_t*, unsigned long long*, cudaStream_t);
-int launch_rpn_filter(const float* objectness, const float* deltas, const float* anchors, int batch,
+int launch_abs_coord(const float* in, long long n, float* out, cudaStream_t st);
+int launch_boxcoder(const float* rel, const float* boxes, long long n, int k, const float* weights, float clip,
+                    float* out, cudaStream_t st);
+int launch_matcher(const float* q, int M, int N, float high, float low, int allow_low_quality, long long* matches,
+                   long long* all_matches_ws, cudaStream_t st);
+int launch_rpn_filter(const float* objectness, const float* deltas, const float* anchors, const float* proposals, int batch,
                       int total, const int* level_sizes_host, int num_levels, const float* image_hw,
                       int pre_k, int post_k, double nms_thr, float score_thr, float min_size, int nms_mode,
                       float* out_boxes, float* out_scores, int* out_index, int* out_count,
@@ -396,10 +401,60 @@ int b200_rpn_filter(const float* objectness, const float* deltas, const float* a
     if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u) ||
         workspace_bytes < b200_rpn_workspace_bytes(batch, total_anchors, num_levels, pre_nms_top_n))
         return B200_ERR_WORKSPACE;
-    return launch_rpn_filter(objectness, deltas, anchors, batch, total_anchors, level_sizes_host, num_levels,
+    return launch_rpn_filter(objectness, deltas, anchors, nullptr, batch, total_anchors, level_sizes_host, num_levels,
                              image_hw, pre_nms_top_n, post_nms_top_n, nms_thr, score_thr, min_size, nms_mode,
                              out_boxes, out_scores, out_index, out_count, workspace, workspace_bytes,
                              static_cast<cudaStream_t>(stream));
+}
+
+int b200_rpn_filter_proposals(const float* objectness, const float* proposals, int32_t batch,
+                              int32_t total_anchors, const int32_t* level_sizes_host, int32_t num_levels,
+                              const float* image_hw, int32_t pre_nms_top_n, int32_t post_nms_top_n, double nms_thr,
+                              float score_thr, float min_size, int32_t nms_mode, float* out_boxes,
+                              float* out_scores, int32_t* out_index, int32_t* out_count, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    if (!objectness || !proposals || !level_sizes_host || !image_hw || !out_boxes || !out_scores || !out_count ||
+        batch < 1 || total_anchors < 1 || num_levels < 1 || num_levels > 16 || pre_nms_top_n < 1 ||
+        post_nms_top_n < 1)
+        return B200_ERR_INVALID;
+    if (nms_mode != B200_NMS_TV_CLASS && nms_mode != B200_NMS_TV_TRICK) return B200_ERR_INVALID;
+    if (!aligned16(proposals) || !aligned16(out_boxes)) return B200_ERR_INVALID;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u) ||
+        workspace_bytes < b200_rpn_workspace_bytes(batch, total_anchors, num_levels, pre_nms_top_n))
+        return B200_ERR_WORKSPACE;
+    return launch_rpn_filter(objectness, nullptr, nullptr, proposals, batch, total_anchors, level_sizes_host,
+                             num_levels, image_hw, pre_nms_top_n, post_nms_top_n, nms_thr, score_thr, min_size,
+                             nms_mode, out_boxes, out_scores, out_index, out_count, workspace, workspace_bytes,
+                             static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------- element-wise drop-ins
+int b200_abs_coord(const float* boxes, int64_t n, float* out, void* stream) {
+    if (n < 0) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;
+    if (!boxes || !out || !aligned16(boxes) || !aligned16(out)) return B200_ERR_INVALID;
+    return launch_abs_coord(boxes, n, out, static_cast<cudaStream_t>(stream));
+}
+
+int b200_boxcoder_decode(const float* rel_codes, const float* boxes, int64_t n, int32_t boxes_per_row,
+                         const float* weights_host, float xform_clip, float* out, void* stream) {
+    if (n < 0 || boxes_per_row < 1 || !weights_host) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;
+    if (!rel_codes || !boxes || !out || !aligned16(rel_codes) || !aligned16(boxes) || !aligned16(out))
+        return B200_ERR_INVALID;
+    return launch_boxcoder(rel_codes, boxes, n, boxes_per_row, weights_host, xform_clip, out,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int b200_matcher(const float* quality, int32_t m, int32_t n, float high_thr, float low_thr,
+                 int32_t allow_low_quality, int64_t* matches, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+    if (m < 1 || n < 1 || !quality || !matches) return B200_ERR_INVALID;
+    if (allow_low_quality && (!workspace || workspace_bytes < sizeof(long long) * (size_t)n ||
+                              (reinterpret_cast<uintptr_t>(workspace) & 7u)))
+        return B200_ERR_WORKSPACE;
+    return launch_matcher(quality, m, n, high_thr, low_thr, allow_low_quality, reinterpret_cast<long long*>(matches),
+                          reinterpret_cast<long long*>(workspace), static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------ pack

@@ -25,6 +25,7 @@ struct RpnParams {
     const float* obj;       // [B, total]
     const float* deltas;    // [B, total, 4]
     const float* anchors;   // [total, 4]
+    const float* proposals; // [B, total, 4] already decoded boxes (then deltas / anchors are unused)
     const float* image_hw;  // [B, 2]
     int B, total, L, Ktot, pre_k, post_k;
     int level_off[kMaxLevels], level_n[kMaxLevels], level_k[kMaxLevels], level_koff[kMaxLevels];
@@ -148,16 +149,22 @@ k_rpn_select(const __grid_constant__ RpnParams P) {
             const int i = (int)(unsigned)sel[r];
             a = P.level_off[l] + i;
             prob = sigmoid_ref(src[i]);                                            // rpn.py:255
-            const float4 an = *reinterpret_cast<const float4*>(P.anchors + 4 * (size_t)a);
-            const float4 d = *reinterpret_cast<const float4*>(P.deltas + ((size_t)b * P.total + a) * 4);
-            // BoxCoder.decode_single, weights (1,1,1,1)                               _utils.py:199-221
-            const float w = __fsub_rn(an.z, an.x), h = __fsub_rn(an.w, an.y);
-            const float cx = __fadd_rn(an.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(an.y, __fmul_rn(0.5f, h));
-            const float dw = fminf(d.z, kXformClip), dh = fminf(d.w, kXformClip);
-            const float pcx = __fadd_rn(__fmul_rn(d.x, w), cx), pcy = __fadd_rn(__fmul_rn(d.y, h), cy);
-            const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
-            float x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw)), y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
-            float x2 = __fadd_rn(pcx, __fmul_rn(0.5f, pw)), y2 = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+            float x1, y1, x2, y2;
+            if (P.proposals) {
+                const float4 pb = *reinterpret_cast<const float4*>(P.proposals + ((size_t)b * P.total + a) * 4);
+                x1 = pb.x; y1 = pb.y; x2 = pb.z; y2 = pb.w;
+            } else {
+                const float4 an = *reinterpret_cast<const float4*>(P.anchors + 4 * (size_t)a);
+                const float4 d = *reinterpret_cast<const float4*>(P.deltas + ((size_t)b * P.total + a) * 4);
+                // BoxCoder.decode_single, weights (1,1,1,1)                           _utils.py:199-221
+                const float w = __fsub_rn(an.z, an.x), h = __fsub_rn(an.w, an.y);
+                const float cx = __fadd_rn(an.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(an.y, __fmul_rn(0.5f, h));
+                const float dw = fminf(d.z, kXformClip), dh = fminf(d.w, kXformClip);
+                const float pcx = __fadd_rn(__fmul_rn(d.x, w), cx), pcy = __fadd_rn(__fmul_rn(d.y, h), cy);
+                const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
+                x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw)); y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+                x2 = __fadd_rn(pcx, __fmul_rn(0.5f, pw)); y2 = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+            }
             // clip_boxes_to_image (rpn.py:260)
             x1 = fminf(fmaxf(x1, 0.f), img_w); x2 = fminf(fmaxf(x2, 0.f), img_w);
             y1 = fminf(fmaxf(y1, 0.f), img_h); y2 = fminf(fmaxf(y2, 0.f), img_h);
@@ -290,13 +297,13 @@ size_t rpn_workspace_bytes(int batch, int total, int num_levels, int pre_k) {
     return rpn_carve(batch, num_levels, pre_k, nullptr, 0, nullptr) + 256;
 }
 
-int launch_rpn_filter(const float* objectness, const float* deltas, const float* anchors, int batch,
+int launch_rpn_filter(const float* objectness, const float* deltas, const float* anchors, const float* proposals, int batch,
                       int total, const int* level_sizes_host, int num_levels, const float* image_hw,
                       int pre_k, int post_k, double nms_thr, float score_thr, float min_size, int nms_mode,
                       float* out_boxes, float* out_scores, int* out_index, int* out_count,
                       void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     RpnParams P{};
-    P.obj = objectness; P.deltas = deltas; P.anchors = anchors; P.image_hw = image_hw;
+    P.obj = objectness; P.deltas = deltas; P.anchors = anchors; P.proposals = proposals; P.image_hw = image_hw;
     P.B = batch; P.total = total; P.L = num_levels; P.pre_k = pre_k; P.post_k = post_k;
     P.score_thr = score_thr; P.min_size = min_size;
     int off = 0, koff = 0, kmax = 0;

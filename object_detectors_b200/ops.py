@@ -334,6 +334,76 @@ def rpn_filter(objectness: Tensor, deltas: Tensor, anchors: Tensor, level_sizes:
     return boxes, scores, index, count
 
 
+def rpn_filter_proposals(objectness: Tensor, proposals: Tensor, level_sizes: Sequence[int], image_hw: Tensor,
+                         pre_nms_top_n: int, post_nms_top_n: int, nms_thr: float = 0.7, score_thr: float = 0.0,
+                         min_size: float = 1e-3, nms_mode: int = NMS_TV_CLASS):
+    """As rpn_filter, on boxes that are already decoded ([B, total, 4])."""
+    lib = _lib.load()
+    objectness = _need_cuda(objectness, "objectness", torch.float32)
+    proposals = _need_cuda(proposals, "proposals", torch.float32)
+    image_hw = _need_cuda(image_hw, "image_hw", torch.float32)
+    b, total = objectness.shape
+    dev = objectness.device
+    lv = (C.c_int32 * len(level_sizes))(*[int(v) for v in level_sizes])
+    boxes = torch.zeros((b, post_nms_top_n, 4), dtype=torch.float32, device=dev)
+    scores = torch.zeros((b, post_nms_top_n), dtype=torch.float32, device=dev)
+    index = torch.zeros((b, post_nms_top_n), dtype=torch.int32, device=dev)
+    count = torch.zeros((b,), dtype=torch.int32, device=dev)
+    nbytes = lib.b200_rpn_workspace_bytes(b, total, len(level_sizes), pre_nms_top_n)
+    ws = workspace(nbytes, dev, "rpn")
+    _lib.check(lib.b200_rpn_filter_proposals(_ptr(objectness), _ptr(proposals), b, total, lv, len(level_sizes),
+                                             _ptr(image_hw), int(pre_nms_top_n), int(post_nms_top_n),
+                                             float(nms_thr), float(np.float32(score_thr)),
+                                             float(np.float32(min_size)), int(nms_mode), _ptr(boxes), _ptr(scores),
+                                             _ptr(index), _ptr(count), _ptr(ws), ws.numel(), _stream()),
+               "b200_rpn_filter_proposals")
+    return boxes, scores, index, count
+
+
+# ------------------------------------------------------------------------------- element-wise
+def abs_coord(box: Tensor) -> Tensor:
+    """[..., 4] xc,yc,w,h -> x1,y1,x2,y2 (helper.get_abs_coord)."""
+    lib = _lib.load()
+    box = _need_cuda(box, "box", torch.float32)
+    if box.data_ptr() % 16:
+        box = box.clone()
+    out = torch.empty_like(box)
+    _lib.check(lib.b200_abs_coord(_ptr(box), box.numel() // 4, _ptr(out), _stream()), "b200_abs_coord")
+    return out
+
+
+def boxcoder_decode(rel_codes: Tensor, boxes: Tensor, weights=(1.0, 1.0, 1.0, 1.0),
+                    xform_clip: float = 4.135166556742356) -> Tensor:
+    """rel_codes [n, 4k], boxes [n,4] -> [n, 4k] (BoxCoder.decode_single)."""
+    lib = _lib.load()
+    rel_codes = _need_cuda(rel_codes, "rel_codes", torch.float32)
+    boxes = _need_cuda(boxes, "boxes").to(torch.float32).contiguous()
+    n = boxes.shape[0]
+    k = rel_codes.shape[1] // 4 if n else 1
+    if rel_codes.data_ptr() % 16:
+        rel_codes = rel_codes.clone()
+    if boxes.data_ptr() % 16:
+        boxes = boxes.clone()
+    out = torch.empty_like(rel_codes)
+    w = (C.c_float * 4)(*[float(v) for v in weights])
+    _lib.check(lib.b200_boxcoder_decode(_ptr(rel_codes), _ptr(boxes), n, k, w, float(np.float32(xform_clip)),
+                                        _ptr(out), _stream()), "b200_boxcoder_decode")
+    return out
+
+
+def matcher(quality: Tensor, high: float, low: float, allow_low_quality: bool = False) -> Tensor:
+    """[M,N] quality -> int64 [N] matches (Matcher.__call__)."""
+    lib = _lib.load()
+    quality = _need_cuda(quality, "match_quality_matrix", torch.float32)
+    m, n = quality.shape
+    matches = torch.empty((n,), dtype=torch.int64, device=quality.device)
+    ws = workspace(8 * n, quality.device, "matcher")
+    _lib.check(lib.b200_matcher(_ptr(quality), m, n, float(np.float32(high)), float(np.float32(low)),
+                                int(bool(allow_low_quality)), _ptr(matches), _ptr(ws), ws.numel(), _stream()),
+               "b200_matcher")
+    return matches
+
+
 def pack_detections(det: Tensor, det_count: Tensor) -> Tensor:
     lib = _lib.load()
     b, max_det = det.shape[0], det.shape[1]

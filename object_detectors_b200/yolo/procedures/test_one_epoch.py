@@ -1,0 +1,69 @@
+"""Drop-in for ``yolo/procedures/test_one_epoch.py`` (reference): same signature
+``test_one_epoch(dataloader, model, yolo_loss, cfg) -> list[dict]`` and the same result list.
+
+Lines 22-36 of the reference (decode, xyxy, score, mask, per-image gather, nms_majority) are one
+fused call; the result emission (reference :41-66: rescale to the original image, 80->91 class ids,
+xywh + area) is done for the whole batch at once with a single device->host transfer instead of
+several ``.tolist()`` round trips per image.
+
+Reference behaviours kept on purpose:
+  * ``cfg.yolo.inf_iou_threshold`` is read but the threshold actually used is nms_majority's default
+    0.6 (reference :8,:36);
+  * images without candidates are dropped from the prediction list BEFORE it is matched with
+    ``targets`` by position (reference :34,:37,:41-47), so the image sizes / ids of later images
+    shift.  That is a reference bug, reproduced by default because a drop-in must return what the
+    reference returns; ``strict_reference=False`` attributes every detection to its own image.
+"""
+from __future__ import annotations
+
+import torch
+
+from ..utilities import helper
+
+NMS_IOU = 0.6   # helper.nms_majority's default, the value the reference really runs with
+
+
+def _emit(det, det_count, targets, inp_dim, dset_name, strict_reference):
+    counts = det_count.tolist()                                   # the one sync of the batch
+    kept_images = [b for b, k in enumerate(counts) if k > 0]
+    if not kept_images:
+        return []
+    dev = det.device
+    rows = torch.cat([det[b, :counts[b]] for b in kept_images], dim=0)                     # [sumK, 6]
+    # position in the filtered list (reference) or true image index
+    owner_of = {b: (i if strict_reference else b) for i, b in enumerate(kept_images)}
+    owner = torch.cat([torch.full((counts[b],), owner_of[b], dtype=torch.long, device=dev) for b in kept_images])
+    size_hw = torch.stack([t["img_size"].to(dev, torch.float32) for t in targets])         # [B, 2] (h, w)
+    image_ids = torch.stack([t["image_id"].reshape(()).to(dev) for t in targets])
+    sw, sh = size_hw[owner, 1], size_hw[owner, 0]
+    x1 = rows[:, 0] / inp_dim * sw
+    y1 = rows[:, 1] / inp_dim * sh
+    x2 = rows[:, 2] / inp_dim * sw
+    y2 = rows[:, 3] / inp_dim * sh
+    w, h = x2 - x1, y2 - y1
+    cls = rows[:, 5].long()
+    cat = helper.torch80_to_91(cls) if dset_name == "coco" else cls + 1
+    packed = torch.stack((x1, y1, w, h, w * h, rows[:, 4]), dim=1).cpu().tolist()
+    cat = cat.cpu().tolist()
+    ids = image_ids[owner].cpu().tolist()
+    return [{"bbox": p[:4], "area": p[4], "category_id": c, "score": p[5], "image_id": i}
+            for p, c, i in zip(packed, cat, ids)]
+
+
+def test_one_epoch(dataloader, model, yolo_loss, cfg, strict_reference: bool = True):
+    confidence = cfg.yolo.inf_confidence
+    _ = cfg.yolo.inf_iou_threshold          # read and ignored, exactly like the reference
+    inp_dim = cfg.dataset.inp_dim
+    yolo_loss.set_img_size(inp_dim)
+    model.eval()
+    dset_name = dataloader.dset_name
+    torch.backends.cudnn.benchmark = True
+    results = []
+    with torch.no_grad():
+        for images, targets in dataloader:
+            images = images.to("cuda", non_blocking=True)
+            targets = [{k: v.to("cuda", non_blocking=True) for k, v in t.items()} for t in targets]
+            heads = model(images)
+            det, _keep, _anchor, det_count, _cand = yolo_loss.postprocess(heads, conf_thr=confidence, nms_thr=NMS_IOU)
+            results.extend(_emit(det, det_count, targets, inp_dim, dset_name, strict_reference))
+    return results

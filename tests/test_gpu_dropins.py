@@ -1,0 +1,210 @@
+"""GPU tests of the reference-signature drop-ins (object_detectors_b200.yolo.*, .tvision.*): the
+Python call sites of the reference keep their names, arguments and layouts, so these tests read like
+calls into the reference; expected values come from the CPU oracle / golden fixtures."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from object_detectors_b200 import synthetic as syn
+from oracle import cref, tv_ref, yolo_ref
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class AttrDict(dict):
+    __getattr__ = dict.__getitem__
+
+
+def _cfg(img, classes, anchors, dset, class_loss, tfidf):
+    yolo = AttrDict(classes=classes, img_size=img, ignore_threshold=0.5, iou_type=1, class_loss=class_loss,
+                    inf_confidence=0.1, inf_iou_threshold=0.6, tfidf=tfidf, tfidf_variant="smooth", tfidf_norm=0)
+    dataset = AttrDict(anchors=[[list(p) for p in s] for s in anchors], dset_name=dset, inp_dim=img,
+                       num_classes=classes)
+    return AttrDict(yolo=yolo, dataset=dataset)
+
+
+def _idf(name):
+    return torch.from_numpy(np.load(os.path.join(G, f"idf_{name}_smooth.npy")))
+
+
+# ------------------------------------------------------------------------------------- helper.py
+def test_helper_get_abs_coord_and_bbox_iou():
+    from object_detectors_b200.yolo.utilities import helper
+    g = np.random.Generator(np.random.PCG64(5))
+    box = torch.from_numpy(g.random((7, 33, 4)).astype(np.float32))
+    np.testing.assert_array_equal(helper.get_abs_coord(box.cuda()).cpu().numpy(), yolo_ref.abs_coord(box).numpy())
+    np.testing.assert_array_equal(helper.get_abs_coord(box[0].cuda()).cpu().numpy(), yolo_ref.abs_coord(box[0]).numpy())
+    cx, _ = yolo_ref.grid_table(syn.COCO_ANCHORS, 416, (13, 26, 52))
+    gt = torch.from_numpy(syn.gt_targets(31, 1, 80, max_gt=20, min_gt=20)[0]["bbox"])
+    for kind in (0, 1, 2):
+        want = yolo_ref.bbox_iou(gt.unsqueeze(1), cx.unsqueeze(0), kind).numpy()
+        got = helper.bbox_iou(gt.cuda().unsqueeze(1), cx.cuda().unsqueeze(0), kind).cpu().numpy()
+        np.testing.assert_array_equal(got, want)
+        pw = yolo_ref.bbox_iou(gt, cx[:20], kind).numpy()
+        np.testing.assert_array_equal(helper.bbox_iou(gt.cuda(), cx[:20].cuda(), kind).cpu().numpy(), pw)
+    # differentiable call (loss side): same values, gradient flows
+    a = gt.cuda().clone().requires_grad_(True)
+    out = helper.bbox_iou(a, cx[:20].cuda(), 1)
+    out.sum().backward()
+    assert a.grad is not None and torch.isfinite(a.grad).all()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), yolo_ref.bbox_iou(gt, cx[:20], 1).numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_helper_nms_majority_matches_reference_golden():
+    from object_detectors_b200.yolo.utilities import helper
+    gold = np.load(os.path.join(G, "nms_majority_boxes.npz"))
+    for i in range(4):
+        seed, n, k, c = (int(v) for v in gold[f"args_{i}"])
+        boxes, scores, labels = syn.random_boxes(seed, n, clusters=k, num_classes=c)
+        P = torch.from_numpy(np.concatenate([boxes, scores[:, None], labels[:, None].astype(np.float32)], 1)).cuda()
+        before = P.clone()
+        kept = helper.nms_majority(P, 0.6)
+        np.testing.assert_array_equal(kept.cpu().numpy(), gold[f"kept_{i}"])          # what the reference returned
+        # in-place relabel of the kept rows, nothing else touched
+        changed = (P != before).any(dim=1).nonzero().flatten().cpu().numpy()
+        ki, kl = cref.nms_majority(before.cpu().numpy(), 0.6, c)
+        relabelled = ki[kl != before.cpu().numpy()[ki, 5].astype(np.int32)]
+        np.testing.assert_array_equal(np.sort(changed), np.sort(relabelled))
+
+
+# ------------------------------------------------------------------------------------ YOLOForw
+def test_yoloforw_forward_and_get_target():
+    from object_detectors_b200.yolo.nets.yolo_forw import YOLOForw
+    heads = syn.yolo_heads(3, 1, 416, 80, syn.COCO_ANCHORS, "clustered")
+    idf = _idf("coco")
+    model = YOLOForw(_cfg(416, 80, syn.COCO_ANCHORS, "coco", 1, [0, 0]), idf_logits=idf)
+    pred = model([torch.from_numpy(h).cuda() for h in heads]).cpu().numpy()
+    ref = yolo_ref.decode([torch.from_numpy(h) for h in heads], syn.COCO_ANCHORS, 416, 80, idf, True).numpy()
+    assert pred.shape == (1, 10647, 85)
+    assert np.all(np.abs(pred[..., :4] - ref[..., :4]) <= 1e-5 * np.maximum(np.abs(ref[..., :4]), 416))
+    assert np.all(np.abs(pred[..., 4:] - ref[..., 4:]) <= 1e-5 * np.abs(ref[..., 4:]) + 1e-12)
+    with pytest.raises(NotImplementedError):
+        model([torch.from_numpy(h).cuda() for h in heads], targets=[{}])
+
+    gold = np.load(os.path.join(G, "match_416.npz"))
+    targets = syn.gt_targets(31, 3, 80, max_gt=20)
+    tt = [{k: torch.from_numpy(v).cuda() for k, v in t.items()} for t in targets]
+    cx, inw = model.grid_table((13, 26, 52))
+    rcx, rinw = yolo_ref.grid_table(syn.COCO_ANCHORS, 416, (13, 26, 52))
+    np.testing.assert_array_equal(cx.cpu().numpy(), rcx.numpy())
+    for kind in (0, 1):
+        model.iou_type = kind
+        tgt, tcls, obj, noobj = model.get_target(tt, cx, inw, ignore_threshold=0.5)
+        np.testing.assert_array_equal(torch.cat(obj).cpu().numpy(), gold[f"obj_{kind}"])
+        np.testing.assert_array_equal(np.packbits(noobj.cpu().numpy()), gold[f"noobj_{kind}"])
+        np.testing.assert_array_equal(tcls.argmax(1).cpu().numpy(), gold[f"tcls_argmax_{kind}"])
+        np.testing.assert_allclose(tgt.cpu().numpy(), gold[f"tgt_{kind}"], rtol=1e-5, atol=1e-6)
+
+
+# -------------------------------------------------------------------------------- test_one_epoch
+class _Loader(list):
+    dset_name = "coco"
+
+
+def test_test_one_epoch_reproduces_reference_results():
+    from object_detectors_b200.yolo.nets.yolo_forw import YOLOForw
+    from object_detectors_b200.yolo.procedures.test_one_epoch import test_one_epoch as run
+    cfg = _cfg(608, 80, syn.COCO_ANCHORS, "coco", 1, [0, 0])
+    idf = _idf("coco")
+    heads = syn.yolo_heads(203, 4, 608, 80, syn.COCO_ANCHORS, "clustered")
+    # blank out image 1 so that the reference's "drop empty images" path (and its index shift) is hit
+    for h in heads:
+        h[1, 4::85] = -20.0
+    yolo = YOLOForw(cfg, idf_logits=idf)
+    model = types.SimpleNamespace(eval=lambda: None, __call__=None)
+
+    class _Model:
+        def eval(self):
+            return self
+
+        def __call__(self, images):
+            return [torch.from_numpy(h).cuda() for h in heads]
+
+    sizes = [(480, 640), (375, 500), (427, 640), (600, 800)]
+    targets = [{"img_size": torch.tensor(s), "image_id": torch.tensor(1000 + i)} for i, s in enumerate(sizes)]
+    loader = _Loader([(torch.zeros(4, 3, 8, 8), targets)])
+    got = run(loader, _Model(), yolo, cfg)
+
+    recs = yolo_ref.postprocess([torch.from_numpy(h) for h in heads], syn.COCO_ANCHORS, 608, 80, idf, True)
+    assert recs[1]["det6"].shape[0] == 0
+    kept = [r["kept"] for r in recs if r["kept"].shape[0] > 0]           # reference :34,:37
+    coco91 = [c for c in range(1, 91) if c not in (12, 26, 29, 30, 45, 66, 68, 69, 71, 83)]
+    want = []
+    for i, rows in enumerate(kept):                                        # reference :41-66, targets[i] by position
+        h, w = sizes[i]
+        for r in rows.numpy():
+            x1, y1, x2, y2 = r[0] / 608 * w, r[1] / 608 * h, r[2] / 608 * w, r[3] / 608 * h
+            want.append((1000 + i, coco91[int(r[5])], float(r[4]), [x1, y1, x2 - x1, y2 - y1]))
+    assert len(got) == len(want) > 0
+    for g, (iid, cat, score, bbox) in zip(got, want):
+        assert g["image_id"] == iid and g["category_id"] == cat
+        assert abs(g["score"] - score) <= 1e-5 * abs(score)
+        np.testing.assert_allclose(g["bbox"], bbox, rtol=1e-4, atol=1e-2)
+        assert abs(g["area"] - g["bbox"][2] * g["bbox"][3]) <= 1e-3 * max(g["area"], 1.0)
+    fixed = run(loader, _Model(), yolo, cfg, strict_reference=False)
+    assert sorted({d["image_id"] for d in fixed}) == [1000, 1002, 1003]
+
+
+# ------------------------------------------------------------------------------------- tvision
+def test_tvision_boxes_match_torchvision():
+    from torchvision.ops import boxes as tvb
+    from object_detectors_b200.tvision import boxes as b2
+    b, s, l = syn.random_boxes(7, 900, clusters=15, num_classes=6)
+    tb, ts, tl = torch.from_numpy(b), torch.from_numpy(s), torch.from_numpy(l)
+    np.testing.assert_array_equal(b2.nms(tb.cuda(), ts.cuda(), 0.5).cpu().numpy(), tvb.nms(tb, ts, 0.5).numpy())
+    np.testing.assert_array_equal(b2.batched_nms(tb.cuda(), ts.cuda(), tl.cuda(), 0.5, "vanilla").cpu().numpy(),
+                                  tvb._batched_nms_vanilla(tb, ts, tl, 0.5).numpy())
+    np.testing.assert_array_equal(b2.batched_nms(tb.cuda(), ts.cuda(), tl.cuda(), 0.5).cpu().numpy(),
+                                  tvb._batched_nms_coordinate_trick(tb, ts, tl, 0.5).numpy())
+    np.testing.assert_array_equal(b2.box_iou(tb[:50].cuda(), tb.cuda()).cpu().numpy(), tvb.box_iou(tb[:50], tb).numpy())
+    assert b2.nms(tb[:0].cuda(), ts[:0].cuda(), 0.5).numel() == 0
+    np.testing.assert_array_equal(b2.clip_boxes_to_image(tb.cuda(), (300, 400)).cpu().numpy(),
+                                  tvb.clip_boxes_to_image(tb, (300, 400)).numpy())
+    np.testing.assert_array_equal(b2.remove_small_boxes(tb.cuda(), 20.0).cpu().numpy(),
+                                  tvb.remove_small_boxes(tb, 20.0).numpy())
+
+
+def test_boxcoder_and_matcher():
+    from object_detectors_b200.tvision._utils import BoxCoder, Matcher
+    obj, deltas, anchors, per_level = syn.rpn_inputs(41, 1, 224, 320)
+    d, a = torch.from_numpy(deltas[0]), torch.from_numpy(anchors)
+    for w in ((1.0, 1.0, 1.0, 1.0), (10.0, 10.0, 5.0, 5.0)):
+        got = BoxCoder(w).decode_single(d.cuda(), a.cuda()).cpu().numpy()
+        want = tv_ref.decode_single(d, a, w).numpy()
+        assert np.all(np.abs(got - want) <= 1e-5 * np.maximum(np.abs(want), 320))
+    got = BoxCoder((1.0, 1.0, 1.0, 1.0)).decode(d.cuda(), [a.cuda()]).cpu().numpy()
+    assert got.shape == (a.shape[0], 1, 4)
+    # Matcher on a real IoU matrix with exact ties (duplicated predictions)
+    gt, _, _ = syn.random_boxes(3, 12, clusters=3)
+    pr, _, _ = syn.random_boxes(4, 700, clusters=3)
+    pr[100:110] = pr[0:10]
+    q = tv_ref.box_iou(torch.from_numpy(gt), torch.from_numpy(pr))
+    for allow in (False, True):
+        for hi, lo in ((0.7, 0.3), (0.5, 0.5)):
+            want = tv_ref.matcher(q.clone(), hi, lo, allow).numpy()
+            got = Matcher(hi, lo, allow)(q.cuda()).cpu().numpy()
+            np.testing.assert_array_equal(got, want)
+
+
+def test_rpn_filter_proposals_bound_like_the_reference():
+    from object_detectors_b200.tvision import rpn as b200_rpn
+    gold = np.load(os.path.join(G, "rpn_filter.npz"))
+    for tag in ("s", "m"):
+        seed, bsz, ih, iw, pre, post = (int(v) for v in gold[f"{tag}_args"])
+        obj, deltas, anchors, per_level = syn.rpn_inputs(seed, bsz, ih, iw)
+        a = torch.from_numpy(anchors)
+        props = torch.stack([tv_ref.decode_single(torch.from_numpy(deltas[i]), a) for i in range(bsz)])
+        fake_self = types.SimpleNamespace(pre_nms_top_n=lambda: pre, post_nms_top_n=lambda: post, nms_thresh=0.7,
+                                          score_thresh=0.0, min_size=1e-3)
+        # the reference ran on CPU, where torchvision picks the strategy by numel > 4000
+        n_kept = sum(min(pre, n) for n in per_level)
+        strategy = "vanilla" if n_kept * 4 > 4000 else "coordinate_trick"
+        boxes, scores = b200_rpn.filter_proposals(fake_self, props.cuda(), torch.from_numpy(obj).reshape(-1, 1).cuda(),
+                                                  [(ih, iw)] * bsz, per_level, strategy=strategy)
+        for i in range(bsz):
+            np.testing.assert_array_equal(boxes[i].cpu().numpy(), gold[f"{tag}_boxes_{i}"])
+            np.testing.assert_allclose(scores[i].cpu().numpy(), gold[f"{tag}_scores_{i}"], rtol=1e-5)
