@@ -181,6 +181,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    lib.b200_set_decode_variant({"gated": 0, "stream": 1, "bulk": 2}[args.variant])
 
     heads_np = make_heads(1000 + rank, BATCH)
     heads = [torch.from_numpy(h).to(dev) for h in heads_np]
@@ -302,7 +303,7 @@ def run_b200(args):
                                    "22743 anchors/image, softmax classes x IDF, conf 0.1, NMS 0.6",
                        "batch_per_gpu": BATCH, "global_batch": BATCH * world, "img_size": IMG,
                        "l2_policy": "inputs (494.9 MB/step) larger than L2 (126 MB), no flush needed",
-                       "candidates_per_step": cands, "kept_per_step": kept, "streams": n_streams,
+                       "candidates_per_step": cands, "kept_per_step": kept, "streams": n_streams, "decode_variant": args.variant,
                        "exchange": "nccl all_gather of fixed-capacity kept lists" if world > 1 else "none (1 GPU)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "k_decode_filter", "kernel_ms": k_ms,
@@ -326,6 +327,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default="gated", choices=["gated", "stream", "bulk"],
+                    help="fused decode kernel variant (include/b200det.h: B200_DECODE_*)")
     ap.add_argument("--streams", type=int, default=3, help="software pipeline depth (independent plans on own streams)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -151,6 +151,17 @@ int b200_yolo_postprocess_host(const b200_yolo_layout* layout, const float* cons
  * before and after the fused decode+filter kernel. */
 int b200_debug_set_decode_events(void* ev_begin, void* ev_end);
 
+/* Variants of the fused decode+filter kernel.  All produce identical results; they differ in how the
+ * head tensors are fetched (process-wide setting, default B200_DECODE_GATED):
+ *   GATED   register path; the objectness plane is read for every cell, class and box planes only by
+ *           lanes that hold a cell whose objectness can still pass the threshold (score <= conf).
+ *           DRAM traffic is input dependent (184 MB of the 495 MB batch on the benchmark input).
+ *   STREAM  register path; every byte of the head tensors is read once, coalesced 128-bit loads.
+ *           Input independent: the variant the HBM roofline fraction is quoted for.
+ *   BULK    as STREAM, tiles staged in shared memory by cp.async.bulk (TMA) + mbarrier. */
+enum { B200_DECODE_GATED = 0, B200_DECODE_STREAM = 1, B200_DECODE_BULK = 2 };
+int b200_set_decode_variant(int variant);
+
 /* ------------------------------------------------------------------------------------------
  * NMS on caller-provided boxes, batched over segments (images, or image x level)
  * ---------------------------------------------------------------------------------------- */

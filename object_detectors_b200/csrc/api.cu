@@ -7,7 +7,8 @@
 #include "nms.cuh"
 
 namespace b200 {
-int launch_decode_filter(const DecodeParams& p, bool softmax, cudaStream_t stream);
+int launch_decode_filter(const DecodeParams& p, bool softmax, int gate, cudaStream_t stream);
+int launch_decode_filter_bulk(const DecodeParams& p, bool softmax, cudaStream_t stream);
 int launch_decode_dense(const DecodeParams& p, bool softmax, float* out, cudaStream_t stream);
 int launch_box_iou(const float*, int, const float*, int, int, int, float*, cudaStream_t);
 int launch_box_iou_pair(const float*, const float*, int, int, int, float*, cudaStream_t);
@@ -134,6 +135,12 @@ size_t b200_yolo_workspace_bytes(const b200_yolo_layout* layout, int32_t capacit
 
 // Optional profiling hook (bench.py): events recorded on the call's stream right before / after
 // the fused decode+filter kernel, so its duration can be measured inside a timed region.
+static int g_decode_variant = B200_DECODE_GATED;
+int b200_set_decode_variant(int variant) {
+    if (variant < B200_DECODE_GATED || variant > B200_DECODE_BULK) return B200_ERR_INVALID;
+    g_decode_variant = variant;
+    return B200_OK;
+}
 static void* g_ev_decode_begin = nullptr;
 static void* g_ev_decode_end = nullptr;
 int b200_debug_set_decode_events(void* ev_begin, void* ev_end) {
@@ -155,7 +162,10 @@ static int yolo_run(const b200_yolo_layout* layout, const float* const* heads, c
     p.status = np.status;
     B200_CUDA_TRY(cudaMemsetAsync(count_buf, 0, sizeof(int) * (size_t)layout->batch, st));
     if (g_ev_decode_begin) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(g_ev_decode_begin), st));
-    const int rc2 = launch_decode_filter(p, layout->softmax != 0, st);
+    int rc2 = 1;
+    if (g_decode_variant == B200_DECODE_BULK) rc2 = launch_decode_filter_bulk(p, layout->softmax != 0, st);
+    if (rc2 == 1)   // not bulk, or the tile does not fit in shared memory
+        rc2 = launch_decode_filter(p, layout->softmax != 0, g_decode_variant == B200_DECODE_GATED ? 1 : 0, st);
     if (rc2 != B200_OK) return rc2;
     if (g_ev_decode_end) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(g_ev_decode_end), st));
     if (!nms_carve_scratch(&np, (size_t)layout->batch * capacity, (size_t)layout->batch, (size_t)capacity,

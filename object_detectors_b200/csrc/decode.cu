@@ -40,7 +40,7 @@ int make_decode_params(const b200_yolo_layout* L, const float* const* heads, con
         // 128-bit loads need every plane row (hw floats apart) 16 B aligned
         const bool aligned = (d.hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(heads[s]) & 15u) == 0);
         d.vec = aligned ? 4 : 1;
-        d.tiles = cdiv(d.hw, 32 * d.vec);
+        d.tiles = cdiv(d.hw, 128);   // 32 lanes x 4 cells per warp task
         d.task_begin = task;
         d.anchor_off = anchor_off;
         d.inw = (float)d.grid;
@@ -60,54 +60,83 @@ int make_decode_params(const b200_yolo_layout* L, const float* const* heads, con
 // ------------------------------------------------------------------------------------------
 // fused decode + filter
 // ------------------------------------------------------------------------------------------
-template <int VEC>
-__device__ __forceinline__ void load_row(const float* p, bool in, float (&v)[VEC]) {
+// `sink` folds every loaded word into a register that is (never, but unprovably) stored at the end
+// of the task.  Without it ptxas sinks the class-plane loads under the live-cell predicate -- the
+// inline-asm `volatile` does not bind ptxas -- and the kernel silently degrades from a coalesced
+// stream into sector-granular gathers (measured: 184 MB of DRAM reads instead of 495 MB, same time).
+// Every lane owns kCellsPerLane = 4 cells: 4 consecutive ones fetched by one 128-bit load when the
+// plane rows are 16 B aligned (VEC = 4), else the cells lane, lane+32, lane+64, lane+96 of the tile
+// fetched by four coalesced 32-bit loads (VEC = 1, odd grids).
+static constexpr int kCellsPerLane = 4;
+template <int VEC, bool STREAM>
+__device__ __forceinline__ void load_row(const float* p, const bool (&in)[kCellsPerLane], float (&v)[kCellsPerLane],
+                                         unsigned& sink) {
     if constexpr (VEC == 4) {
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (in) r = ldg_stream_v4(p);
+        if (in[0]) r = ldg_stream_v4(p);
         v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
     } else {
-        v[0] = in ? ldg_stream_f32(p) : 0.f;
+#pragma unroll
+        for (int k = 0; k < kCellsPerLane; ++k) v[k] = in[k] ? ldg_stream_f32(p + 32 * k) : 0.f;
     }
+    if constexpr (STREAM) sink ^= __float_as_uint(v[0]) ^ __float_as_uint(v[1]) ^ __float_as_uint(v[2]) ^ __float_as_uint(v[3]);
 }
 
 static constexpr float kLog2e = 1.4426950408889634f;
+#ifndef DF_U
+#define DF_U 8        // class planes loaded per chunk (tuned on B200: 8 planes x 6 CTAs/SM)
+#endif
+#ifndef DF_MINB
+#define DF_MINB 6     // resident CTAs per SM the register budget is set for
+#endif
 
 // One warp task: 32*VEC cells of one (scale, b, a).
-template <int VEC, bool SOFTMAX, bool HAS_IDF, int U>
+template <int VEC, bool SOFTMAX, bool HAS_IDF, int U, bool STREAM>
 __device__ __forceinline__ void decode_filter_task(const DecodeParams& p, const ScaleDev& sc, int b,
                                                    int a, int tile, int lane) {
-    const int hw0 = (tile * 32 + lane) * VEC;
-    const bool in = hw0 < sc.hw;  // hw % VEC == 0, so a lane is entirely in or out
+    constexpr int NC = kCellsPerLane;
+    // cell k of this lane: VEC=4 -> hw0 + k ; VEC=1 -> hw0 + 32*k
+    const int hw0 = VEC == 4 ? (tile * 32 + lane) * 4 : tile * 128 + lane;
+    constexpr int kStep = VEC == 4 ? 1 : 32;
+    bool in[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) in[k] = hw0 + k * kStep < sc.hw;   // VEC=4: hw % 4 == 0, all or nothing
     const int C = p.C;
     const size_t plane = (size_t)sc.hw;
     const float* base = sc.head + ((size_t)(b * p.A + a) * (size_t)(5 + C)) * plane + (size_t)hw0;
 
     // --- objectness plane: which cells can still pass?  score = conf*maxp <= conf ------------
-    float t4[VEC];
-    load_row<VEC>(base + 4 * plane, in, t4);
-    float conf[VEC];
-    bool live[VEC];
+    unsigned sink = 0u;
+    float t4[NC];
+    load_row<VEC, STREAM>(base + 4 * plane, in, t4, sink);
+    float conf[NC];
+    bool live[NC];
     bool any_live = false;
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
+    for (int k = 0; k < NC; ++k) {
         conf[k] = sigmoid_ref(t4[k]);
-        live[k] = in && (conf[k] > p.thr);
+        live[k] = in[k] && (conf[k] > p.thr);
         any_live |= live[k];
     }
 
-    // --- class sweep: running max (first index wins) and softmax denominator -----------------
-    float m[VEC], s[VEC];
-    int arg[VEC];
+    // GATED variant (STREAM == false): class and box planes are fetched only where a cell can still
+    // pass -- per lane for the 128-bit path (one load spans the lane's 4 cells), per cell otherwise.
+    bool want[NC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) { m[k] = -INFINITY; s[k] = 0.f; arg[k] = 0; }
+    for (int k = 0; k < NC; ++k) want[k] = STREAM ? in[k] : (VEC == 4 ? (in[k] && any_live) : live[k]);
+
+    // --- class sweep: running max (first index wins) and softmax denominator -----------------
+    float m[NC], s[NC];
+    int arg[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) { m[k] = -INFINITY; s[k] = 0.f; arg[k] = 0; }
 
     const float* cls = base + 5 * plane;
     int c = 0;
     for (; c + U <= C; c += U) {
-        float v[U][VEC];
+        float v[U][NC];
 #pragma unroll
-        for (int u = 0; u < U; ++u) load_row<VEC>(cls + (size_t)(c + u) * plane, in, v[u]);
+        for (int u = 0; u < U; ++u) load_row<VEC, STREAM>(cls + (size_t)(c + u) * plane, want, v[u], sink);
         if (any_live) {
             float w[U];
             if constexpr (HAS_IDF) {
@@ -115,7 +144,7 @@ __device__ __forceinline__ void decode_filter_task(const DecodeParams& p, const 
                 for (int u = 0; u < U; ++u) w[u] = __ldg(p.idf + c + u);
             }
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) {
+            for (int k = 0; k < NC; ++k) {
                 if (live[k]) {
                     float x[U];
                     const float m_old = m[k];
@@ -141,12 +170,12 @@ __device__ __forceinline__ void decode_filter_task(const DecodeParams& p, const 
         }
     }
     for (; c < C; ++c) {  // tail classes (C % U)
-        float v[VEC];
-        load_row<VEC>(cls + (size_t)c * plane, in, v);
+        float v[NC];
+        load_row<VEC, STREAM>(cls + (size_t)c * plane, want, v, sink);
         if (any_live) {
             const float w = HAS_IDF ? __ldg(p.idf + c) : 1.0f;
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) {
+            for (int k = 0; k < NC; ++k) {
                 if (live[k]) {
                     const float x = HAS_IDF ? __fmul_rn(w, v[k]) : v[k];
                     const float m_old = m[k];
@@ -161,18 +190,20 @@ __device__ __forceinline__ void decode_filter_task(const DecodeParams& p, const 
     }
 
     // --- box planes (last chunk of the stream) ------------------------------------------------
-    float tb[4][VEC];
+    float tb[4][NC];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) load_row<VEC>(base + (size_t)u * plane, in, tb[u]);
+    for (int u = 0; u < 4; ++u) load_row<VEC, STREAM>(base + (size_t)u * plane, want, tb[u], sink);
+    // never true for finite thresholds; keeps every load above architecturally visible
+    if (STREAM && sink == 0x9e3779b9u && p.thr < -3.0e38f) atomicOr(p.status, (int)sink);
 
     // --- threshold + compaction ----------------------------------------------------------------
-    float score[VEC];
-    bool pass[VEC];
-    unsigned ballots[VEC];
+    float score[NC];
+    bool pass[NC];
+    unsigned ballots[NC];
     int total = 0;
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
+    for (int k = 0; k < NC; ++k) {
         // max_c softmax = exp(0)/sum ; max_c sigmoid = sigmoid(max logit)
         float best = 0.f;
         if (live[k]) best = SOFTMAX ? __fdiv_rn(1.0f, s[k]) : sigmoid_ref(m[k]);
@@ -189,11 +220,11 @@ __device__ __forceinline__ void decode_filter_task(const DecodeParams& p, const 
 
     int before = 0;
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
+    for (int k = 0; k < NC; ++k) {
         if (pass[k]) {
             const int slot = slot0 + before + __popc(ballots[k] & lt);
             if (slot < p.cap) {
-                const int hw = hw0 + k;
+                const int hw = hw0 + k * kStep;
                 const int gy_i = hw / sc.grid;
                 const int gx_i = hw - gy_i * sc.grid;
                 // cxypwh[:, :2] = (idx + 0.5) / in_w   (yolo_forw.py:104-107)
@@ -219,8 +250,8 @@ __device__ __forceinline__ void decode_filter_task(const DecodeParams& p, const 
     }
 }
 
-template <bool SOFTMAX, bool HAS_IDF>
-__global__ void __launch_bounds__(128, 8)
+template <bool SOFTMAX, bool HAS_IDF, bool STREAM>
+__global__ void __launch_bounds__(128, DF_MINB)
 k_decode_filter(const __grid_constant__ DecodeParams p) {
     const int lane = threadIdx.x & 31;
     const int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -236,21 +267,195 @@ k_decode_filter(const __grid_constant__ DecodeParams p) {
     const int a = ba % p.A;
     const int b = ba / p.A;
     if (sc.vec == 4)
-        decode_filter_task<4, SOFTMAX, HAS_IDF, 4>(p, sc, b, a, tile, lane);
+        decode_filter_task<4, SOFTMAX, HAS_IDF, DF_U, STREAM>(p, sc, b, a, tile, lane);
     else
-        decode_filter_task<1, SOFTMAX, HAS_IDF, 8>(p, sc, b, a, tile, lane);
+        decode_filter_task<1, SOFTMAX, HAS_IDF, 8, STREAM>(p, sc, b, a, tile, lane);
 }
 
-int launch_decode_filter(const DecodeParams& p, bool softmax, cudaStream_t stream) {
+template <bool STREAM>
+static void launch_df(const DecodeParams& p, bool softmax, bool idf, int blocks, int threads, cudaStream_t stream) {
+    if (softmax) {
+        if (idf) k_decode_filter<true, true, STREAM><<<blocks, threads, 0, stream>>>(p);
+        else     k_decode_filter<true, false, STREAM><<<blocks, threads, 0, stream>>>(p);
+    } else {
+        if (idf) k_decode_filter<false, true, STREAM><<<blocks, threads, 0, stream>>>(p);
+        else     k_decode_filter<false, false, STREAM><<<blocks, threads, 0, stream>>>(p);
+    }
+}
+
+// gate = 0: every byte of the head tensors is read (coalesced stream, input independent);
+// gate = 1: class / box planes are only fetched for lanes that hold a live cell (sector gathers).
+int launch_decode_filter(const DecodeParams& p, bool softmax, int gate, cudaStream_t stream) {
     const int warps_per_block = 4;
     const int blocks = cdiv(p.total_tasks, warps_per_block);
     const bool idf = p.idf != nullptr;
+    if (gate) launch_df<false>(p, softmax, idf, blocks, 32 * warps_per_block, stream);
+    else      launch_df<true>(p, softmax, idf, blocks, 32 * warps_per_block, stream);
+    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused decode + filter, TMA bulk-copy variant (the default for heads whose rows are 16 B aligned)
+// ------------------------------------------------------------------------------------------
+// One CTA owns 128 consecutive cells of one (scale, b, a).  Its (5+C) plane-row segments (512 B each)
+// are pulled into shared memory by cp.async.bulk copies that complete on one mbarrier, so a CTA has
+// its whole tile (43.5 KB for COCO) in flight at once and the SM keeps ~5 tiles = ~200 KB
+// outstanding -- far more than the ~45 KB the HBM latency-bandwidth product asks for -- without
+// holding the data in registers.  Threads then work cell-per-thread out of shared memory: a cell
+// whose objectness cannot pass the threshold costs one sigmoid, a live cell runs the exact
+// two-pass softmax (max, then sum of exp) like the reference.  Every byte of the head tensors is
+// fetched exactly once whatever the input looks like.
+// Scales whose plane rows are not 16 B aligned (odd grids: 13, 19, ...) run the register path
+// (decode_filter_task<VEC=1>) inside the same launch.
+static constexpr int kBulkCells = 128;
+
+struct BulkParams {
+    DecodeParams d;
+    int cta_begin[B200_MAX_SCALES + 1];
+    int bulk[B200_MAX_SCALES];        // 1: bulk-copy CTAs, 0: register-path CTAs (4 warp tasks each)
+    int tiles[B200_MAX_SCALES];       // bulk: 128-cell tiles per (b, a)
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <bool SOFTMAX, bool HAS_IDF>
+__global__ void __launch_bounds__(kBulkCells)
+k_decode_filter_bulk(const __grid_constant__ BulkParams q) {
+    extern __shared__ __align__(128) float tile[];       // [(5+C)][128]
+    __shared__ __align__(8) unsigned long long bar;
+    const DecodeParams& p = q.d;
+    const int tid = threadIdx.x, lane = tid & 31;
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < B200_MAX_SCALES; ++i)
+        if (i < p.num_scales && (int)blockIdx.x >= q.cta_begin[i]) s = i;
+    const ScaleDev& sc = p.sc[s];
+    const int local = blockIdx.x - q.cta_begin[s];
+    if (!q.bulk[s]) {
+        const int task = local * 4 + (tid >> 5);
+        if (task >= p.B * p.A * sc.tiles) return;
+        const int t = task % sc.tiles, ba = task / sc.tiles;
+        decode_filter_task<1, SOFTMAX, HAS_IDF, 8, true>(p, sc, ba / p.A, ba % p.A, t, lane);
+        return;
+    }
+    const int tl = local % q.tiles[s];
+    const int ba = local / q.tiles[s];
+    const int a = ba % p.A, b = ba / p.A;
+    const int C = p.C, CH = 5 + C;
+    const int cell0 = tl * kBulkCells;
+    const int ncell = min(kBulkCells, sc.hw - cell0);
+    const unsigned row_bytes = (unsigned)ncell * 4u;
+    const float* base = sc.head + ((size_t)(b * p.A + a) * (size_t)CH) * (size_t)sc.hw + (size_t)cell0;
+    const unsigned bar_a = smem_u32(&bar);
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid < 32) {
+        if (tid == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(row_bytes * (unsigned)CH) : "memory");
+        for (int c = lane; c < CH; c += 32) {
+            const unsigned dst = smem_u32(tile + c * kBulkCells);
+            const float* src = base + (size_t)c * (size_t)sc.hw;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(src), "r"(row_bytes), "r"(bar_a) : "memory");
+        }
+    }
+    {   // wait for the tile (phase 0)
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(bar_a) : "memory");
+    }
+
+    // ---- cell per thread -------------------------------------------------------------------------
+    const bool in = tid < ncell;
+    float conf = 0.f, score = 0.f;
+    int arg = 0;
+    bool pass = false;
+    if (in) {
+        conf = sigmoid_ref(tile[4 * kBulkCells + tid]);
+        if (conf > p.thr) {                                   // score = conf * maxp <= conf
+            float m = -INFINITY;
+            for (int c = 0; c < C; ++c) {
+                const float x = HAS_IDF ? __fmul_rn(__ldg(p.idf + c), tile[(5 + c) * kBulkCells + tid])
+                                        : tile[(5 + c) * kBulkCells + tid];
+                if (x > m) { m = x; arg = c; }                // first maximum wins
+            }
+            float best;
+            if (SOFTMAX) {
+                float sum = 0.f;
+                for (int c = 0; c < C; ++c) {
+                    const float x = HAS_IDF ? __fmul_rn(__ldg(p.idf + c), tile[(5 + c) * kBulkCells + tid])
+                                            : tile[(5 + c) * kBulkCells + tid];
+                    sum = __fadd_rn(sum, ex2_approx(__fmul_rn(__fsub_rn(x, m), kLog2e)));
+                }
+                best = __fdiv_rn(1.0f, sum);                  // max_c softmax = exp(0) / sum
+            } else {
+                best = sigmoid_ref(m);
+            }
+            score = __fmul_rn(conf, best);                    // test_one_epoch.py:25
+            pass = score > p.thr;                             // :26
+        }
+    }
+    const unsigned bal = __ballot_sync(kFullMask, pass);
+    if (bal == 0u) return;
+    int slot0 = 0;
+    if (lane == 0) slot0 = atomicAdd(p.count + b, __popc(bal));
+    slot0 = __shfl_sync(kFullMask, slot0, 0);
+    if (!pass) return;
+    const int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
+    if (slot >= p.cap) { atomicOr(p.status, 1); return; }
+    const int hw = cell0 + tid;
+    const int gy_i = hw / sc.grid, gx_i = hw - gy_i * sc.grid;
+    const float cx = __fdiv_rn((float)gx_i + 0.5f, sc.inw), cy = __fdiv_rn((float)gy_i + 0.5f, sc.inw);
+    const float bx = __fmul_rn(__fsub_rn(__fadd_rn(sigmoid_ref(tile[0 * kBulkCells + tid]), __fmul_rn(cx, sc.inw)), 0.5f), sc.stride);
+    const float by = __fmul_rn(__fsub_rn(__fadd_rn(sigmoid_ref(tile[1 * kBulkCells + tid]), __fmul_rn(cy, sc.inw)), 0.5f), sc.stride);
+    const float bw = __fmul_rn(__fmul_rn(__fmul_rn(expf(tile[2 * kBulkCells + tid]), sc.anc[a][0]), sc.inw), sc.stride);
+    const float bh = __fmul_rn(__fmul_rn(__fmul_rn(expf(tile[3 * kBulkCells + tid]), sc.anc[a][1]), sc.inw), sc.stride);
+    const Box bb = abs_coord(bx, by, bw, bh);
+    float4* d4 = reinterpret_cast<float4*>(p.slab + (size_t)b * (size_t)p.cap + (size_t)slot);
+    d4[0] = make_float4(bb.x1, bb.y1, bb.x2, bb.y2);
+    d4[1] = make_float4(score, __int_as_float(arg), __int_as_float(sc.anchor_off + hw * p.A + a), 0.f);
+}
+
+// returns B200_OK, or 1 when the tile does not fit in shared memory (caller falls back)
+int launch_decode_filter_bulk(const DecodeParams& p, bool softmax, cudaStream_t stream) {
+    const size_t smem = (size_t)(5 + p.C) * kBulkCells * sizeof(float);
+    if (smem > 100 * 1024) return 1;
+    BulkParams q;
+    q.d = p;
+    int cta = 0;
+    bool any_bulk = false;
+    for (int s = 0; s < p.num_scales; ++s) {
+        q.cta_begin[s] = cta;
+        q.bulk[s] = p.sc[s].vec == 4 ? 1 : 0;
+        q.tiles[s] = cdiv(p.sc[s].hw, kBulkCells);
+        if (q.bulk[s]) { cta += p.B * p.A * q.tiles[s]; any_bulk = true; }
+        else           cta += cdiv(p.B * p.A * p.sc[s].tiles, 4);
+    }
+    for (int s = p.num_scales; s <= B200_MAX_SCALES; ++s) q.cta_begin[s] = cta;
+    if (!any_bulk) return 1;
+    const bool idf = p.idf != nullptr;
+    static size_t attr[4] = {0, 0, 0, 0};
+    const int which = (softmax ? 2 : 0) + (idf ? 1 : 0);
+    if (smem > 48 * 1024 && smem > attr[which]) {
+        cudaError_t e;
+        if (softmax) e = idf ? cudaFuncSetAttribute(k_decode_filter_bulk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                             : cudaFuncSetAttribute(k_decode_filter_bulk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        else         e = idf ? cudaFuncSetAttribute(k_decode_filter_bulk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                             : cudaFuncSetAttribute(k_decode_filter_bulk<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return B200_ERR_CUDA;
+        attr[which] = smem;
+    }
     if (softmax) {
-        if (idf) k_decode_filter<true, true><<<blocks, 32 * warps_per_block, 0, stream>>>(p);
-        else     k_decode_filter<true, false><<<blocks, 32 * warps_per_block, 0, stream>>>(p);
+        if (idf) k_decode_filter_bulk<true, true><<<cta, kBulkCells, smem, stream>>>(q);
+        else     k_decode_filter_bulk<true, false><<<cta, kBulkCells, smem, stream>>>(q);
     } else {
-        if (idf) k_decode_filter<false, true><<<blocks, 32 * warps_per_block, 0, stream>>>(p);
-        else     k_decode_filter<false, false><<<blocks, 32 * warps_per_block, 0, stream>>>(p);
+        if (idf) k_decode_filter_bulk<false, true><<<cta, kBulkCells, smem, stream>>>(q);
+        else     k_decode_filter_bulk<false, false><<<cta, kBulkCells, smem, stream>>>(q);
     }
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }

@@ -19,7 +19,7 @@ struct ScaleDev {
     int grid;           // W == H
     int hw;             // grid*grid
     int vec;            // cells per lane: 4 when every plane row is 16 B aligned, else 1
-    int tiles;          // warp tiles per (b, a) = cdiv(hw, 32*vec)
+    int tiles;          // warp tiles per (b, a) = cdiv(hw, 128): 32 lanes x 4 cells
     int task_begin;     // first warp task of this scale
     int anchor_off;     // flat anchor index of (h=0,w=0,a=0) of this scale
     float inw;          // (float)grid                       (yolo_forw.py:116)
