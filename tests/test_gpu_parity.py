@@ -317,3 +317,33 @@ def test_rpn_filter(shape, bsz, pre, post, strategy):
         assert k == len(want)
         np.testing.assert_array_equal(index[i, :k].cpu().numpy(), i1[want])
         np.testing.assert_array_equal(boxes[i, :k].cpu().numpy(), b1.numpy()[want])
+
+
+@pytest.mark.parametrize("name", ["c1_416_idf", "c2_608_b4", "odd_grid_352", "lvis_96_a6", "tiny_sigmoid"])
+def test_decode_variants_agree(name):
+    """The three fetch strategies of the fused decode kernel (gated / stream / TMA bulk) must give the
+    same candidates: identical anchor sets and labels, values equal up to the softmax summation order."""
+    from object_detectors_b200 import _lib
+    ops = _ops()
+    lib = _lib.load()
+    heads, b, img, c, anchors, idf, softmax = _case(name)
+    gh = _gpu_heads(heads)
+    gi = None if idf is None else idf.cuda()
+    outs = []
+    try:
+        for variant in (_lib.DECODE_GATED, _lib.DECODE_STREAM, _lib.DECODE_BULK):
+            assert lib.b200_set_decode_variant(variant) == 0
+            o = ops.yolo_decode_filter(gh, anchors, img, c, gi, softmax, 0.1)
+            torch.cuda.synchronize()
+            outs.append({k: v.clone() for k, v in o.items()})
+    finally:
+        lib.b200_set_decode_variant(_lib.DECODE_GATED)
+    ref = outs[0]
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o["count"].cpu().numpy(), ref["count"].cpu().numpy())
+        for i in range(b):
+            n = int(ref["count"][i])
+            np.testing.assert_array_equal(o["anchor"][i, :n].cpu().numpy(), ref["anchor"][i, :n].cpu().numpy())
+            np.testing.assert_array_equal(o["label"][i, :n].cpu().numpy(), ref["label"][i, :n].cpu().numpy())
+            np.testing.assert_array_equal(o["box"][i, :n].cpu().numpy(), ref["box"][i, :n].cpu().numpy())
+            _close_score(o["score"][i, :n].cpu().numpy(), ref["score"][i, :n].cpu().numpy())
