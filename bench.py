@@ -46,6 +46,18 @@ CONF_THR, NMS_THR = 0.1, 0.6
 MAX_DET = 256          # kept-detection capacity per image in the exchanged message
 CAPACITY = 4096        # candidate slab rows per image (overflow is reported, never silent)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_decode_filter launch on this workload, from the
+# `ncu --set full` captures summarised in profiles/r01_kernels_gated.txt / r01_decode_stream.txt
+NCU_TRAFFIC_BYTES = {"gated": 168146944 + 8370432, "stream": 495031552 + 14940160, "bulk": None}
+ROOFLINE_NOTE = {
+    "gated": "default variant: reads the objectness plane of every cell but class/box planes only for lanes that "
+             "hold a cell with sigmoid(obj) > conf_thr (score <= conf), so DRAM traffic is input dependent and below "
+             "the algorithmic bytes; kernel_ms is measured while the NMS kernels of other steps overlap it "
+             "(3-stream software pipeline). `stream_variant` gives the input-independent streaming kernel.",
+    "stream": "every byte of the head tensors is read once (traffic == algorithmic bytes)",
+    "bulk": "TMA bulk-copy staging, every byte read once",
+}
+
 
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -262,6 +274,43 @@ def run_b200(args):
     kept = int(plan.det_count.sum())
     cands = int(plan.cand_count.sum())
 
+    # ---- the input-independent streaming variant of the decode kernel, same loop, for the record ----
+    stream_variant = None
+    if args.variant == "gated":
+        lib.b200_set_decode_variant(1)
+        sv_steps = min(args.steps, 400)
+        fence_in()
+        for i in range(10):
+            step(i)
+        fence_out()
+        torch.cuda.synchronize()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(sv_steps)]
+        for a, b in ev2:
+            a.record(); b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        fence_in()
+        for i in range(sv_steps):
+            lib.b200_debug_set_decode_events(C.c_void_p(ev2[i][0].cuda_event), C.c_void_p(ev2[i][1].cuda_event))
+            step(i)
+        lib.b200_debug_set_decode_events(None, None)
+        fence_out()
+        s1.record()
+        torch.cuda.synchronize()
+        lib.b200_set_decode_variant(0)
+        sv_ms = s0.elapsed_time(s1)
+        sv_k = float(np.mean([a.elapsed_time(b) for a, b in ev2]))
+        t = torch.tensor([sv_ms, sv_k], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sv_ms, sv_k = float(t[0]), float(t[1])
+        stream_variant = {"value": world * BATCH * sv_steps / (sv_ms * 1e-3), "unit": "images/s", "steps": sv_steps,
+                          "kernel_ms": sv_k, "achieved_GBs": algo_bytes / (sv_k * 1e-3) / 1e9,
+                          "traffic": NCU_TRAFFIC_BYTES["stream"]}
+
     # ---- e2e through the host-buffer entry point: H2D of every head tensor + D2H of detections --
     heads_pin = [torch.from_numpy(h).pin_memory() for h in heads_np]
     idf_host = load_idf()
@@ -306,8 +355,9 @@ def run_b200(args):
                        "candidates_per_step": cands, "kept_per_step": kept, "streams": n_streams, "decode_variant": args.variant,
                        "exchange": "nccl all_gather of fixed-capacity kept lists" if world > 1 else "none (1 GPU)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_decode_filter", "kernel_ms": k_ms,
-                         "algorithmic_bytes": algo_bytes, "peak_source": peak_src},
+                         "traffic": NCU_TRAFFIC_BYTES[args.variant], "kernel": "k_decode_filter (" + args.variant + ")",
+                         "kernel_ms": k_ms, "algorithmic_bytes": algo_bytes, "peak_source": peak_src,
+                         "note": ROOFLINE_NOTE[args.variant]},
             "cpu_baseline": {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": "16 images of the same 608/COCO workload, 3 timed passes, oracle port "
                                        "(torch CPU ops, all host threads)"},
@@ -315,6 +365,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": args.steps * (4 + (1 if world > 1 else 0)),
             "clocks": clocks,
+            "stream_variant": stream_variant,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

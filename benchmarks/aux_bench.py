@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Device timings of the other BASELINE.json configurations (C3 LVIS decode+NMS, C4 target matching,
+C5 RPN proposal filter).  These are parity-test shapes, not bench.py lines; the numbers go into
+DESIGN.md / profiles/.  One JSON line per configuration.
+
+    python benchmarks/aux_bench.py [--reps 20]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from object_detectors_b200 import ops, synthetic as syn  # noqa: E402
+
+HBM_GBS = 6534.1
+try:
+    HBM_GBS = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+LANE_OPS_PEAK = 148 * 4 * 32 * 1.965e9      # lane-instructions / s at the max SM clock
+
+
+def timeit(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def c3_lvis(reps, batch=8):
+    # LVIS-1203, 6 anchors / scale, 608: 219.8 MB per image -> batch 8 = 1.76 GB (C3 is quoted at b32)
+    heads = [torch.randn((batch, 6 * 1208, g, g), device="cuda") for g in (19, 38, 76)]
+    for h in heads:
+        h[:, 4::1208] = h[:, 4::1208] * 1.5 - 6.0
+    idf = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "idf_lvis_smooth.npy"))).cuda()
+    plan = ops.YoloPostprocess([19, 38, 76], batch, syn.LVIS_ANCHORS, 608, 1203, True, 0.1, 0.6, ops.NMS_MAJORITY,
+                               4096, 256, "cuda")
+    ms = timeit(lambda: plan(heads, idf), reps)
+    plan.check_status()
+    nbytes = sum(h.numel() * 4 for h in heads)
+    return {"config": "C3 YOLOv3-608 LVIS-1203 A=6 decode+filter+nms_majority", "batch": batch, "ms": ms,
+            "images_per_s": batch / ms * 1e3, "algorithmic_GBs": nbytes / ms / 1e6, "hbm_frac": nbytes / ms / 1e6 / HBM_GBS,
+            "candidates": int(plan.cand_count.sum()), "kept": int(plan.det_count.sum())}
+
+
+def c4_match(reps, batch=64, max_gt=100):
+    from oracle import yolo_ref
+    cx, _ = yolo_ref.grid_table(syn.COCO_ANCHORS, 608, (19, 38, 76))
+    targets = syn.gt_targets(77, batch, 80, max_gt=max_gt)
+    gt = np.zeros((batch, max_gt, 4), np.float32)
+    cnt = np.zeros((batch,), np.int32)
+    for i, t in enumerate(targets):
+        cnt[i] = t["bbox"].shape[0]
+        gt[i, :cnt[i]] = t["bbox"]
+    g, c, a = torch.from_numpy(gt).cuda(), torch.from_numpy(cnt).cuda(), cx.cuda()
+    out = []
+    for kind, name, ops_per_pair in ((0, "IoU", 12), (1, "GIoU", 23)):
+        ms = timeit(lambda: ops.iou_match(g, c, a, kind, 0.5), reps)
+        pairs = int(cnt.sum()) * a.shape[0]
+        out.append({"config": f"C4 target matching {name}, b{batch}, M<=100, N=22743", "ms": ms, "pairs": pairs,
+                    "pairs_per_s": pairs / ms * 1e3, "images_per_s": batch / ms * 1e3,
+                    "sm_issue_frac": pairs * ops_per_pair / (ms * 1e-3) / LANE_OPS_PEAK})
+    return out
+
+
+def c5_rpn(reps, batch=16):
+    obj, deltas, anchors, per_level = syn.rpn_inputs(41, batch, 800, 1344)
+    o, d, a = torch.from_numpy(obj).cuda(), torch.from_numpy(deltas).cuda(), torch.from_numpy(anchors).cuda()
+    hw = torch.tensor([[800.0, 1333.0]] * batch).cuda()
+    out = []
+    for pre in (2000, 1000):
+        for mode, name in ((ops.NMS_TV_CLASS, "vanilla"), (ops.NMS_TV_TRICK, "coordinate_trick")):
+            ms = timeit(lambda: ops.rpn_filter(o, d, a, per_level, hw, pre, pre, 0.7, 0.0, 1e-3, mode), reps)
+            b, s, i, c = ops.rpn_filter(o, d, a, per_level, hw, pre, pre, 0.7, 0.0, 1e-3, mode)
+            out.append({"config": f"C5 RPN filter 800x1344 b{batch} pre/post={pre} {name}", "ms": ms,
+                        "images_per_s": batch / ms * 1e3, "proposals_kept": int(c.sum()),
+                        "objectness_GBs": o.numel() * 4 / ms / 1e6})
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args()
+    rows = [c3_lvis(max(args.reps // 4, 3))] + c4_match(args.reps) + c5_rpn(args.reps)
+    for r in rows:
+        print(json.dumps(r), flush=True)
+
+
+if __name__ == "__main__":
+    main()
