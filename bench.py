@@ -48,9 +48,16 @@ CAPACITY = 4096        # candidate slab rows per image (overflow is reported, ne
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_decode_filter launch on this workload, from the
 # `ncu --set full` captures summarised in profiles/r01_kernels_gated.txt / r01_decode_stream.txt
-NCU_TRAFFIC_BYTES = {"gated": 168146944 + 8370432, "stream": 495031552 + 14940160, "bulk": None}
+NCU_TRAFFIC_BYTES = {"ring": None, "gated": 168146944 + 8370432, "stream": 495031552 + 14940160, "bulk": None}
 ROOFLINE_NOTE = {
-    "gated": "default variant: reads the objectness plane of every cell but class/box planes only for lanes that "
+    "ring": "default variant: persistent TMA ring (cp.async.bulk.tensor.2d + mbarrier), every byte of the head tensors "
+            "is read exactly once whatever the input (traffic == algorithmic bytes).  All durations are CUDA events on "
+            "the launching streams inside the timed region.  Decode kernels of neighbouring steps overlap on the "
+            "device, so kernel_ms = union of the decode kernels' [start, end] intervals / launches (the time the decode "
+            "stage occupied per launch; `achieved` uses it); kernel_ms_launch_to_end is the plain per-launch "
+            "start-to-end mean, which counts the shared interval twice; step_rate_GBs = algorithmic bytes per step "
+            "period; isolated = the same kernel alone on an idle GPU",
+    "gated": "reads the objectness plane of every cell but class/box planes only for lanes that "
              "hold a cell with sigmoid(obj) > conf_thr (score <= conf), so DRAM traffic is input dependent and below "
              "the algorithmic bytes; kernel_ms is measured while the NMS kernels of other steps overlap it "
              "(3-stream software pipeline). `stream_variant` gives the input-independent streaming kernel.",
@@ -193,7 +200,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    lib.b200_set_decode_variant({"gated": 0, "stream": 1, "bulk": 2}[args.variant])
+    VARIANTS = {"gated": 0, "stream": 1, "bulk": 2, "ring": 3}
+    lib.b200_set_decode_variant(VARIANTS[args.variant])
 
     heads_np = make_heads(1000 + rank, BATCH)
     heads = [torch.from_numpy(h).to(dev) for h in heads_np]
@@ -212,7 +220,7 @@ def run_b200(args):
     gathered = [torch.empty((world * msg_len,), dtype=torch.float32, device=dev) for _ in range(n_streams)] if world > 1 else None
 
     def step(i):
-        k = i % n_streams
+        k = i % n_streams      # n_streams is rebound to 1 for the isolated-kernel measurement
         with torch.cuda.stream(streams[k]):
             det, keep, anchor, dcnt, ccnt = plans[k](heads, idf)
             if world > 1:
@@ -229,87 +237,83 @@ def run_b200(args):
         for st in streams:
             torch.cuda.current_stream().wait_stream(st)
 
-    fence_in()
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    fence_out()
-    torch.cuda.synchronize()
-    for pl in plans:
-        pl.check_status()
-
-    # per-step events around the fused decode+filter kernel (roofline numerator)
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a, b in k_ev:
-        a.record(); b.record()          # materialise the cudaEvent_t handles
-    torch.cuda.synchronize()
+    def timed_loop(steps, warm, sample_clocks=False):
+        """`warm` untimed steps, then exactly `steps` timed ones bracketed by barrier + synchronize; returns
+        (total ms, mean decode-kernel ms from per-step CUDA events on the launching stream), max over ranks."""
+        fence_in()
+        for i in range(warm):
+            step(i)
+        fence_out()
+        torch.cuda.synchronize()
+        for pl in plans:
+            pl.check_status()
+        k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in k_ev:
+            a.record(); b.record()          # materialise the cudaEvent_t handles
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sample_clocks and rank == 0:
+            sampler.start()
+        t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin.record()
+        fence_in()
+        for i in range(steps):
+            lib.b200_debug_set_decode_events(C.c_void_p(k_ev[i][0].cuda_event), C.c_void_p(k_ev[i][1].cuda_event))
+            step(i)
+        lib.b200_debug_set_decode_events(None, None)
+        fence_out()
+        t_end.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = t_begin.elapsed_time(t_end)
+        k = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+        # Decode kernels of neighbouring steps run concurrently (that is what keeps HBM busy while a single
+        # launch winds down), so launch-to-end times double count the shared interval.  busy = length of the
+        # UNION of the decode kernels' [start, end] intervals / launches: the time the decode stage really
+        # occupied per launch.
+        iv = sorted((t_begin.elapsed_time(a), t_begin.elapsed_time(b)) for a, b in k_ev)
+        busy, cur_a, cur_b = 0.0, iv[0][0], iv[0][1]
+        for a_, b_ in iv[1:]:
+            if a_ > cur_b:
+                busy += cur_b - cur_a
+                cur_a, cur_b = a_, b_
+            else:
+                cur_b = max(cur_b, b_)
+        busy = (busy + cur_b - cur_a) / steps
+        t = torch.tensor([ms, k, busy], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for pl in plans:
+            pl.check_status()
+        return float(t[0]), float(t[1]), float(t[2])
 
     sampler = ClockSampler(local)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_begin.record()
-    fence_in()
-    for i in range(args.steps):
-        lib.b200_debug_set_decode_events(C.c_void_p(k_ev[i][0].cuda_event), C.c_void_p(k_ev[i][1].cuda_event))
-        step(i)
-    lib.b200_debug_set_decode_events(None, None)
-    fence_out()
-    t_end.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    ms_total, k_ms, k_busy = timed_loop(args.steps, max(args.warmup, 3), sample_clocks=True)
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = t_begin.elapsed_time(t_end)
-    k_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
-    t = torch.tensor([ms_total, k_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, k_ms = float(t[0]), float(t[1])
-    for pl in plans:
-        pl.check_status()
     plan = plans[0]
     kept = int(plan.det_count.sum())
     cands = int(plan.cand_count.sum())
 
-    # ---- the input-independent streaming variant of the decode kernel, same loop, for the record ----
-    stream_variant = None
-    if args.variant == "gated":
-        lib.b200_set_decode_variant(1)
-        sv_steps = min(args.steps, 400)
-        fence_in()
-        for i in range(10):
-            step(i)
-        fence_out()
-        torch.cuda.synchronize()
-        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(sv_steps)]
-        for a, b in ev2:
-            a.record(); b.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        fence_in()
-        for i in range(sv_steps):
-            lib.b200_debug_set_decode_events(C.c_void_p(ev2[i][0].cuda_event), C.c_void_p(ev2[i][1].cuda_event))
-            step(i)
-        lib.b200_debug_set_decode_events(None, None)
-        fence_out()
-        s1.record()
-        torch.cuda.synchronize()
-        lib.b200_set_decode_variant(0)
-        sv_ms = s0.elapsed_time(s1)
-        sv_k = float(np.mean([a.elapsed_time(b) for a, b in ev2]))
-        t = torch.tensor([sv_ms, sv_k], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sv_ms, sv_k = float(t[0]), float(t[1])
-        stream_variant = {"value": world * BATCH * sv_steps / (sv_ms * 1e-3), "unit": "images/s", "steps": sv_steps,
-                          "kernel_ms": sv_k, "achieved_GBs": algo_bytes / (sv_k * 1e-3) / 1e9,
-                          "traffic": NCU_TRAFFIC_BYTES["stream"]}
+    # ---- for the record: the decode kernel alone (one stream, nothing overlapping it), and the other variant ----
+    n_streams_main = n_streams
+    n_streams = 1
+    iso_steps = min(args.steps, 200)
+    iso_ms, iso_k, _ = timed_loop(iso_steps, 5)
+    n_streams = n_streams_main
+    isolated = {"kernel_ms": iso_k, "achieved_GBs": algo_bytes / (iso_k * 1e-3) / 1e9,
+                "note": "same kernel, one stream, no other kernel resident; NMS kernels follow it serially"}
+    other = "gated" if args.variant != "gated" else "ring"
+    lib.b200_set_decode_variant(VARIANTS[other])
+    ov_steps = min(args.steps, 400)
+    ov_ms, ov_k, ov_busy = timed_loop(ov_steps, 10)
+    lib.b200_set_decode_variant(VARIANTS[args.variant])
+    assert int(plans[0].det_count.sum()) == kept and int(plans[0].cand_count.sum()) == cands, "variants disagree"
+    other_variant = {"variant": other, "value": world * BATCH * ov_steps / (ov_ms * 1e-3), "unit": "images/s",
+                     "steps": ov_steps, "kernel_ms": ov_busy, "kernel_ms_launch_to_end": ov_k, "traffic": NCU_TRAFFIC_BYTES[other],
+                     "note": ROOFLINE_NOTE[other]}
 
     # ---- e2e through the host-buffer entry point: H2D of every head tensor + D2H of detections --
     heads_pin = [torch.from_numpy(h).pin_memory() for h in heads_np]
@@ -341,7 +345,7 @@ def run_b200(args):
 
     if rank == 0:
         peak, peak_src = _peaks()
-        achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+        achieved = algo_bytes / (k_busy * 1e-3) / 1e9
         cpu_v, cores, cpu_ts = time_cpu(sample_batch=16, reps=3)
         line = {
             "metric": METRIC, "value": world * BATCH * args.steps / (ms_total * 1e-3), "unit": "images/s",
@@ -356,8 +360,11 @@ def run_b200(args):
                        "exchange": "nccl all_gather of fixed-capacity kept lists" if world > 1 else "none (1 GPU)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES[args.variant], "kernel": "k_decode_filter (" + args.variant + ")",
-                         "kernel_ms": k_ms, "algorithmic_bytes": algo_bytes, "peak_source": peak_src,
-                         "note": ROOFLINE_NOTE[args.variant]},
+                         "kernel_ms": k_busy, "kernel_ms_launch_to_end": k_ms,
+                         "launch_to_end_GBs": algo_bytes / (k_ms * 1e-3) / 1e9,
+                         "algorithmic_bytes": algo_bytes, "peak_source": peak_src,
+                         "step_rate_GBs": algo_bytes / (ms_total / args.steps * 1e-3) / 1e9,
+                         "isolated": isolated, "note": ROOFLINE_NOTE[args.variant]},
             "cpu_baseline": {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": "16 images of the same 608/COCO workload, 3 timed passes, oracle port "
                                        "(torch CPU ops, all host threads)"},
@@ -365,7 +372,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": args.steps * (4 + (1 if world > 1 else 0)),
             "clocks": clocks,
-            "stream_variant": stream_variant,
+            "other_variant": other_variant,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -378,7 +385,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variant", default="gated", choices=["gated", "stream", "bulk"],
+    ap.add_argument("--variant", default="ring", choices=["ring", "gated", "stream", "bulk"],
                     help="fused decode kernel variant (include/b200det.h: B200_DECODE_*)")
     ap.add_argument("--streams", type=int, default=3, help="software pipeline depth (independent plans on own streams)")
     args = ap.parse_args()

@@ -151,16 +151,29 @@ int b200_yolo_postprocess_host(const b200_yolo_layout* layout, const float* cons
  * before and after the fused decode+filter kernel. */
 int b200_debug_set_decode_events(void* ev_begin, void* ev_end);
 
-/* Variants of the fused decode+filter kernel.  All produce identical results; they differ in how the
- * head tensors are fetched (process-wide setting, default B200_DECODE_GATED):
+/* Profiling hook: three more cudaEvent_t (NULL to disable) recorded by the next NMS launches after the
+ * plan, pairs and resolve kernels; with b200_debug_set_decode_events this gives a per-step timeline. */
+int b200_debug_set_timeline(void* after_plan, void* after_pairs, void* after_resolve);
+/* Profiling hook: device buffer int64[segments, 8] that the resolve kernel fills with clock64 stamps at its
+ * phase boundaries (A stage, B fixed point, C vote, D order, E emit, end) + n and K; NULL to disable. */
+int b200_debug_set_resolve_prof(void* buf);
+
+/* Variants of the fused decode+filter kernel.  All produce identical candidates; they differ in how the
+ * head tensors are fetched (process-wide setting, default B200_DECODE_RING):
+ *   RING    persistent CTAs; every warp streams 64-cell tiles through its own shared-memory stages with
+ *           2-D tensor-map TMA (cp.async.bulk.tensor) + mbarrier and sweeps only the cells whose
+ *           objectness can still pass.  Every byte of the head tensors is read exactly once, whatever
+ *           the input looks like: the variant the HBM roofline fraction is quoted for.
+ *   STREAM  register path; every byte is read once with coalesced 128-bit loads.
+ *   BULK    one 128-cell tile per CTA staged by 1-D cp.async.bulk row copies (first TMA prototype).
  *   GATED   register path; the objectness plane is read for every cell, class and box planes only by
  *           lanes that hold a cell whose objectness can still pass the threshold (score <= conf).
- *           DRAM traffic is input dependent (184 MB of the 495 MB batch on the benchmark input).
- *   STREAM  register path; every byte of the head tensors is read once, coalesced 128-bit loads.
- *           Input independent: the variant the HBM roofline fraction is quoted for.
- *   BULK    as STREAM, tiles staged in shared memory by cp.async.bulk (TMA) + mbarrier. */
-enum { B200_DECODE_GATED = 0, B200_DECODE_STREAM = 1, B200_DECODE_BULK = 2 };
+ *           DRAM traffic is input dependent (176 MB of the 495 MB batch on the benchmark input). */
+enum { B200_DECODE_GATED = 0, B200_DECODE_STREAM = 1, B200_DECODE_BULK = 2, B200_DECODE_RING = 3 };
 int b200_set_decode_variant(int variant);
+/* Tuning hook of the RING variant (values <= 0 keep the current setting): warps per CTA (1..8),
+ * shared-memory stages per warp (warps x stages <= 32), persistent CTAs per SM (1..4). */
+int b200_debug_set_ring(int warps, int stages_per_warp, int ctas_per_sm);
 
 /* ------------------------------------------------------------------------------------------
  * NMS on caller-provided boxes, batched over segments (images, or image x level)

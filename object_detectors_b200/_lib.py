@@ -10,7 +10,7 @@ MAX_ANCHORS = 8
 
 NMS_MAJORITY, NMS_TV, NMS_TV_CLASS, NMS_TV_TRICK = 0, 1, 2, 3
 IOU, GIOU, DIOU, CIOU, IOU_TV = 0, 1, 2, 3, 4
-DECODE_GATED, DECODE_STREAM, DECODE_BULK = 0, 1, 2
+DECODE_GATED, DECODE_STREAM, DECODE_BULK, DECODE_RING = 0, 1, 2, 3
 
 LIB_PATH = os.environ.get("B200DET_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc",
                                                          "libb200det.so")
@@ -42,7 +42,10 @@ SIGNATURES = {
                                         _p, _sz, _p]),
     "b200_yolo_postprocess_host": (C.c_int, [_LP, _PP, _p, _f32, _f64, _i32, _i32, _i32, _p, _p, _p, _p]),
     "b200_debug_set_decode_events": (C.c_int, [_p, _p]),
+    "b200_debug_set_timeline": (C.c_int, [_p, _p, _p]),
+    "b200_debug_set_resolve_prof": (C.c_int, [_p]),
     "b200_set_decode_variant": (C.c_int, [C.c_int]),
+    "b200_debug_set_ring": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "b200_nms_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "b200_nms": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _f64, _i32, _p, _p, _p, _p, _sz, _p]),
     "b200_box_iou": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _p, _p]),

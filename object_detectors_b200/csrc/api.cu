@@ -4,11 +4,15 @@
 #include <mutex>
 
 #include "decode.cuh"
+#include "decode_ring.cuh"
 #include "nms.cuh"
 
 namespace b200 {
 int launch_decode_filter(const DecodeParams& p, bool softmax, int gate, cudaStream_t stream);
 int launch_decode_filter_bulk(const DecodeParams& p, bool softmax, cudaStream_t stream);
+int launch_decode_filter_ring(const DecodeParams& p, bool softmax, int* tile_counter, cudaStream_t stream);
+void ring_set_tuning(int warps, int slots_per_warp, int ctas_per_sm);
+void ring_set_tile_cells(int tc);
 int launch_decode_dense(const DecodeParams& p, bool softmax, float* out, cudaStream_t stream);
 int launch_box_iou(const float*, int, const float*, int, int, int, float*, cudaStream_t);
 int launch_box_iou_pair(const float*, const float*, int, int, int, float*, cudaStream_t);
@@ -45,6 +49,7 @@ struct Carver {
 
 struct YoloWs {
     int* count;
+    int* ticket;        // tile ticket counter of the ring decode kernel (directly behind `count`)
     Cand* slab;
     float4* cbox;
     float* cscore;
@@ -62,6 +67,7 @@ size_t yolo_ws_layout(int batch, int cap, void* base, size_t bytes, YoloWs* w) {
     YoloWs& o = w ? *w : tmp;
     const unsigned char* start = c.p;
     o.count = c.take<int>((size_t)batch);
+    o.ticket = c.take<int>(kTicketInts);
     o.slab = c.take<Cand>(T);
     o.cbox = c.take<float4>(T);
     o.cscore = c.take<float>(T);
@@ -91,6 +97,7 @@ static __global__ void k_pack(const float* __restrict__ det, const int* __restri
 }
 }  // namespace b200
 
+namespace b200 { extern cudaEvent_t g_nms_timeline[3]; extern long long* g_resolve_prof; }
 using namespace b200;
 
 extern "C" {
@@ -135,12 +142,29 @@ size_t b200_yolo_workspace_bytes(const b200_yolo_layout* layout, int32_t capacit
 
 // Optional profiling hook (bench.py): events recorded on the call's stream right before / after
 // the fused decode+filter kernel, so its duration can be measured inside a timed region.
-static int g_decode_variant = B200_DECODE_GATED;
+static int g_decode_variant = B200_DECODE_RING;
 int b200_set_decode_variant(int variant) {
-    if (variant < B200_DECODE_GATED || variant > B200_DECODE_BULK) return B200_ERR_INVALID;
+    if (variant < B200_DECODE_GATED || variant > B200_DECODE_RING) return B200_ERR_INVALID;
     g_decode_variant = variant;
     return B200_OK;
 }
+int b200_debug_set_ring(int warps, int stages_per_warp, int ctas_per_sm) {
+    if (ctas_per_sm >= 100) {          // hundreds digit selects the tile: 1xx = 32 cells, otherwise 64
+        ring_set_tile_cells(32);
+        ctas_per_sm -= 100;
+    } else if (ctas_per_sm > 0) {
+        ring_set_tile_cells(64);
+    }
+    ring_set_tuning(warps, stages_per_warp, ctas_per_sm);
+    return B200_OK;
+}
+int b200_debug_set_timeline(void* after_plan, void* after_pairs, void* after_resolve) {
+    b200::g_nms_timeline[0] = static_cast<cudaEvent_t>(after_plan);
+    b200::g_nms_timeline[1] = static_cast<cudaEvent_t>(after_pairs);
+    b200::g_nms_timeline[2] = static_cast<cudaEvent_t>(after_resolve);
+    return B200_OK;
+}
+int b200_debug_set_resolve_prof(void* buf) { b200::g_resolve_prof = static_cast<long long*>(buf); return B200_OK; }
 static void* g_ev_decode_begin = nullptr;
 static void* g_ev_decode_end = nullptr;
 int b200_debug_set_decode_events(void* ev_begin, void* ev_end) {
@@ -160,11 +184,19 @@ static int yolo_run(const b200_yolo_layout* layout, const float* const* heads, c
     p.cap = capacity;
     p.count = count_buf;
     p.status = np.status;
-    B200_CUDA_TRY(cudaMemsetAsync(count_buf, 0, sizeof(int) * (size_t)layout->batch, st));
+    if (count_buf == w.count) {
+        // slab cursors and the ring kernel's ticket counter sit in one block: one memset node
+        B200_CUDA_TRY(cudaMemsetAsync(w.count, 0, (size_t)(reinterpret_cast<unsigned char*>(w.ticket + kTicketInts) -
+                                                           reinterpret_cast<unsigned char*>(w.count)), st));
+    } else {
+        B200_CUDA_TRY(cudaMemsetAsync(count_buf, 0, sizeof(int) * (size_t)layout->batch, st));
+        if (g_decode_variant == B200_DECODE_RING) B200_CUDA_TRY(cudaMemsetAsync(w.ticket, 0, sizeof(int) * kTicketInts, st));
+    }
     if (g_ev_decode_begin) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(g_ev_decode_begin), st));
     int rc2 = 1;
-    if (g_decode_variant == B200_DECODE_BULK) rc2 = launch_decode_filter_bulk(p, layout->softmax != 0, st);
-    if (rc2 == 1)   // not bulk, or the tile does not fit in shared memory
+    if (g_decode_variant == B200_DECODE_RING) rc2 = launch_decode_filter_ring(p, layout->softmax != 0, w.ticket, st);
+    else if (g_decode_variant == B200_DECODE_BULK) rc2 = launch_decode_filter_bulk(p, layout->softmax != 0, st);
+    if (rc2 == 1)   // register path asked for, or the staged tile does not fit in shared memory
         rc2 = launch_decode_filter(p, layout->softmax != 0, g_decode_variant == B200_DECODE_GATED ? 1 : 0, st);
     if (rc2 != B200_OK) return rc2;
     if (g_ev_decode_end) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(g_ev_decode_end), st));

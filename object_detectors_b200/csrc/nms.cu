@@ -23,6 +23,8 @@
 //                applies the majority relabel (helper.py:368-375) and emits.
 //  k_nms_canon   (YOLO stage API only) sorts the unordered candidate slab by flat anchor index and
 //                writes the reference's ascending-anchor candidate list (test_one_epoch.py:27-28).
+#include <stdlib.h>
+
 #include "decode.cuh"
 #include "nms.cuh"
 
@@ -34,12 +36,17 @@ static constexpr int kPlanThreads = 512;
 static constexpr int kPlanTiles = 512;          // tile summaries kept in shared memory (n <= 32768)
 static constexpr int kBins = 128;               // 8 size classes x 16 y bands
 static constexpr int kPairThreads = 256;
-static constexpr int kResolveThreads = 1024;
-static constexpr int kResolveWarps = kResolveThreads / 32;
+#ifndef RESOLVE_MINB
+#define RESOLVE_MINB 2
+#endif
+static constexpr int kResolveMaxThreads = 1024;     // resolve CTAs are launched with g_resolve_threads <= this
+static constexpr int kResolveMaxWarps = kResolveMaxThreads / 32;
+#define kResolveThreads ((int)blockDim.x)
+#define kResolveWarps ((int)(blockDim.x >> 5))
 static constexpr int kKeptSmem = 2048;          // slow path: kept boxes sorted in shared memory
 static constexpr int kVoteFlag = 1 << 30;
 static constexpr int kVoteListCap = 128;
-static constexpr size_t kResolveSmem = 200 * 1024;
+
 
 __device__ __forceinline__ int next_pow2(int n) {
     int p = 1;
@@ -172,6 +179,24 @@ __device__ void bitonic_sort(unsigned long long* key, int* val, int P) {
             __syncthreads();
         }
     }
+}
+
+// exclusive rank of a flag over the CTA (nwarps warps, runtime); `running` accumulates the total
+__device__ __forceinline__ int block_rank_rt(bool flag, int* scratch, int& running, int nwarps) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(kFullMask, flag);
+    if (lane == 0) scratch[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < nwarps; ++w) {
+        const int c = scratch[w];
+        if (w < warp) before += c;
+        total += c;
+    }
+    const int rank = running + before + __popc(bal & ((1u << lane) - 1u));
+    running += total;
+    __syncthreads();
+    return rank;
 }
 
 // exclusive rank of a flag over the CTA (NW warps); `running` accumulates the total
@@ -538,7 +563,6 @@ __device__ __forceinline__ int block_exclusive_scan(int* a, int n, int* scratch)
         if (lane == 31) scratch[warp] = incl;
         __syncthreads();
         int before = 0, total = 0;
-#pragma unroll
         for (int w = 0; w < kResolveWarps; ++w) { const int c = scratch[w]; if (w < warp) before += c; total += c; }
         if (i < n) a[i] = carry + before + incl - v;
         carry += total;
@@ -579,6 +603,7 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
 
     for (int w = tid; w < nw; w += kResolveThreads) { f.Kset[w] = 0ull; f.Rset[w] = 0ull; }
     __syncthreads();
+    if (P.prof && tid == 0) P.prof[seg * 8 + 0] = clock64();
     // ---- A. stage boxes and the non-zero structure of the mask rows --------------------------------
     for (int p = tid; p < n; p += kResolveThreads) {
         const Item it = load_raw<SLAB>(P, off, perm[p], unit);
@@ -606,6 +631,7 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
     __syncthreads();
     const RowReader R{cw, dom, (size_t)P.max_words};
 
+    if (P.prof && tid == 0) P.prof[seg * 8 + 1] = clock64();
     // ---- B. fixed point over bitsets ----------------------------------------------------------------
     int pending;
     do {
@@ -628,6 +654,7 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
         pending = __syncthreads_count(undecided > 0);
     } while (pending > 0);
 
+    if (P.prof && tid == 0) P.prof[seg * 8 + 2] = clock64();
     if (MODE == B200_NMS_MAJORITY) {
         // ---- C. first suppressor + vote (helper.py:368-369), voters gathered per kept box ---------
         for (int p = tid; p <= n; p += kResolveThreads) f.voff[p] = 0;
@@ -690,12 +717,13 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
         __syncthreads();
     }
 
+    if (P.prof && tid == 0) P.prof[seg * 8 + 3] = clock64();
     // ---- D. kept boxes in (score desc, canonical index asc) order ------------------------------------
     int running = 0;
     for (int p0 = 0; p0 < n; p0 += kResolveThreads) {
         const int p = p0 + tid;
         const bool kept = p < n && get_bit(f.Kset, p);
-        const int k = block_rank<kResolveWarps>(kept, f.scan, running);
+        const int k = block_rank_rt(kept, f.scan, running, kResolveWarps);
         if (kept) f.klist[k] = p;
     }
     const int K = running;
@@ -710,6 +738,7 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
     __syncthreads();
     bitonic_sort(skey, sval, Pk);
 
+    if (P.prof && tid == 0) P.prof[seg * 8 + 4] = clock64();
     // ---- E. emit -----------------------------------------------------------------------------------------
     const int Kout = SLAB ? min(K, P.max_det) : K;
     if (SLAB && P.det_keep) {
@@ -764,6 +793,8 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
             if (P.labels_out) P.labels_out[off + t] = lab;
         }
     }
+    if (P.prof && tid == 0) P.prof[seg * 8 + 5] = clock64();
+    if (P.prof && tid == 0) { P.prof[seg * 8 + 6] = n; P.prof[seg * 8 + 7] = K; }
     if (tid == 0) {
         if (SLAB) {
             P.det_count[seg] = Kout;
@@ -787,7 +818,7 @@ __device__ void resolve_slow(const NmsParams& P, int seg, long long off, int n, 
     unsigned long long* Rset = reinterpret_cast<unsigned long long*>(q); q += sizeof(unsigned long long) * P.max_words;
     unsigned long long* skey = reinterpret_cast<unsigned long long*>(q); q += sizeof(unsigned long long) * kKeptSmem;
     int* sval = reinterpret_cast<int*>(q);                               q += sizeof(int) * kKeptSmem;
-    int* sm_vote = reinterpret_cast<int*>(q);                            q += sizeof(int) * kResolveWarps * kVoteListCap;
+    int* sm_vote = reinterpret_cast<int*>(q);                            q += sizeof(int) * kResolveMaxWarps * kVoteListCap;
     int* sm_scan = reinterpret_cast<int*>(q);
     const unsigned long long* dom = P.dom + (size_t)seg * (size_t)P.max_seg * (size_t)P.max_words;
     const int* perm = P.gperm + off;
@@ -819,7 +850,7 @@ __device__ void resolve_slow(const NmsParams& P, int seg, long long off, int n, 
     for (int p0 = 0; p0 < n; p0 += kResolveThreads) {
         const int p = p0 + tid;
         const bool kept = p < n && get_bit(Kset, p);
-        const int k = block_rank<kResolveWarps>(kept, sm_scan, running);
+        const int k = block_rank_rt(kept, sm_scan, running, kResolveWarps);
         if (kept) klist[k] = p;
     }
     const int K = running;
@@ -946,11 +977,11 @@ __device__ void resolve_slow(const NmsParams& P, int seg, long long off, int n, 
 
 __host__ __device__ inline size_t slow_smem_bytes(int max_words) {
     return sizeof(unsigned long long) * 2 * (size_t)max_words + sizeof(unsigned long long) * kKeptSmem +
-           sizeof(int) * kKeptSmem + sizeof(int) * kResolveWarps * kVoteListCap + sizeof(int) * 32;
+           sizeof(int) * kKeptSmem + sizeof(int) * kResolveMaxWarps * kVoteListCap + sizeof(int) * 32;
 }
 
 template <bool SLAB>
-__global__ void __launch_bounds__(kResolveThreads, 1)
+__global__ void __launch_bounds__(kResolveMaxThreads, RESOLVE_MINB)
 k_nms_resolve(const __grid_constant__ NmsParams P, const unsigned smem_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int seg = blockIdx.x;
@@ -1030,6 +1061,10 @@ bool nms_carve_scratch(NmsParams* P, size_t total, size_t segments, size_t max_s
     return true;
 }
 
+// optional profiling events (b200_debug_set_timeline): recorded after plan, pairs and resolve
+cudaEvent_t g_nms_timeline[3] = {nullptr, nullptr, nullptr};
+long long* g_resolve_prof = nullptr;
+
 int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
     if (num_segments <= 0) return B200_OK;
     if (num_segments > 65535) return B200_ERR_INVALID;
@@ -1055,12 +1090,29 @@ int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
     if (cudaMemsetAsync(P.work_count, 0, 2 * sizeof(int), stream) != cudaSuccess) return B200_ERR_CUDA;
     if (P.from_slab) k_nms_plan<true><<<num_segments, kPlanThreads, 0, stream>>>(P);
     else             k_nms_plan<false><<<num_segments, kPlanThreads, 0, stream>>>(P);
+    if (g_nms_timeline[0]) cudaEventRecord(g_nms_timeline[0], stream);
     const int pair_ctas = 8 * sms;                       // 8 x 256 threads per SM, tiles pulled from a queue
     if (P.from_slab) k_nms_pairs<true><<<pair_ctas, kPairThreads, 0, stream>>>(P);
     else             k_nms_pairs<false><<<pair_ctas, kPairThreads, 0, stream>>>(P);
 
+    if (g_nms_timeline[1]) cudaEventRecord(g_nms_timeline[1], stream);
+    P.prof = g_resolve_prof;
+    // Resolve CTAs (one per segment) are latency bound; they are kept small enough (threads, shared memory) to
+    // share an SM with the streaming decode kernel of the next pipeline stage instead of waiting for it.
+    static int resolve_threads = 0;
+    static size_t resolve_smem = 0;
+    if (resolve_threads == 0) {
+        const char* e = getenv("B200_RESOLVE_THREADS");
+        int t = e ? atoi(e) : 1024;
+        if (t < 64 || t > kResolveMaxThreads || (t & 31)) t = 1024;
+        const char* k = getenv("B200_RESOLVE_SMEM_KB");
+        int kb = k ? atoi(k) : 112;
+        if (kb < 16 || kb > 200) kb = 200;
+        resolve_smem = (size_t)kb * 1024;
+        resolve_threads = t;
+    }
     const size_t slow_bytes = slow_smem_bytes(P.max_words);
-    const size_t smem = kResolveSmem > slow_bytes ? kResolveSmem : slow_bytes;
+    const size_t smem = resolve_smem > slow_bytes ? resolve_smem : slow_bytes;
     if (smem > 227 * 1024) return B200_ERR_INVALID;   // max_seg beyond ~1.4M boxes
     static size_t attr_bytes[2] = {0, 0};
     if (smem > attr_bytes[P.from_slab ? 1 : 0]) {
@@ -1070,8 +1122,9 @@ int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
         if (e != cudaSuccess) return B200_ERR_CUDA;
         attr_bytes[P.from_slab ? 1 : 0] = smem;
     }
-    if (P.from_slab) k_nms_resolve<true><<<num_segments, kResolveThreads, smem, stream>>>(P, (unsigned)smem);
-    else             k_nms_resolve<false><<<num_segments, kResolveThreads, smem, stream>>>(P, (unsigned)smem);
+    if (P.from_slab) k_nms_resolve<true><<<num_segments, resolve_threads, smem, stream>>>(P, (unsigned)smem);
+    else             k_nms_resolve<false><<<num_segments, resolve_threads, smem, stream>>>(P, (unsigned)smem);
+    if (g_nms_timeline[2]) cudaEventRecord(g_nms_timeline[2], stream);
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }
 

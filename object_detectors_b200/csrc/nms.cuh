@@ -55,6 +55,7 @@ struct NmsParams {
     int* gsup;                  // [T] first suppressor | vote flag (MAJORITY, slow path)
     int* gklist;                // [T] kept positions (slow path)
     int* gnewlab;               // [T] label of each kept box after the majority vote (slow path)
+    long long* prof;            // debug: [S, 8] clock64 stamps of the resolve phases (nullptr = off)
 };
 
 // scratch bytes needed for T boxes in S segments of at most max_seg boxes each

@@ -321,7 +321,7 @@ def test_rpn_filter(shape, bsz, pre, post, strategy):
 
 @pytest.mark.parametrize("name", ["c1_416_idf", "c2_608_b4", "odd_grid_352", "lvis_96_a6", "tiny_sigmoid"])
 def test_decode_variants_agree(name):
-    """The three fetch strategies of the fused decode kernel (gated / stream / TMA bulk) must give the
+    """The four fetch strategies of the fused decode kernel (gated / stream / TMA bulk / TMA ring) must give the
     same candidates: identical anchor sets and labels, values equal up to the softmax summation order."""
     from object_detectors_b200 import _lib
     ops = _ops()
@@ -331,13 +331,13 @@ def test_decode_variants_agree(name):
     gi = None if idf is None else idf.cuda()
     outs = []
     try:
-        for variant in (_lib.DECODE_GATED, _lib.DECODE_STREAM, _lib.DECODE_BULK):
+        for variant in (_lib.DECODE_GATED, _lib.DECODE_STREAM, _lib.DECODE_BULK, _lib.DECODE_RING):
             assert lib.b200_set_decode_variant(variant) == 0
             o = ops.yolo_decode_filter(gh, anchors, img, c, gi, softmax, 0.1)
             torch.cuda.synchronize()
             outs.append({k: v.clone() for k, v in o.items()})
     finally:
-        lib.b200_set_decode_variant(_lib.DECODE_GATED)
+        lib.b200_set_decode_variant(_lib.DECODE_RING)
     ref = outs[0]
     for o in outs[1:]:
         np.testing.assert_array_equal(o["count"].cpu().numpy(), ref["count"].cpu().numpy())
