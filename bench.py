@@ -47,8 +47,8 @@ MAX_DET = 256          # kept-detection capacity per image in the exchanged mess
 CAPACITY = 4096        # candidate slab rows per image (overflow is reported, never silent)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_decode_filter launch on this workload, from the
-# `ncu --set full` captures summarised in profiles/r01_kernels_gated.txt / r01_decode_stream.txt
-NCU_TRAFFIC_BYTES = {"ring": None, "gated": 168146944 + 8370432, "stream": 495031552 + 14940160, "bulk": None}
+# `ncu --set full` captures summarised in profiles/r01_kernels_ring.txt / r01_kernels_gated.txt / r01_decode_stream.txt
+NCU_TRAFFIC_BYTES = {"ring": 494937600 + 4668160, "gated": 168146944 + 8370432, "stream": 495031552 + 14940160, "bulk": None}
 ROOFLINE_NOTE = {
     "ring": "default variant: persistent TMA ring (cp.async.bulk.tensor.2d + mbarrier), every byte of the head tensors "
             "is read exactly once whatever the input (traffic == algorithmic bytes).  All durations are CUDA events on "
