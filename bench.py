@@ -4,10 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path (b200_yolo_postprocess: fused decode+filter kernel, then the
-per-image order+NMS kernel) over one batch of 64 images per GPU (weak scaling: every rank owns its
-own 64-image batch, as the reference's DistributedSampler does); at N > 1 each step ends with the
-one exchange the path has, an NCCL all-gather of the fixed-capacity kept-detection messages.
+A "step" is one pass of the hot path (b200_yolo_postprocess_decode: fused decode+filter kernel, then
+b200_yolo_postprocess_nms: plan / pairs / resolve kernels) over one batch of 64 images per GPU (weak scaling:
+every rank owns its own 64-image batch, as the reference's DistributedSampler does); at N > 1 each step ends
+with the one exchange the path has, a pack kernel + ncclAllGather of the fixed-capacity kept-detection
+messages.  Steps are software pipelined: decode kernels rotate over 3 decode streams (so the HBM stream never
+drains), NMS chains over 3 other streams, the exchange has its own; 6 workspaces rotate.
 
 Printed JSON (one line, rank 0):
   value     whole-job images/s with the head tensors resident in HBM (device-timed, max over ranks)
@@ -187,8 +189,14 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------- GPU
 def run_b200(args):
+    # NCCL / torch may print banners on stdout; the contract is ONE JSON line there, so fd 1 is pointed at
+    # stderr for the duration of the run and the line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch.distributed as dist
     from object_detectors_b200 import _lib, ops
+    from object_detectors_b200.distributed import DetectionExchange
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,6 +206,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the exchanged messages are a few hundred KB: one or two NCCL channels (CTAs) move them, more would only
+        # take SMs from the decode stream
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     VARIANTS = {"gated": 0, "stream": 1, "bulk": 2, "ring": 3}
@@ -209,29 +220,59 @@ def run_b200(args):
     grids = [h.shape[2] for h in heads]
     n_anchor = sum(g * g * 3 for g in grids)
     algo_bytes = BATCH * n_anchor * (5 + NUM_CLASSES) * 4
-    # Two independent plans (own outputs + workspace) on two streams: the latency-bound NMS kernels of
-    # step i overlap the HBM-bound decode kernel of step i+1.  Every step's work completes inside the
-    # timed region (the end event waits for both streams).
-    n_streams = max(1, args.streams)
+    # Software pipeline: decode launches of consecutive steps go round-robin over `dstreams` streams (kernels on
+    # one stream are serial, so exactly that many decode kernels are in flight and the HBM stream never drains),
+    # the latency-bound NMS chain of a step (+ the exchange at N > 1) runs on one of `nstreams` other streams after
+    # the step's decode (event), and `plans` workspaces rotate (a workspace is reused only after its NMS has
+    # finished).  Every step's work completes inside the timed region (the end event waits for all streams).
+    n_d, n_n = max(1, args.dstreams), max(1, args.nstreams)
+    n_p = max(args.plans, n_d + 1)
+    lib.b200_debug_set_ring(*[int(x) for x in args.ring.split(",")])
     plans = [ops.YoloPostprocess(grids, BATCH, syn.COCO_ANCHORS, IMG, NUM_CLASSES, True, CONF_THR, NMS_THR,
-                                 ops.NMS_MAJORITY, CAPACITY, MAX_DET, dev) for _ in range(n_streams)]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
-    msg_len = BATCH * (1 + MAX_DET * 6)
-    gathered = [torch.empty((world * msg_len,), dtype=torch.float32, device=dev) for _ in range(n_streams)] if world > 1 else None
+                                 ops.NMS_MAJORITY, CAPACITY, MAX_DET, dev) for _ in range(n_p)]
+    d_streams = [torch.cuda.Stream(device=dev) for _ in range(n_d)]
+    n_streams_ = [torch.cuda.Stream(device=dev) for _ in range(n_n)]
+    # the exchange has its own stream: an all-gather that waits for a slower peer must not hold up the next
+    # NMS chain; all ranks enqueue the gathers in step order on it
+    x_stream = torch.cuda.Stream(device=dev)
+    streams = d_streams + n_streams_ + [x_stream]
+    dec_done = [torch.cuda.Event() for _ in plans]
+    nms_done = [torch.cuda.Event() for _ in plans]      # workspace + outputs of plan k are free again
+    det_ready = [torch.cuda.Event() for _ in plans]
+    exchange = DetectionExchange(BATCH, MAX_DET, dev, slots=n_p)
+    serial = [False]          # True: one stream does everything (the isolated-kernel measurement)
 
     def step(i):
-        k = i % n_streams      # n_streams is rebound to 1 for the isolated-kernel measurement
-        with torch.cuda.stream(streams[k]):
-            det, keep, anchor, dcnt, ccnt = plans[k](heads, idf)
-            if world > 1:
-                msg = ops.pack_detections(det, dcnt)
-                dist.all_gather_into_tensor(gathered[k], msg)
+        k = i % n_p
+        pl = plans[k]
+        if serial[0]:
+            d = n = d_streams[0]
+        else:
+            d, n = d_streams[i % n_d], n_streams_[i % n_n]
+            d.wait_event(nms_done[k])                # workspace k is free again
+        pl.decode(heads, idf, d)
+        if not serial[0]:
+            dec_done[k].record(d)
+            n.wait_event(dec_done[k])
+        pl.nms(n)
+        if world > 1:
+            x = n if serial[0] else x_stream
+            if not serial[0]:
+                det_ready[k].record(n)
+                x.wait_event(det_ready[k])
+            exchange(pl.det, pl.det_count, x, k)
+            if not serial[0]:
+                nms_done[k].record(x)
+        elif not serial[0]:
+            nms_done[k].record(n)
 
     def fence_in():
         ev = torch.cuda.Event()
         ev.record()
         for st in streams:
             st.wait_event(ev)
+        for e in nms_done:
+            e.record()
 
     def fence_out():
         for st in streams:
@@ -259,9 +300,11 @@ def run_b200(args):
         t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_begin.record()
         fence_in()
+        h0 = time.perf_counter()
         for i in range(steps):
             lib.b200_debug_set_decode_events(C.c_void_p(k_ev[i][0].cuda_event), C.c_void_p(k_ev[i][1].cuda_event))
             step(i)
+        host_us[0] = (time.perf_counter() - h0) / steps * 1e6      # host enqueue time per step (diagnostic)
         lib.b200_debug_set_decode_events(None, None)
         fence_out()
         t_end.record()
@@ -290,19 +333,20 @@ def run_b200(args):
             pl.check_status()
         return float(t[0]), float(t[1]), float(t[2])
 
+    host_us = [0.0]
     sampler = ClockSampler(local)
     ms_total, k_ms, k_busy = timed_loop(args.steps, max(args.warmup, 3), sample_clocks=True)
     clocks = sampler.stop() if rank == 0 else None
+    host_enqueue_us = host_us[0]
     plan = plans[0]
     kept = int(plan.det_count.sum())
     cands = int(plan.cand_count.sum())
 
     # ---- for the record: the decode kernel alone (one stream, nothing overlapping it), and the other variant ----
-    n_streams_main = n_streams
-    n_streams = 1
+    serial[0] = True
     iso_steps = min(args.steps, 200)
     iso_ms, iso_k, _ = timed_loop(iso_steps, 5)
-    n_streams = n_streams_main
+    serial[0] = False
     isolated = {"kernel_ms": iso_k, "achieved_GBs": algo_bytes / (iso_k * 1e-3) / 1e9,
                 "note": "same kernel, one stream, no other kernel resident; NMS kernels follow it serially"}
     other = "gated" if args.variant != "gated" else "ring"
@@ -356,8 +400,12 @@ def run_b200(args):
                                    "22743 anchors/image, softmax classes x IDF, conf 0.1, NMS 0.6",
                        "batch_per_gpu": BATCH, "global_batch": BATCH * world, "img_size": IMG,
                        "l2_policy": "inputs (494.9 MB/step) larger than L2 (126 MB), no flush needed",
-                       "candidates_per_step": cands, "kept_per_step": kept, "streams": n_streams, "decode_variant": args.variant,
-                       "exchange": "nccl all_gather of fixed-capacity kept lists" if world > 1 else "none (1 GPU)"},
+                       "candidates_per_step": cands, "kept_per_step": kept,
+                       "pipeline": {"decode_streams": n_d, "nms_streams": n_n, "workspaces": n_p, "ring": args.ring},
+                       "decode_variant": args.variant,
+                       "exchange": ("ncclAllGather of fixed-capacity kept lists, " +
+                                    ("direct NCCL binding" if exchange.nccl is not None else "torch.distributed"))
+                       if world > 1 else "none (1 GPU)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES[args.variant], "kernel": "k_decode_filter (" + args.variant + ")",
                          "kernel_ms": k_busy, "kernel_ms_launch_to_end": k_ms,
@@ -370,11 +418,13 @@ def run_b200(args):
                                        "(torch CPU ops, all host threads)"},
             "e2e": {"value": world * BATCH * e2e_steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-            "gpu_launches": args.steps * (4 + (1 if world > 1 else 0)),
+            "gpu_launches": args.steps * (4 + (2 if world > 1 else 0)),
+            "host_enqueue_us_per_step": host_enqueue_us,
             "clocks": clocks,
             "other_variant": other_variant,
         }
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    exchange.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -387,7 +437,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", default="ring", choices=["ring", "gated", "stream", "bulk"],
                     help="fused decode kernel variant (include/b200det.h: B200_DECODE_*)")
-    ap.add_argument("--streams", type=int, default=3, help="software pipeline depth (independent plans on own streams)")
+    ap.add_argument("--dstreams", type=int, default=3, help="decode streams = decode kernels in flight")
+    ap.add_argument("--nstreams", type=int, default=3, help="streams for the NMS chains (+ exchange)")
+    ap.add_argument("--plans", type=int, default=6, help="rotating workspaces")
+    ap.add_argument("--ring", default="4,1,101", help="RING decode: warps per CTA, stages per warp, CTAs per SM (+100: 32-cell tiles)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

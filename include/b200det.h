@@ -135,6 +135,18 @@ int b200_yolo_postprocess(const b200_yolo_layout* layout, const float* const* he
                           int32_t* det_anchor, int32_t* det_count, int32_t* cand_count,
                           int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same call split at its one internal dependency, for callers that pipeline batches over several
+ * streams (bench.py): phase 1 leaves the unordered candidate slab in `workspace`, phase 2 consumes it.
+ * Phase 2 may run on another stream once phase 1 has completed (event); a workspace must not be handed to
+ * phase 1 again before its phase 2 has finished.  b200_yolo_postprocess == decode + nms on one stream. */
+int b200_yolo_postprocess_decode(const b200_yolo_layout* layout, const float* const* heads,
+                                 const float* idf, float conf_thr, int32_t capacity, int32_t* status,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+int b200_yolo_postprocess_nms(const b200_yolo_layout* layout, double nms_thr, int32_t nms_mode,
+                              int32_t capacity, int32_t max_det, float* det, int32_t* det_keep,
+                              int32_t* det_anchor, int32_t* det_count, int32_t* cand_count,
+                              int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
 /* End-to-end variant with HOST buffers: copies the heads host->device (pinned or pageable),
  * runs b200_yolo_postprocess and copies det / det_count back.  Device staging comes from an
  * internal pool sized on first use; synchronises before returning.

@@ -40,6 +40,8 @@ SIGNATURES = {
     "b200_yolo_decode_filter": (C.c_int, [_LP, _PP, _p, _f32, _i32, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "b200_yolo_postprocess": (C.c_int, [_LP, _PP, _p, _f32, _f64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p,
                                         _p, _sz, _p]),
+    "b200_yolo_postprocess_decode": (C.c_int, [_LP, _PP, _p, _f32, _i32, _p, _p, _sz, _p]),
+    "b200_yolo_postprocess_nms": (C.c_int, [_LP, _f64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "b200_yolo_postprocess_host": (C.c_int, [_LP, _PP, _p, _f32, _f64, _i32, _i32, _i32, _p, _p, _p, _p]),
     "b200_debug_set_decode_events": (C.c_int, [_p, _p]),
     "b200_debug_set_timeline": (C.c_int, [_p, _p, _p]),

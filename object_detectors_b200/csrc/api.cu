@@ -173,9 +173,10 @@ int b200_debug_set_decode_events(void* ev_begin, void* ev_end) {
     return B200_OK;
 }
 
-static int yolo_run(const b200_yolo_layout* layout, const float* const* heads, const float* idf,
-                    float conf_thr, int capacity, int* count_buf, NmsParams& np, const YoloWs& w,
-                    cudaStream_t st) {
+// phase 1: slab cursors + ticket counter cleared, fused decode+filter into the slab
+static int yolo_decode_phase(const b200_yolo_layout* layout, const float* const* heads, const float* idf,
+                             float conf_thr, int capacity, int* count_buf, int* status, const YoloWs& w,
+                             cudaStream_t st, int* anchor_space) {
     DecodeParams p{};
     const int rc = make_decode_params(layout, heads, idf, &p);
     if (rc != B200_OK) return rc;
@@ -183,7 +184,8 @@ static int yolo_run(const b200_yolo_layout* layout, const float* const* heads, c
     p.slab = w.slab;
     p.cap = capacity;
     p.count = count_buf;
-    p.status = np.status;
+    p.status = status;
+    if (anchor_space) *anchor_space = p.N;
     if (count_buf == w.count) {
         // slab cursors and the ring kernel's ticket counter sit in one block: one memset node
         B200_CUDA_TRY(cudaMemsetAsync(w.count, 0, (size_t)(reinterpret_cast<unsigned char*>(w.ticket + kTicketInts) -
@@ -200,6 +202,12 @@ static int yolo_run(const b200_yolo_layout* layout, const float* const* heads, c
         rc2 = launch_decode_filter(p, layout->softmax != 0, g_decode_variant == B200_DECODE_GATED ? 1 : 0, st);
     if (rc2 != B200_OK) return rc2;
     if (g_ev_decode_end) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(g_ev_decode_end), st));
+    return B200_OK;
+}
+
+// phase 2: order + NMS of the slab
+static int yolo_nms_phase(const b200_yolo_layout* layout, int capacity, const int* count_buf, NmsParams& np,
+                          const YoloWs& w, int anchor_space, cudaStream_t st) {
     if (!nms_carve_scratch(&np, (size_t)layout->batch * capacity, (size_t)layout->batch, (size_t)capacity,
                            w.nms, w.nms_bytes))
         return B200_ERR_WORKSPACE;
@@ -207,9 +215,18 @@ static int yolo_run(const b200_yolo_layout* layout, const float* const* heads, c
     np.count = count_buf;
     np.cap = capacity;
     np.from_slab = 1;
-    np.anchor_space = p.N;
+    np.anchor_space = anchor_space;
     np.max_seg = capacity;
     return launch_nms(np, layout->batch, st);
+}
+
+static int yolo_run(const b200_yolo_layout* layout, const float* const* heads, const float* idf,
+                    float conf_thr, int capacity, int* count_buf, NmsParams& np, const YoloWs& w,
+                    cudaStream_t st) {
+    int anchor_space = 0;
+    const int rc = yolo_decode_phase(layout, heads, idf, conf_thr, capacity, count_buf, np.status, w, st, &anchor_space);
+    if (rc != B200_OK) return rc;
+    return yolo_nms_phase(layout, capacity, count_buf, np, w, anchor_space, st);
 }
 
 int b200_yolo_decode_filter(const b200_yolo_layout* layout, const float* const* heads,
@@ -255,6 +272,41 @@ int b200_yolo_postprocess(const b200_yolo_layout* layout, const float* const* he
     np.cand_count_out = cand_count;
     np.max_det = max_det;
     return yolo_run(layout, heads, idf, conf_thr, capacity, w.count, np, w, static_cast<cudaStream_t>(stream));
+}
+
+int b200_yolo_postprocess_decode(const b200_yolo_layout* layout, const float* const* heads, const float* idf,
+                                 float conf_thr, int32_t capacity, int32_t* status, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    if (!layout || !status || capacity < 1) return B200_ERR_INVALID;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return B200_ERR_WORKSPACE;
+    YoloWs w;
+    if (!yolo_ws_layout(layout->batch, capacity, workspace, workspace_bytes, &w)) return B200_ERR_WORKSPACE;
+    return yolo_decode_phase(layout, heads, idf, conf_thr, capacity, w.count, status, w,
+                             static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int b200_yolo_postprocess_nms(const b200_yolo_layout* layout, double nms_thr, int32_t nms_mode, int32_t capacity,
+                              int32_t max_det, float* det, int32_t* det_keep, int32_t* det_anchor,
+                              int32_t* det_count, int32_t* cand_count, int32_t* status, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    if (!layout || !det || !det_count || !status || capacity < 1 || max_det < 1) return B200_ERR_INVALID;
+    if (layout->num_scales < 1 || layout->num_scales > B200_MAX_SCALES) return B200_ERR_INVALID;
+    if (nms_mode < B200_NMS_MAJORITY || nms_mode > B200_NMS_TV_TRICK) return B200_ERR_INVALID;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return B200_ERR_WORKSPACE;
+    YoloWs w;
+    if (!yolo_ws_layout(layout->batch, capacity, workspace, workspace_bytes, &w)) return B200_ERR_WORKSPACE;
+    NmsParams np{};
+    np.mode = nms_mode;
+    np.thr_f = (float)nms_thr;
+    np.thr_d = nms_thr;
+    np.status = status;
+    np.cbox = w.cbox; np.cscore = w.cscore; np.clabel = w.clabel; np.canchor = w.canchor;
+    np.det = det; np.det_keep = det_keep; np.det_anchor = det_anchor; np.det_count = det_count;
+    np.cand_count_out = cand_count;
+    np.max_det = max_det;
+    int anchor_space = 0;
+    for (int s = 0; s < layout->num_scales; ++s) anchor_space += layout->grid[s] * layout->grid[s] * layout->num_anchors;
+    return yolo_nms_phase(layout, capacity, w.count, np, w, anchor_space, static_cast<cudaStream_t>(stream));
 }
 
 // ----------------------------------------------------------------------------- host-buffer e2e

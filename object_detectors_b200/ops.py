@@ -176,6 +176,24 @@ class YoloPostprocess:
             "b200_yolo_postprocess")
         return self.det, self.det_keep, self.det_anchor, self.det_count, self.cand_count
 
+    def decode(self, heads: Sequence[Tensor], idf: Optional[Tensor] = None, stream: Optional[torch.cuda.Stream] = None):
+        """Phase 1 (b200_yolo_postprocess_decode) on `stream` (default: current): candidates into the plan's slab."""
+        arr = (C.c_void_p * len(heads))(*[h.data_ptr() for h in heads])
+        idf = _idf_arg(idf, self.num_classes, self.dev)
+        st = _stream() if stream is None else C.c_void_p(stream.cuda_stream)
+        _lib.check(self.lib.b200_yolo_postprocess_decode(
+            C.byref(self.lay), arr, _ptr(idf), self.conf_thr, self.cap, _ptr(self.status), _ptr(self.ws),
+            self.ws_bytes, st), "b200_yolo_postprocess_decode")
+
+    def nms(self, stream: Optional[torch.cuda.Stream] = None):
+        """Phase 2 (b200_yolo_postprocess_nms) on `stream` (default: current), ordered after phase 1."""
+        st = _stream() if stream is None else C.c_void_p(stream.cuda_stream)
+        _lib.check(self.lib.b200_yolo_postprocess_nms(
+            C.byref(self.lay), self.nms_thr, self.nms_mode, self.cap, self.max_det, _ptr(self.det),
+            _ptr(self.det_keep), _ptr(self.det_anchor), _ptr(self.det_count), _ptr(self.cand_count),
+            _ptr(self.status), _ptr(self.ws), self.ws_bytes, st), "b200_yolo_postprocess_nms")
+        return self.det, self.det_keep, self.det_anchor, self.det_count, self.cand_count
+
     def check_status(self):
         st = int(self.status.item())
         if st & 1:
