@@ -57,8 +57,13 @@ enum {
     B200_NMS_TV_CLASS = 2,
     /* torchvision.ops.batched_nms, "coordinate trick" strategy: boxes are shifted by
      * label*(max_coordinate+1) in fp32 and suppressed class-agnostically. */
-    B200_NMS_TV_TRICK = 3
+    B200_NMS_TV_TRICK = 3,
+    /* torchvision.ops.batched_nms as shipped: per segment, the coordinate trick when boxes.numel() (4n) is
+     * at most the switch limit, the per-class strategy above it (boxes.py; limit 100 000 on CUDA, 4 000 on
+     * CPU; b200_set_batched_nms_auto_limit). */
+    B200_NMS_TV_AUTO = 4
 };
+int b200_set_batched_nms_auto_limit(int64_t numel);
 
 /* pairwise IoU flavours of helper.bbox_iou (yolo/utilities/helper.py:221-277) + torchvision */
 enum {
@@ -186,6 +191,37 @@ int b200_set_decode_variant(int variant);
 /* Tuning hook of the RING variant (values <= 0 keep the current setting): warps per CTA (1..8),
  * shared-memory stages per warp (warps x stages <= 32), persistent CTAs per SM (1..4). */
 int b200_debug_set_ring(int warps, int stages_per_warp, int ctas_per_sm);
+
+/* Replaces the inference branch of the legacy per-head layer YOLOLoss.forward(input, targets=None)
+ * (yolo/nets/yolo_loss.py:34-105; callers yolo/benchmark.py:63, telemetry.py:46-92).
+ * head: [B, A*(5+C), in_h, in_w] fp32; out: [B, A*in_h*in_w, 5+C] with rows ordered (a, h, w);
+ * stride_* = fp32(img_size / in_*); anchors_scaled: DEVICE [A][2] fp32 = anchor_px / stride (:40). */
+int b200_yolo_legacy_decode(const float* head, int32_t batch, int32_t num_anchors, int32_t num_classes,
+                            int32_t in_h, int32_t in_w, float stride_w, float stride_h,
+                            const float* anchors_scaled, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ROI-head box post-process (Faster R-CNN family)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Replaces RoIHeads.postprocess_detections (torchvision_models/tvision/roi_heads.py:715-781) for a batch:
+ * scores = softmax (activation 0) / gombit (1) / sigmoid (2) of tfidf*class_logits, per-class box decode
+ * with BoxCoder weights `weights_host` (x,y,w,h), clip to the image, background column dropped,
+ * score > score_thr, w,h >= min_size, batched_nms per class (nms_mode B200_NMS_TV_CLASS or _TV_TRICK),
+ * first max_det by score.
+ *   class_logits [R, C], box_regression [R, 4C], proposals [R, 4] (images concatenated),
+ *   row_offsets [B+1] device int32, image_hw [B, 2] device fp32 (height, width), tfidf [C] or NULL.
+ * Outputs per image: det [B, max_det, 6] = x1,y1,x2,y2,score,label; det_keep [B, max_det] (index into the
+ * image's filtered candidate list, may be NULL); det_count [B]; cand_count [B] (may be NULL).
+ * capacity: candidate slab rows per image (status |= 1 on overflow). */
+size_t b200_roi_workspace_bytes(int32_t batch, int32_t capacity);
+int b200_roi_postprocess(const float* class_logits, const float* box_regression, const float* proposals,
+                         const int32_t* row_offsets, int32_t batch, int32_t total_rows, int32_t num_classes,
+                         const float* image_hw, const float* tfidf, int32_t activation,
+                         const float* weights_host, float xform_clip, float score_thr, float min_size,
+                         double nms_thr, int32_t nms_mode, int32_t capacity, int32_t max_det, float* det,
+                         int32_t* det_keep, int32_t* det_count, int32_t* cand_count, int32_t* status,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * NMS on caller-provided boxes, batched over segments (images, or image x level)

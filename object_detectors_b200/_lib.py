@@ -8,7 +8,7 @@ import os
 MAX_SCALES = 4
 MAX_ANCHORS = 8
 
-NMS_MAJORITY, NMS_TV, NMS_TV_CLASS, NMS_TV_TRICK = 0, 1, 2, 3
+NMS_MAJORITY, NMS_TV, NMS_TV_CLASS, NMS_TV_TRICK, NMS_TV_AUTO = 0, 1, 2, 3, 4
 IOU, GIOU, DIOU, CIOU, IOU_TV = 0, 1, 2, 3, 4
 DECODE_GATED, DECODE_STREAM, DECODE_BULK, DECODE_RING = 0, 1, 2, 3
 
@@ -48,6 +48,11 @@ SIGNATURES = {
     "b200_debug_set_resolve_prof": (C.c_int, [_p]),
     "b200_set_decode_variant": (C.c_int, [C.c_int]),
     "b200_debug_set_ring": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "b200_yolo_legacy_decode": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _p, _p, _p]),
+    "b200_roi_workspace_bytes": (_sz, [_i32, _i32]),
+    "b200_roi_postprocess": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _i32, C.POINTER(C.c_float), _f32, _f32,
+                                       _f32, _f64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "b200_set_batched_nms_auto_limit": (C.c_int, [_i64]),
     "b200_nms_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "b200_nms": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _f64, _i32, _p, _p, _p, _p, _sz, _p]),
     "b200_box_iou": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _p, _p]),

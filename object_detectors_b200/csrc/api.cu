@@ -97,7 +97,7 @@ static __global__ void k_pack(const float* __restrict__ det, const int* __restri
 }
 }  // namespace b200
 
-namespace b200 { extern cudaEvent_t g_nms_timeline[3]; extern long long* g_resolve_prof; }
+namespace b200 { extern cudaEvent_t g_nms_timeline[3]; extern long long* g_resolve_prof; extern long long g_batched_nms_auto_limit; }
 using namespace b200;
 
 extern "C" {
@@ -162,6 +162,11 @@ int b200_debug_set_timeline(void* after_plan, void* after_pairs, void* after_res
     b200::g_nms_timeline[0] = static_cast<cudaEvent_t>(after_plan);
     b200::g_nms_timeline[1] = static_cast<cudaEvent_t>(after_pairs);
     b200::g_nms_timeline[2] = static_cast<cudaEvent_t>(after_resolve);
+    return B200_OK;
+}
+int b200_set_batched_nms_auto_limit(int64_t numel) {
+    if (numel < 0) return B200_ERR_INVALID;
+    b200::g_batched_nms_auto_limit = numel;
     return B200_OK;
 }
 int b200_debug_set_resolve_prof(void* buf) { b200::g_resolve_prof = static_cast<long long*>(buf); return B200_OK; }
@@ -258,7 +263,7 @@ int b200_yolo_postprocess(const b200_yolo_layout* layout, const float* const* he
                           int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
     if (!layout || !det || !det_count || !status || capacity < 1 || max_det < 1)
         return B200_ERR_INVALID;
-    if (nms_mode < B200_NMS_MAJORITY || nms_mode > B200_NMS_TV_TRICK) return B200_ERR_INVALID;
+    if (nms_mode < B200_NMS_MAJORITY || nms_mode > B200_NMS_TV_AUTO) return B200_ERR_INVALID;
     if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return B200_ERR_WORKSPACE;
     YoloWs w;
     if (!yolo_ws_layout(layout->batch, capacity, workspace, workspace_bytes, &w)) return B200_ERR_WORKSPACE;
@@ -291,7 +296,7 @@ int b200_yolo_postprocess_nms(const b200_yolo_layout* layout, double nms_thr, in
                               size_t workspace_bytes, void* stream) {
     if (!layout || !det || !det_count || !status || capacity < 1 || max_det < 1) return B200_ERR_INVALID;
     if (layout->num_scales < 1 || layout->num_scales > B200_MAX_SCALES) return B200_ERR_INVALID;
-    if (nms_mode < B200_NMS_MAJORITY || nms_mode > B200_NMS_TV_TRICK) return B200_ERR_INVALID;
+    if (nms_mode < B200_NMS_MAJORITY || nms_mode > B200_NMS_TV_AUTO) return B200_ERR_INVALID;
     if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return B200_ERR_WORKSPACE;
     YoloWs w;
     if (!yolo_ws_layout(layout->batch, capacity, workspace, workspace_bytes, &w)) return B200_ERR_WORKSPACE;
@@ -420,7 +425,7 @@ int b200_nms(const float* boxes, const float* scores, const int32_t* labels, con
     if (num_segments == 0) return B200_OK;
     if (!seg_offsets || !keep_count) return B200_ERR_INVALID;
     if (total_boxes > 0 && (!boxes || !scores || !keep || !aligned16(boxes))) return B200_ERR_INVALID;
-    if (mode < B200_NMS_MAJORITY || mode > B200_NMS_TV_TRICK) return B200_ERR_INVALID;
+    if (mode < B200_NMS_MAJORITY || mode > B200_NMS_TV_AUTO) return B200_ERR_INVALID;
     if (mode != B200_NMS_TV && !labels && total_boxes > 0) return B200_ERR_INVALID;
     const size_t ms = max_segment > 0 ? (size_t)max_segment : (size_t)total_boxes;
     NmsParams np{};

@@ -78,6 +78,12 @@ struct Item {
     int label;
 };
 
+// coordinate-trick arithmetic: always (TV_TRICK) or per segment (TV_AUTO, unit == 0 where the segment is
+// large enough for torchvision to switch to its per-class loop)
+__device__ __forceinline__ bool uses_shift(const NmsParams& P) {
+    return P.mode == B200_NMS_TV_TRICK || P.mode == B200_NMS_TV_AUTO;
+}
+
 // by index i inside the segment
 template <bool SLAB>
 __device__ __forceinline__ Item load_raw(const NmsParams& P, long long off, int i, float unit) {
@@ -97,7 +103,7 @@ __device__ __forceinline__ Item load_raw(const NmsParams& P, long long off, int 
         it.label = P.labels ? P.labels[off + i] : 0;
         tie = (unsigned)i;
     }
-    if (P.mode == B200_NMS_TV_TRICK) {
+    if (uses_shift(P)) {
         // boxes + idxs.to(boxes) * (boxes.max() + 1)   (torchvision boxes.py coordinate trick)
         const float sh = __fmul_rn((float)it.label, unit);
         it.b = make_float4(__fadd_rn(it.b.x, sh), __fadd_rn(it.b.y, sh), __fadd_rn(it.b.z, sh), __fadd_rn(it.b.w, sh));
@@ -290,7 +296,8 @@ k_nms_plan(const __grid_constant__ NmsParams P) {
 
     // ---- coordinate-trick unit, y range of the box centres ------------------------------------
     float unit = 0.f;
-    if (P.mode == B200_NMS_TV_TRICK) {
+    // torchvision.ops.batched_nms: coordinate trick unless boxes.numel() > limit (then per-class "vanilla")
+    if (P.mode == B200_NMS_TV_TRICK || (P.mode == B200_NMS_TV_AUTO && 4ll * n_true <= P.auto_limit)) {
         float mx = -INFINITY;
         for (int i = tid; i < n; i += kPlanThreads) {
             const float4 b = SLAB ? reinterpret_cast<const float4*>(P.slab + off + i)[0]
@@ -298,8 +305,8 @@ k_nms_plan(const __grid_constant__ NmsParams P) {
             mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
         }
         unit = __fadd_rn(block_reduce_max(mx, red), 1.0f);
-        if (tid == 0) P.shift_unit[seg] = unit;
     }
+    if (uses_shift(P) && tid == 0) P.shift_unit[seg] = unit;
     float lo = INFINITY, hi = -INFINITY;
     for (int i = tid; i < n; i += kPlanThreads) {
         const Item it = load_raw<SLAB>(P, off, i, unit);
@@ -424,7 +431,7 @@ __device__ __forceinline__ void pair_tile(const NmsParams& P, int seg, int rt, i
     long long off;
     int n, n_true;
     segment_range(P, seg, off, n, n_true);
-    const float unit = P.mode == B200_NMS_TV_TRICK ? P.shift_unit[seg] : 0.f;
+    const float unit = uses_shift(P) ? P.shift_unit[seg] : 0.f;
     const int tid = threadIdx.x;
     const int r = tid >> 2, cg = tid & 3;
     unsigned long long* dom = P.dom + (size_t)seg * (size_t)P.max_seg * (size_t)P.max_words;
@@ -502,6 +509,7 @@ k_nms_pairs(const __grid_constant__ NmsParams P) {
         const int rt = w.y >> 16, ct = w.y & 0xffff;
         switch (P.mode) {
             case B200_NMS_MAJORITY: pair_tile<B200_NMS_MAJORITY, SLAB>(P, w.x, rt, ct, S); break;
+            case B200_NMS_TV_AUTO:    // shifted boxes of different labels never intersect: the label test is exact for both
             case B200_NMS_TV_CLASS: pair_tile<B200_NMS_TV_CLASS, SLAB>(P, w.x, rt, ct, S); break;
             default:                pair_tile<B200_NMS_TV, SLAB>(P, w.x, rt, ct, S); break;   // TV, TV_TRICK
         }
@@ -596,7 +604,7 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
     const int nw = cdiv(n, 64);      // <= 64 on this path
     FastSmem f;
     fast_carve(f, smem_raw, n, nw);
-    const float unit = P.mode == B200_NMS_TV_TRICK ? P.shift_unit[seg] : 0.f;
+    const float unit = uses_shift(P) ? P.shift_unit[seg] : 0.f;
     const unsigned long long* dom = P.dom + (size_t)seg * (size_t)P.max_seg * (size_t)P.max_words;
     unsigned long long* cw = compact ? reinterpret_cast<unsigned long long*>(f.u) : nullptr;
     const int* perm = P.gperm + off;
@@ -811,7 +819,7 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
 template <int MODE, bool SLAB>
 __device__ void resolve_slow(const NmsParams& P, int seg, long long off, int n, unsigned char* smem_raw) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float unit = P.mode == B200_NMS_TV_TRICK ? P.shift_unit[seg] : 0.f;
+    const float unit = uses_shift(P) ? P.shift_unit[seg] : 0.f;
     const int nw = cdiv(n, 64);
     unsigned char* q = smem_raw;
     unsigned long long* Kset = reinterpret_cast<unsigned long long*>(q); q += sizeof(unsigned long long) * P.max_words;
@@ -1065,7 +1073,10 @@ bool nms_carve_scratch(NmsParams* P, size_t total, size_t segments, size_t max_s
 cudaEvent_t g_nms_timeline[3] = {nullptr, nullptr, nullptr};
 long long* g_resolve_prof = nullptr;
 
+long long g_batched_nms_auto_limit = 100000;   // torchvision 0.26 on CUDA (4000 on CPU)
+
 int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
+    P.auto_limit = g_batched_nms_auto_limit;
     if (num_segments <= 0) return B200_OK;
     if (num_segments > 65535) return B200_ERR_INVALID;
     if (P.max_seg < 1) P.max_seg = 1;

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 from ._lib import (CIOU, DIOU, GIOU, IOU, IOU_TV, NMS_MAJORITY, NMS_TV, NMS_TV_CLASS,  # noqa: F401
-                   NMS_TV_TRICK)
+                   NMS_TV_AUTO, NMS_TV_TRICK)
 
 Tensor = torch.Tensor
 
@@ -420,6 +420,66 @@ def matcher(quality: Tensor, high: float, low: float, allow_low_quality: bool = 
                                 int(bool(allow_low_quality)), _ptr(matches), _ptr(ws), ws.numel(), _stream()),
                "b200_matcher")
     return matches
+
+
+def yolo_legacy_decode(head: Tensor, anchors_px, num_classes: int, img_size) -> Tensor:
+    """One head of the legacy YOLOLoss layer (yolo/nets/yolo_loss.py:34-105, inference branch):
+    [B, A*(5+C), H, W] -> [B, A*H*W, 5+C], rows ordered (a, h, w)."""
+    lib = _lib.load()
+    head = _need_cuda(head, "input", torch.float32)
+    b, _, in_h, in_w = head.shape
+    na = len(anchors_px)
+    if head.shape[1] != na * (5 + num_classes):
+        raise RuntimeError("head channels do not match anchors x (5 + classes)")
+    stride_h, stride_w = img_size / in_h, img_size / in_w           # python floats, as the reference (:38-39)
+    scaled = torch.tensor([(a_w / stride_w, a_h / stride_h) for a_w, a_h in anchors_px], dtype=torch.float32,
+                          device=head.device)                        # FloatTensor(scaled_anchors) (:91-92)
+    out = torch.empty((b, na * in_h * in_w, 5 + num_classes), dtype=torch.float32, device=head.device)
+    _lib.check(lib.b200_yolo_legacy_decode(_ptr(head), b, na, num_classes, in_h, in_w, float(np.float32(stride_w)),
+                                           float(np.float32(stride_h)), _ptr(scaled), _ptr(out), _stream()),
+               "b200_yolo_legacy_decode")
+    return out
+
+
+ROI_SOFTMAX, ROI_GOMBIT, ROI_SIGMOID = 0, 1, 2
+
+
+def roi_postprocess(class_logits: Tensor, box_regression: Tensor, proposals: Sequence[Tensor], image_shapes,
+                    tfidf: Optional[Tensor] = None, activation: int = ROI_SOFTMAX,
+                    weights=(10.0, 10.0, 5.0, 5.0), xform_clip: float = 4.135166556742356,
+                    score_thresh: float = 0.05, nms_thresh: float = 0.5, detections_per_img: int = 100,
+                    min_size: float = 1e-2, nms_mode: int = NMS_TV_AUTO, capacity: Optional[int] = None):
+    """RoIHeads.postprocess_detections (roi_heads.py:715-781) for the whole batch in two launches + NMS.
+    Returns (det [B, D, 6], det_keep [B, D], det_count [B], cand_count [B])."""
+    lib = _lib.load()
+    class_logits = _need_cuda(class_logits, "class_logits", torch.float32)
+    box_regression = _need_cuda(box_regression, "box_regression", torch.float32)
+    dev = class_logits.device
+    rows = [int(p.shape[0]) for p in proposals]
+    b, r, c = len(rows), int(class_logits.shape[0]), int(class_logits.shape[1])
+    if sum(rows) != r or box_regression.shape[1] != 4 * c:
+        raise RuntimeError("class_logits / box_regression / proposals disagree on the number of rows or classes")
+    prop = torch.cat([p.to(torch.float32) for p in proposals], 0).contiguous() if r else torch.zeros((0, 4), device=dev)
+    prop = _need_cuda(prop, "proposals", torch.float32)
+    off = torch.tensor(np.concatenate([[0], np.cumsum(rows)]), dtype=torch.int32, device=dev)
+    hw = torch.tensor([[float(h), float(w)] for h, w in image_shapes], dtype=torch.float32, device=dev)
+    if tfidf is not None:
+        tfidf = torch.as_tensor(tfidf, dtype=torch.float32, device=dev).expand(c).contiguous()
+    cap = int(capacity or max(1, max(rows) * (c - 1)))
+    d = int(detections_per_img)
+    det = torch.empty((b, d, 6), dtype=torch.float32, device=dev)
+    keep = torch.empty((b, d), dtype=torch.int32, device=dev)
+    dcnt = torch.zeros((b,), dtype=torch.int32, device=dev)
+    ccnt = torch.zeros((b,), dtype=torch.int32, device=dev)
+    status = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ws = workspace(lib.b200_roi_workspace_bytes(b, cap), dev, "roi")
+    w4 = (C.c_float * 4)(*[float(v) for v in weights])
+    _lib.check(lib.b200_roi_postprocess(
+        _ptr(class_logits), _ptr(box_regression), _ptr(prop), _ptr(off), b, r, c, _ptr(hw), _ptr(tfidf), int(activation),
+        w4, float(np.float32(xform_clip)), float(np.float32(score_thresh)), float(np.float32(min_size)),
+        float(nms_thresh), int(nms_mode), cap, d, _ptr(det), _ptr(keep), _ptr(dcnt), _ptr(ccnt), _ptr(status), _ptr(ws),
+        ws.numel(), _stream()), "b200_roi_postprocess")
+    return det, keep, dcnt, ccnt, status
 
 
 def pack_detections(det: Tensor, det_count: Tensor) -> Tensor:

@@ -202,3 +202,36 @@ def rpn_inputs(seed: int, batch: int, img_h: int = 800, img_w: int = 1344):
     obj = g.standard_normal((batch, n), dtype=np.float32) * np.float32(2.0) - np.float32(3.0)
     deltas = g.standard_normal((batch, n, 4), dtype=np.float32) * np.float32(0.2)
     return obj, deltas, anchors, per_level
+
+
+def roi_inputs(seed: int, rows_per_image: Sequence[int], num_classes: int, img_h: int = 800, img_w: int = 1216):
+    """Box-head outputs of a Faster R-CNN ROI head: ``class_logits [R, C]`` (background column 0 dominant except for
+    a few foreground rows per cluster), ``box_regression [R, 4C]`` ~ N(0, 0.5^2), ``proposals`` list of ``[r_i, 4]``
+    clustered around a handful of objects so that the per-class NMS has something to suppress."""
+    g = _rng(seed)
+    props, logits, regs = [], [], []
+    for r in rows_per_image:
+        k = int(g.integers(2, 7))
+        centres = g.uniform(0.15, 0.85, size=(k, 2)) * np.array([img_w, img_h])
+        sizes = np.exp(g.uniform(np.log(32), np.log(0.5 * min(img_h, img_w)), size=(k, 2)))
+        cls = g.integers(1, num_classes, size=k)
+        which = g.integers(0, k, size=r)
+        c = centres[which] + g.standard_normal((r, 2)) * sizes[which] * 0.08
+        s = sizes[which] * np.exp(g.standard_normal((r, 2)) * 0.1)
+        p = np.concatenate([c - s / 2, c + s / 2], 1)
+        p[:, 0::2] = np.clip(p[:, 0::2], 0, img_w)
+        p[:, 1::2] = np.clip(p[:, 1::2], 0, img_h)
+        lg = g.standard_normal((r, num_classes)).astype(np.float32)
+        lg[:, 0] += 2.0
+        fg = g.random(r) < 0.6
+        lg[np.arange(r)[fg], cls[which][fg]] += g.uniform(3.0, 7.0, size=int(fg.sum())).astype(np.float32)
+        props.append(p.astype(np.float32))
+        logits.append(lg)
+        regs.append((g.standard_normal((r, 4 * num_classes)) * 0.5).astype(np.float32))
+    return np.concatenate(logits), np.concatenate(regs), props
+
+
+def legacy_head(seed: int, batch: int, num_anchors: int, num_classes: int, grid: int) -> np.ndarray:
+    """One raw head tensor ``[B, A*(5+C), grid, grid]`` ~ N(0, 1.5^2) for the legacy YOLOLoss layer."""
+    g = _rng(seed)
+    return (g.standard_normal((batch, num_anchors * (5 + num_classes), grid, grid)) * 1.5).astype(np.float32)

@@ -115,6 +115,22 @@ def decode_single(rel_codes: Tensor, boxes: Tensor,
     return torch.stack((pcx - half * pw, pcy - half * ph, pcx + half * pw, pcy + half * ph), dim=1)
 
 
+def decode_multi(rel_codes: Tensor, boxes: Tensor,
+                 weights: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)) -> Tensor:
+    """BoxCoder.decode_single with k boxes per row: rel_codes [n, 4k] -> [n, 4k] (_utils.py:186-223)."""
+    w = boxes[:, 2] - boxes[:, 0]
+    h = boxes[:, 3] - boxes[:, 1]
+    cx = boxes[:, 0] + 0.5 * w
+    cy = boxes[:, 1] + 0.5 * h
+    dx, dy = rel_codes[:, 0::4] / weights[0], rel_codes[:, 1::4] / weights[1]
+    dw = torch.clamp(rel_codes[:, 2::4] / weights[2], max=BBOX_XFORM_CLIP)
+    dh = torch.clamp(rel_codes[:, 3::4] / weights[3], max=BBOX_XFORM_CLIP)
+    pcx, pcy = dx * w[:, None] + cx[:, None], dy * h[:, None] + cy[:, None]
+    pw, ph = torch.exp(dw) * w[:, None], torch.exp(dh) * h[:, None]
+    half = torch.tensor(0.5, dtype=pw.dtype)
+    return torch.stack((pcx - half * pw, pcy - half * ph, pcx + half * pw, pcy + half * ph), dim=2).flatten(1)
+
+
 def filter_proposals(objectness: Tensor, deltas: Tensor, anchors: Tensor,
                      per_level: Sequence[int], image_shapes: Sequence[Tuple[int, int]],
                      pre_nms_top_n: int, post_nms_top_n: int, nms_thresh: float = 0.7,
@@ -162,3 +178,47 @@ def matcher(quality: Tensor, high: float, low: float, allow_low_quality: bool = 
         tied = torch.where(quality == row_best[:, None])[1]                # _utils.py:315-344
         matches[tied] = every[tied]
     return matches
+
+
+# --------------------------------------------------------------------------------------
+# ROI-head box post-process  (torchvision_models/tvision/roi_heads.py:715-781)
+# --------------------------------------------------------------------------------------
+def roi_postprocess(class_logits: Tensor, box_regression: Tensor, proposals: Sequence[Tensor], image_shapes,
+                    tfidf, activation: str = "ce", weights=(10.0, 10.0, 5.0, 5.0), score_thresh: float = 0.05,
+                    nms_thresh: float = 0.5, detections_per_img: int = 100, strategy: str = "vanilla"):
+    """RoIHeads.postprocess_detections; ``strategy`` picks the batched_nms arithmetic explicitly
+    ("vanilla" | "coordinate_trick" | "torchvision" = the installed CPU switch at 4000 coordinates).
+    Returns per image (boxes, scores, labels, keep) with ``keep`` indexing the filtered candidate list."""
+    num_classes = class_logits.shape[-1]
+    rows = [len(p) for p in proposals]
+    concat = torch.cat(list(proposals), 0)
+    pred_boxes = decode_multi(box_regression.reshape(concat.shape[0], -1), concat, weights)       # :721
+    pred_boxes = pred_boxes.reshape(concat.shape[0], -1, 4)
+    if activation == "ce":
+        scores = torch.softmax(tfidf * class_logits, -1)                                           # :725
+    elif activation.startswith("gombit"):
+        scores = 1 / (torch.exp(torch.exp(-tfidf * (class_logits - 1.96))))                        # :727
+    else:
+        scores = torch.sigmoid(tfidf * class_logits)                                               # :729
+    out = []
+    for boxes, sc, shape in zip(pred_boxes.split(rows, 0), scores.split(rows, 0), image_shapes):
+        h, w = shape
+        bx = boxes[..., 0::2].clamp(min=0, max=w)                                                  # clip_boxes_to_image
+        by = boxes[..., 1::2].clamp(min=0, max=h)
+        boxes = torch.stack((bx, by), dim=boxes.dim()).reshape(boxes.shape)
+        labels = torch.arange(num_classes).view(1, -1).expand_as(sc)
+        boxes, sc, labels = boxes[:, 1:].reshape(-1, 4), sc[:, 1:].reshape(-1), labels[:, 1:].reshape(-1)   # :752-759
+        inds = torch.nonzero(sc > score_thresh).squeeze(1)                                         # :763
+        boxes, sc, labels = boxes[inds], sc[inds], labels[inds]
+        ws, hs = boxes[:, 2] - boxes[:, 0], boxes[:, 3] - boxes[:, 1]
+        keep = torch.nonzero((ws >= 1e-2) & (hs >= 1e-2)).squeeze(1)                               # :767
+        boxes, sc, labels = boxes[keep], sc[keep], labels[keep]
+        if strategy == "vanilla":
+            k = batched_nms_vanilla(boxes, sc, labels, nms_thresh)
+        elif strategy == "coordinate_trick":
+            k = batched_nms_coordinate_trick(boxes, sc, labels, nms_thresh)
+        else:
+            k = batched_nms(boxes, sc, labels, nms_thresh)
+        k = k[:detections_per_img]                                                                 # :774
+        out.append((boxes[k], sc[k], labels[k], k))
+    return out

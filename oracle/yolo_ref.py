@@ -255,3 +255,30 @@ def screen_margins(heads, anchors, img_size, num_classes, idf, softmax, conf_thr
         m_iou = min(m_iou, float((iou - nms_thr).abs().min()))
     return {"score": m_score, "label": m_label, "iou": m_iou, "score_ties": ties,
             "candidates": [int(r["det6"].shape[0]) for r in cands]}
+
+
+# --------------------------------------------------------------------------------------
+# legacy per-head layer  (yolo/nets/yolo_loss.py:34-105, inference branch)
+# --------------------------------------------------------------------------------------
+def legacy_decode(head: Tensor, anchors_px, num_classes: int, img_size) -> Tensor:
+    """YOLOLoss.forward(input, targets=None): [B, A*(5+C), H, W] -> [B, A*H*W, 5+C], rows ordered (a, h, w)."""
+    bs, in_h, in_w = head.size(0), head.size(2), head.size(3)
+    na = len(anchors_px)
+    stride_h, stride_w = img_size / in_h, img_size / in_w                                   # :38-39
+    scaled = [(a_w / stride_w, a_h / stride_h) for a_w, a_h in anchors_px]                  # :40
+    pred = head.view(bs, na, 5 + num_classes, in_h, in_w).permute(0, 1, 3, 4, 2).contiguous()   # :42
+    x, y = torch.sigmoid(pred[..., 0]), torch.sigmoid(pred[..., 1])                          # :76-77
+    w, h = pred[..., 2], pred[..., 3]
+    conf, cls = torch.sigmoid(pred[..., 4]), torch.sigmoid(pred[..., 5:])                    # :80-81
+    grid_x = torch.linspace(0, in_w - 1, in_w).repeat(in_w, 1).repeat(bs * na, 1, 1).view(x.shape)      # :86-87
+    grid_y = torch.linspace(0, in_h - 1, in_h).repeat(in_h, 1).t().repeat(bs * na, 1, 1).view(y.shape)  # :88-89
+    sa = torch.tensor(scaled, dtype=torch.float32)
+    anchor_w = sa[:, 0:1].repeat(bs, 1).repeat(1, 1, in_h * in_w).view(w.shape)              # :91-94
+    anchor_h = sa[:, 1:2].repeat(bs, 1).repeat(1, 1, in_h * in_w).view(h.shape)
+    boxes = torch.empty(pred[..., :4].shape)
+    boxes[..., 0] = x + grid_x                                                               # :97-100
+    boxes[..., 1] = y + grid_y
+    boxes[..., 2] = torch.exp(w) * anchor_w
+    boxes[..., 3] = torch.exp(h) * anchor_h
+    scale = torch.tensor([stride_w, stride_h] * 2, dtype=torch.float32)                      # :102
+    return torch.cat((boxes.view(bs, -1, 4) * scale, conf.view(bs, -1, 1), cls.view(bs, -1, num_classes)), -1)

@@ -208,3 +208,87 @@ def test_rpn_filter_proposals_bound_like_the_reference():
         for i in range(bsz):
             np.testing.assert_array_equal(boxes[i].cpu().numpy(), gold[f"{tag}_boxes_{i}"])
             np.testing.assert_allclose(scores[i].cpu().numpy(), gold[f"{tag}_scores_{i}"], rtol=1e-5)
+
+
+# --------------------------------------------------------------------------- yolo_loss.py (legacy)
+@pytest.mark.parametrize("grid,head_idx,classes,img", [(13, 0, 80, 416), (38, 1, 20, 608), (7, 2, 3, 224)])
+def test_legacy_yololoss_forward(grid, head_idx, classes, img):
+    """YOLOLoss(cfg, head).forward(input): rows ordered (a, h, w), tolerance of the decode contract
+    (coordinates 1e-5 * max(|ref|, img_size), probabilities 1e-5 * |ref| + 1e-12)."""
+    from object_detectors_b200.yolo.nets.yolo_loss import YOLOLoss
+    x = torch.from_numpy(syn.legacy_head(77 + grid, 2, 3, classes, grid))
+    cfg = dict(anchors=[[list(a) for a in s] for s in syn.COCO_ANCHORS], classes=classes, img_size=img,
+               ignore_threshold=0.5)
+    got = YOLOLoss(cfg, head_idx)(x.cuda()).cpu().numpy()
+    ref = yolo_ref.legacy_decode(x, syn.COCO_ANCHORS[head_idx], classes, img).numpy()
+    assert got.shape == ref.shape == (2, 3 * grid * grid, 5 + classes)
+    assert np.all(np.abs(got[..., :4] - ref[..., :4]) <= 1e-5 * np.maximum(np.abs(ref[..., :4]), img))
+    assert np.all(np.abs(got[..., 4:] - ref[..., 4:]) <= 1e-5 * np.abs(ref[..., 4:]) + 1e-12)
+    if grid == 13:      # and against the reference's own output
+        gold = np.load(os.path.join(G, "legacy_yolo_loss.npz"))
+        s = gold["h13_sample"]
+        g = got[:, gold["h13_rows"]]
+        assert np.all(np.abs(g[..., :4] - s[..., :4]) <= 1e-5 * np.maximum(np.abs(s[..., :4]), img))
+        assert np.all(np.abs(g[..., 4:] - s[..., 4:]) <= 1e-5 * np.abs(s[..., 4:]) + 1e-12)
+
+
+def test_legacy_yololoss_get_target():
+    from object_detectors_b200.yolo.nets.yolo_loss import YOLOLoss
+    cfg = dict(anchors=[[list(a) for a in s] for s in syn.COCO_ANCHORS], classes=80, img_size=416, ignore_threshold=0.5)
+    layer = YOLOLoss(cfg, 1)
+    targets = [{k: torch.from_numpy(v) for k, v in t.items()} for t in syn.gt_targets(33, 2, 80, max_gt=12)]
+    stride = 416 / 26
+    scaled = [(a_w / stride, a_h / stride) for a_w, a_h in syn.COCO_ANCHORS[1]]
+    mask, noobj, tx, ty, tw, th, tconf, tcls = layer.get_target(targets, scaled, 26, 26, 0.5)
+    # restated with torchvision's CPU box_iou exactly as yolo_loss.py:107-161 does
+    for b, t in enumerate(targets):
+        bbox = t["bbox"]
+        gx = torch.clamp(bbox[:, 0] * 26, 0, 26 - 1e-4); gy = torch.clamp(bbox[:, 1] * 26, 0, 26 - 1e-4)
+        gt_box = torch.zeros(bbox.shape); gt_box[:, 2] = bbox[:, 2] * 26; gt_box[:, 3] = bbox[:, 3] * 26
+        shapes = torch.cat([torch.zeros(3, 2), torch.tensor(scaled, dtype=torch.float32)], 1)
+        ious = tv_ref.box_iou(gt_box, shapes)
+        best = ious.max(1)[1]
+        gi, gj = gx.long(), gy.long()
+        assert bool((mask[b, best, gj, gi] == 1).all()) and bool((noobj[b, best, gj, gi] == 0).all())
+        assert int(mask[b].sum()) == len(set(zip(best.tolist(), gj.tolist(), gi.tolist())))
+        want_noobj = torch.ones(3, 26, 26)
+        for i, row in enumerate(ious):
+            want_noobj[row > 0.5, gj[i], gi[i]] = 0
+        want_noobj[best, gj, gi] = 0
+        np.testing.assert_array_equal(noobj[b].cpu().numpy(), want_noobj.numpy())
+
+
+# --------------------------------------------------------------------------------- roi_heads.py
+@pytest.mark.parametrize("tag,loss_name", [("ce", "ce"), ("gombit", "gombit_x"), ("sigmoid", "bce")])
+@pytest.mark.parametrize("strategy", ["vanilla", "coordinate_trick", "torchvision"])
+def test_roi_postprocess_detections_bound_like_the_reference(tag, loss_name, strategy):
+    """postprocess_detections bound onto a RoIHeads-like object; expected values: the oracle (pinned to the
+    reference by tests/test_oracle_golden.py) with the same batched_nms strategy, and for the installed
+    torchvision's own switch (4000 coordinates on CPU) the reference's golden output itself."""
+    from object_detectors_b200 import _lib
+    from object_detectors_b200.tvision import _utils as det_utils, roi_heads as b200_roi
+    gold = np.load(os.path.join(G, "roi_postprocess.npz"))
+    seed, r0, r1, c, ih, iw = [int(v) for v in gold["args"]]
+    logits, regs, props = syn.roi_inputs(seed, [r0, r1], c, ih, iw)
+    idf = torch.from_numpy(gold["idf"])
+    head = types.SimpleNamespace(box_coder=det_utils.BoxCoder((10.0, 10.0, 5.0, 5.0)), loss_function_name=loss_name,
+                                 tfidf_post=idf.cuda(), score_thresh=0.05, nms_thresh=0.5, detections_per_img=100)
+    lib = _lib.load()
+    if strategy == "torchvision":
+        lib.b200_set_batched_nms_auto_limit(4000)        # the CPU oracle's switch point
+    try:
+        boxes, scores, labels = b200_roi.postprocess_detections(
+            head, torch.from_numpy(logits).cuda(), torch.from_numpy(regs).cuda(), [torch.from_numpy(p).cuda() for p in props],
+            [(ih, iw)] * 2, strategy=strategy)
+    finally:
+        lib.b200_set_batched_nms_auto_limit(100000)
+    ref = tv_ref.roi_postprocess(torch.from_numpy(logits), torch.from_numpy(regs), [torch.from_numpy(p) for p in props],
+                                 [(ih, iw)] * 2, idf, loss_name, strategy=strategy)
+    for i, (rb, rs, rl, _) in enumerate(ref):
+        np.testing.assert_array_equal(labels[i].cpu().numpy(), rl.numpy())
+        s, b = scores[i].cpu().numpy(), boxes[i].cpu().numpy()
+        assert np.all(np.abs(s - rs.numpy()) <= 1e-5 * np.abs(rs.numpy()) + 1e-12)
+        assert np.all(np.abs(b - rb.numpy()) <= 1e-5 * np.maximum(np.abs(rb.numpy()), max(ih, iw)))
+        if strategy == "torchvision":
+            np.testing.assert_array_equal(labels[i].cpu().numpy(), gold[f"{tag}_labels_{i}"])
+            assert np.all(np.abs(s - gold[f"{tag}_scores_{i}"]) <= 1e-5 * np.abs(gold[f"{tag}_scores_{i}"]) + 1e-12)

@@ -146,3 +146,29 @@ def test_rpn_filter():
         for i in range(bsz):
             np.testing.assert_array_equal(gold[f"{tag}_boxes_{i}"], fb[i].numpy())
             np.testing.assert_array_equal(gold[f"{tag}_scores_{i}"], fs[i].numpy())
+
+
+@pytest.mark.parametrize("tag", ["h13", "h38"])
+def test_legacy_yolo_loss_decode(tag):
+    """oracle.yolo_ref.legacy_decode == YOLOLoss.forward(input) of the reference (yolo_loss.py:34-105), bit for bit."""
+    gold = np.load(os.path.join(G, "legacy_yolo_loss.npz"))
+    seed, grid, head_idx, classes, img = [int(v) for v in gold[f"{tag}_args"]]
+    x = torch.from_numpy(syn.legacy_head(seed, 2, 3, classes, grid))
+    out = yolo_ref.legacy_decode(x, syn.COCO_ANCHORS[head_idx], classes, img)
+    rows = torch.from_numpy(gold[f"{tag}_rows"])
+    np.testing.assert_array_equal(out[:, rows].numpy(), gold[f"{tag}_sample"])
+    np.testing.assert_array_equal(out.double().sum(dim=1).numpy(), gold[f"{tag}_colsum"])
+
+
+@pytest.mark.parametrize("tag,activation", [("ce", "ce"), ("gombit", "gombit_x"), ("sigmoid", "bce")])
+def test_roi_postprocess(tag, activation):
+    """oracle.tv_ref.roi_postprocess == RoIHeads.postprocess_detections of the reference (roi_heads.py:715-781)."""
+    gold = np.load(os.path.join(G, "roi_postprocess.npz"))
+    seed, r0, r1, c, ih, iw = [int(v) for v in gold["args"]]
+    logits, regs, props = syn.roi_inputs(seed, [r0, r1], c, ih, iw)
+    res = tv_ref.roi_postprocess(torch.from_numpy(logits), torch.from_numpy(regs), [torch.from_numpy(p) for p in props],
+                                 [(ih, iw)] * 2, torch.from_numpy(gold["idf"]), activation, strategy="torchvision")
+    for i, (b, s, l, _) in enumerate(res):
+        np.testing.assert_array_equal(l.numpy(), gold[f"{tag}_labels_{i}"])
+        np.testing.assert_array_equal(s.numpy(), gold[f"{tag}_scores_{i}"])
+        np.testing.assert_array_equal(b.numpy(), gold[f"{tag}_boxes_{i}"])
