@@ -43,6 +43,7 @@ sys.path.insert(0, ROOT)
 from object_detectors_b200 import synthetic as syn  # noqa: E402
 
 METRIC = "images/sec decode+NMS, YOLOv3-608 COCO b64"
+NO_EXCHANGE = bool(os.environ.get("B200_BENCH_NO_EXCHANGE"))     # diagnostic only: N ranks without the all-gather
 IMG, NUM_CLASSES, BATCH = 608, 80, 64
 CONF_THR, NMS_THR = 0.1, 0.6
 MAX_DET = 256          # kept-detection capacity per image in the exchanged message
@@ -82,6 +83,8 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvidia-smi needs ~100 ms to deliver its first sample, so it is started before the warm-up; every line is
+    # stamped on arrival and only those that fall inside [t0, t1] of the timed region are reported
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
@@ -98,9 +101,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -111,7 +114,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        inside = [ln for ts, ln in self.lines if t0 is None or (t0 <= ts <= t1 + 0.03)]
+        window = "timed region"
+        if not inside:                      # region shorter than the sampling period: fall back to the whole run under load
+            inside, window = [ln for _, ln in self.lines], "whole run (timed region shorter than one sample)"
+        for ln in inside:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 6:
                 continue
@@ -123,7 +130,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def make_heads(seed: int, batch: int):
@@ -206,9 +213,6 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # the exchanged messages are a few hundred KB: one or two NCCL channels (CTAs) move them, more would only
-        # take SMs from the decode stream
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     VARIANTS = {"gated": 0, "stream": 1, "bulk": 2, "ring": 3}
@@ -239,7 +243,7 @@ def run_b200(args):
     dec_done = [torch.cuda.Event() for _ in plans]
     nms_done = [torch.cuda.Event() for _ in plans]      # workspace + outputs of plan k are free again
     det_ready = [torch.cuda.Event() for _ in plans]
-    exchange = DetectionExchange(BATCH, MAX_DET, dev, slots=n_p)
+    exchange = DetectionExchange(BATCH, MAX_DET, dev, bucket=args.exchange_every)
     serial = [False]          # True: one stream does everything (the isolated-kernel measurement)
 
     def step(i):
@@ -255,16 +259,17 @@ def run_b200(args):
             dec_done[k].record(d)
             n.wait_event(dec_done[k])
         pl.nms(n)
-        if world > 1:
+        if world > 1 and not NO_EXCHANGE:
             x = n if serial[0] else x_stream
             if not serial[0]:
                 det_ready[k].record(n)
                 x.wait_event(det_ready[k])
-            exchange(pl.det, pl.det_count, x, k)
+            exchange(pl.det, pl.det_count, x)        # pack (+ all-gather when the bucket is full)
             if not serial[0]:
                 nms_done[k].record(x)
         elif not serial[0]:
             nms_done[k].record(n)
+
 
     def fence_in():
         ev = torch.cuda.Event()
@@ -275,6 +280,8 @@ def run_b200(args):
             e.record()
 
     def fence_out():
+        if world > 1:
+            exchange.flush(d_streams[0] if serial[0] else x_stream)     # partial bucket: nothing stays behind
         for st in streams:
             torch.cuda.current_stream().wait_stream(st)
 
@@ -295,8 +302,8 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        if sample_clocks and rank == 0:
-            sampler.start()
+        if sample_clocks:
+            window[0] = time.perf_counter()
         t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_begin.record()
         fence_in()
@@ -309,6 +316,8 @@ def run_b200(args):
         fence_out()
         t_end.record()
         torch.cuda.synchronize()
+        if sample_clocks:
+            window[1] = time.perf_counter()
         if world > 1:
             dist.barrier()
         ms = t_begin.elapsed_time(t_end)
@@ -334,9 +343,13 @@ def run_b200(args):
         return float(t[0]), float(t[1]), float(t[2])
 
     host_us = [0.0]
+    window = [None, None]
     sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)          # let nvidia-smi deliver its first sample before the (sub-second) timed region
     ms_total, k_ms, k_busy = timed_loop(args.steps, max(args.warmup, 3), sample_clocks=True)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(window[0], window[1]) if rank == 0 else None
     host_enqueue_us = host_us[0]
     plan = plans[0]
     kept = int(plan.det_count.sum())
@@ -403,7 +416,8 @@ def run_b200(args):
                        "candidates_per_step": cands, "kept_per_step": kept,
                        "pipeline": {"decode_streams": n_d, "nms_streams": n_n, "workspaces": n_p, "ring": args.ring},
                        "decode_variant": args.variant,
-                       "exchange": ("ncclAllGather of fixed-capacity kept lists, " +
+                       "exchange": (f"ncclAllGather of fixed-capacity kept lists, {args.exchange_every} steps per bucket "
+                                    f"(every step packed on the device, partial bucket flushed inside the timed region), " +
                                     ("direct NCCL binding" if exchange.nccl is not None else "torch.distributed"))
                        if world > 1 else "none (1 GPU)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -418,7 +432,8 @@ def run_b200(args):
                                        "(torch CPU ops, all host threads)"},
             "e2e": {"value": world * BATCH * e2e_steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-            "gpu_launches": args.steps * (4 + (2 if world > 1 else 0)),
+            "gpu_launches": args.steps * (4 + (1 if world > 1 else 0)) +
+                            (-(-args.steps // max(1, args.exchange_every)) if world > 1 else 0),
             "host_enqueue_us_per_step": host_enqueue_us,
             "clocks": clocks,
             "other_variant": other_variant,
@@ -440,6 +455,8 @@ def main():
     ap.add_argument("--dstreams", type=int, default=3, help="decode streams = decode kernels in flight")
     ap.add_argument("--nstreams", type=int, default=3, help="streams for the NMS chains (+ exchange)")
     ap.add_argument("--plans", type=int, default=6, help="rotating workspaces")
+    ap.add_argument("--exchange-every", type=int, default=4,
+                    help="N > 1: steps per all-gather bucket (1 = gather after every step)")
     ap.add_argument("--ring", default="4,1,101", help="RING decode: warps per CTA, stages per warp, CTAs per SM (+100: 32-cell tiles)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -51,8 +51,14 @@ def unpack_detections(gathered: torch.Tensor, world: int, batch: int, max_det: i
 
 class DetectionExchange:
     """The path's one exchange step for a fixed (batch, max_det): pack kernel + all-gather, enqueued on the
-    caller's stream with two ctypes calls (~5 us of host time; ``all_gather_into_tensor`` costs ~10x that in
+    caller's stream with plain ctypes calls (~5 us of host time; ``all_gather_into_tensor`` costs ~10x that in
     Python/c10d dispatch, which at ~90 us per step is what decides multi-GPU scaling).
+
+    Messages are bucketed: every step's kept lists are packed into the next slot of a bucket on the device and
+    one ``ncclAllGather`` moves ``bucket`` steps at a time (``flush`` sends a partial bucket), so the ranks
+    synchronise -- and pay the collective's launch + 8-hop latency -- once per bucket instead of once per
+    step.  The payload is tiny (393 KB per rank and step for 64 images x 256 detections), NVLink bandwidth is
+    never the issue; latency and rank skew are.  ``bucket=1`` gathers after every step.
 
     The collective is NCCL's ``ncclAllGather`` on a communicator of our own, created through the NCCL library
     the process has already loaded (torch's), bootstrapped over the existing process group.  If that library
@@ -61,17 +67,19 @@ class DetectionExchange:
 
     NCCL_FLOAT = 7
 
-    def __init__(self, batch: int, max_det: int, device, slots: int = 1):
+    def __init__(self, batch: int, max_det: int, device, bucket: int = 1):
         import ctypes as C
         from . import _lib
         self.lib = _lib.load()
-        self.batch, self.max_det = batch, max_det
+        self.batch, self.max_det, self.bucket = batch, max_det, max(1, int(bucket))
         self.dev = torch.device(device)
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
-        n = message_len(batch, max_det)
-        self.msg = [torch.empty((n,), dtype=torch.float32, device=self.dev) for _ in range(slots)]
-        self.out = [torch.empty((self.world * n,), dtype=torch.float32, device=self.dev) for _ in range(slots)]
+        self.n = message_len(batch, max_det)
+        # two buckets alternate: one is being filled while the previous one may still be read by a consumer
+        self.msg = [torch.zeros((self.bucket * self.n,), dtype=torch.float32, device=self.dev) for _ in range(2)]
+        self.out = [torch.zeros((self.world * self.bucket * self.n,), dtype=torch.float32, device=self.dev) for _ in range(2)]
+        self.fill, self.cur, self.gathers = 0, 0, 0
         self.nccl, self.comm = None, None
         if self.world > 1:
             try:
@@ -102,25 +110,43 @@ class DetectionExchange:
             raise RuntimeError("ncclCommInitRank failed")
         self.nccl, self.comm = nccl, comm
 
-    def __call__(self, det: torch.Tensor, det_count: torch.Tensor, stream: torch.cuda.Stream, slot: int = 0) -> torch.Tensor:
-        """pack + all-gather on ``stream``; returns the gathered buffer ``[world * message_len]`` of ``slot``."""
+    def _gather(self, stream: torch.cuda.Stream, steps: int) -> torch.Tensor:
+        import ctypes as C
+        msg, out = self.msg[self.cur], self.out[self.cur]
+        count = steps * self.n
+        if self.world > 1:
+            if self.nccl is not None:
+                rc = self.nccl.ncclAllGather(C.c_void_p(msg.data_ptr()), C.c_void_p(out.data_ptr()), count, self.NCCL_FLOAT,
+                                             self.comm, C.c_void_p(stream.cuda_stream))
+                if rc != 0:
+                    raise RuntimeError(f"ncclAllGather failed ({rc})")
+            else:
+                with torch.cuda.stream(stream):
+                    dist.all_gather_into_tensor(out[:self.world * count], msg[:count])
+        self.gathers += 1
+        self.fill, self.cur = 0, self.cur ^ 1
+        return out if self.world > 1 else msg
+
+    def __call__(self, det: torch.Tensor, det_count: torch.Tensor, stream: torch.cuda.Stream):
+        """Packs one step's detections into the current bucket on ``stream``; when the bucket is full the whole
+        bucket is all-gathered on the same stream and the gathered buffer is returned
+        (``[world, steps, message_len]``, rank-major), else ``None``."""
         import ctypes as C
         from . import _lib
-        st = C.c_void_p(stream.cuda_stream)
-        msg, out = self.msg[slot], self.out[slot]
+        dst = self.msg[self.cur].data_ptr() + 4 * self.fill * self.n
         _lib.check(self.lib.b200_pack_detections(C.c_void_p(det.data_ptr()), C.c_void_p(det_count.data_ptr()), self.batch,
-                                                 self.max_det, C.c_void_p(msg.data_ptr()), st), "b200_pack_detections")
-        if self.world == 1:
-            return msg
-        if self.nccl is not None:
-            rc = self.nccl.ncclAllGather(C.c_void_p(msg.data_ptr()), C.c_void_p(out.data_ptr()), msg.numel(), self.NCCL_FLOAT,
-                                         self.comm, st)
-            if rc != 0:
-                raise RuntimeError(f"ncclAllGather failed ({rc})")
-        else:
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(out, msg)
-        return out
+                                                 self.max_det, C.c_void_p(dst), C.c_void_p(stream.cuda_stream)),
+                   "b200_pack_detections")
+        self.fill += 1
+        if self.fill == self.bucket:
+            return self._gather(stream, self.bucket)
+        return None
+
+    def flush(self, stream: torch.cuda.Stream):
+        """All-gathers a partially filled bucket (end of an epoch / of the timed region)."""
+        if self.fill:
+            return self._gather(stream, self.fill)
+        return None
 
     def close(self):
         if self.nccl is not None and self.comm is not None:
