@@ -91,11 +91,42 @@ def c5_rpn(reps, batch=16):
     return out
 
 
+def dense_decode(reps, batch=64):
+    heads = [torch.from_numpy(h).cuda() for h in syn.yolo_heads(1000, batch, 608, 80, syn.COCO_ANCHORS, "clustered")]
+    idf = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "idf_coco_smooth.npy"))).cuda()
+    ms = timeit(lambda: ops.yolo_decode_dense(heads, syn.COCO_ANCHORS, 608, 80, idf, True), reps)
+    nbytes = 2 * sum(h.numel() * 4 for h in heads)          # one read + one write of [B, N, 85]
+    out = [{"config": f"a1 YOLOForw.forward dense decode 608 COCO b{batch} (softmax x IDF)", "ms": ms,
+            "images_per_s": batch / ms * 1e3, "algorithmic_GBs": nbytes / ms / 1e6, "hbm_frac": nbytes / ms / 1e6 / HBM_GBS}]
+    x = torch.from_numpy(syn.legacy_head(5, batch, 3, 80, 76)).cuda()
+    ms = timeit(lambda: ops.yolo_legacy_decode(x, syn.COCO_ANCHORS[2], 80, 608), reps)
+    nbytes = 2 * x.numel() * 4
+    out.append({"config": f"a9 legacy YOLOLoss.forward decode, 76x76 head b{batch}", "ms": ms,
+                "algorithmic_GBs": nbytes / ms / 1e6, "hbm_frac": nbytes / ms / 1e6 / HBM_GBS})
+    return out
+
+
+def roi_heads(reps):
+    out = []
+    for name, c, batch, rows in (("COCO-91", 91, 16, 1000), ("LVIS-1204", 1204, 4, 1000)):
+        logits, regs, props = syn.roi_inputs(51, [rows] * batch, c, 800, 1216)
+        lg, rg = torch.from_numpy(logits).cuda(), torch.from_numpy(regs).cuda()
+        pr = [torch.from_numpy(p).cuda() for p in props]
+        shapes = [(800, 1216)] * batch
+        ms = timeit(lambda: ops.roi_postprocess(lg, rg, pr, shapes, None, ops.ROI_SOFTMAX, capacity=8192), reps)
+        det, keep, dcnt, ccnt, status = ops.roi_postprocess(lg, rg, pr, shapes, None, ops.ROI_SOFTMAX, capacity=8192)
+        nbytes = (lg.numel() + rg.numel()) * 4
+        out.append({"config": f"a13 RoIHeads.postprocess_detections {name} b{batch} x {rows} proposals", "ms": ms,
+                    "images_per_s": batch / ms * 1e3, "input_GBs": nbytes / ms / 1e6, "candidates": int(ccnt.sum()),
+                    "kept": int(dcnt.sum()), "status": int(status.item())})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     args = ap.parse_args()
-    rows = [c3_lvis(max(args.reps // 4, 3))] + c4_match(args.reps) + c5_rpn(args.reps)
+    rows = [c3_lvis(max(args.reps // 4, 3))] + c4_match(args.reps) + c5_rpn(args.reps) + dense_decode(args.reps) + roi_heads(args.reps)
     for r in rows:
         print(json.dumps(r), flush=True)
 

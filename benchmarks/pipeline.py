@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--plans", type=int, default=4)
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--hiprio", action="store_true", help="NMS streams get high priority")
+    ap.add_argument("--no-nms", action="store_true", help="decode kernels only (how fast is the HBM stage alone?)")
+    ap.add_argument("--conf", type=float, default=0.1)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     lib = _lib.load()
@@ -41,8 +43,11 @@ def main():
     heads = [torch.from_numpy(h).to(dev) for h in syn.yolo_heads(1000, BATCH, IMG, NC, syn.COCO_ANCHORS, "clustered")]
     idf = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "idf_coco_smooth.npy"))).to(dev)
     grids = [h.shape[2] for h in heads]
-    plans = [ops.YoloPostprocess(grids, BATCH, syn.COCO_ANCHORS, IMG, NC, True, 0.1, 0.6, ops.NMS_MAJORITY, 4096, 256, dev)
+    plans = [ops.YoloPostprocess(grids, BATCH, syn.COCO_ANCHORS, IMG, NC, True, args.conf, 0.6, ops.NMS_MAJORITY, 4096, 256, dev)
              for _ in range(args.plans)]
+    # every workspace reads its own copy of the input (batch rolled): concurrently running decode kernels must not
+    # find each other's lines in L2
+    inputs = [[h.roll(7 * k, 0).contiguous() for h in heads] for k in range(args.plans)]
     ds = [torch.cuda.Stream(device=dev) for _ in range(args.dstreams)]
     nst = [torch.cuda.Stream(device=dev, priority=-1 if args.hiprio else 0) for _ in range(args.nstreams)]
     dec_done = [torch.cuda.Event() for _ in plans]
@@ -57,8 +62,11 @@ def main():
             d.wait_event(nms_done[k])                 # the workspace is free again
             if ev is not None:
                 lib.b200_debug_set_decode_events(C.c_void_p(ev[0].cuda_event), C.c_void_p(ev[1].cuda_event))
-            plans[k].decode(heads, idf)
+            plans[k].decode(inputs[k], idf)
             dec_done[k].record(d)
+        if args.no_nms:
+            nms_done[k].record(d)
+            return
         with torch.cuda.stream(n):
             n.wait_event(dec_done[k])
             if ev is not None:
@@ -87,7 +95,10 @@ def main():
     torch.cuda.synchronize()
     for pl in plans:
         pl.check_status()
-        assert (int(pl.cand_count.sum()), int(pl.det_count.sum())) == ref
+        assert args.no_nms or (int(pl.cand_count.sum()), int(pl.det_count.sum())) == ref
+    if args.no_nms:
+        for row in evs:
+            row[2] = row[3] = row[4] = row[1]
     ts = np.array([[t0.elapsed_time(e) * 1e3 for e in row] for row in evs])
     lo = args.steps // 4
     period = (ts[-1, 4] - ts[lo, 4]) / (args.steps - 1 - lo)

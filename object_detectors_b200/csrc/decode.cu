@@ -574,7 +574,208 @@ k_decode_dense(const __grid_constant__ DenseParams q) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// dense decode, staged variant (5+C <= kDenseMaxCh): one CTA = 64 cells of one (scale, b, a)
+// ------------------------------------------------------------------------------------------
+// The (5+C) x 64 tile is read once with coalesced row loads into shared memory (row stride 65 floats: both
+// the row-wise and the column-wise accesses below are bank-conflict free), the softmax statistics of a cell
+// are computed by 4 threads over disjoint class quarters, and the output rows (5+C contiguous floats each)
+// are written by warps with lanes across channels.  Every input byte is read once and every output byte
+// written once; 8 CTAs per SM hide the latency.
+// probabilities of the dense outputs: ex2.approx (2 ulp) + correctly rounded reciprocal -- well inside the 1e-5
+// relative contract and a third of the instructions of expf + IEEE division; box coordinates keep expf
+__device__ __forceinline__ float sigmoid_fast(float x) {
+    return __frcp_rn(__fadd_rn(1.0f, ex2_approx(__fmul_rn(-x, kLog2e))));
+}
+
+static constexpr int kDenseCells = 64;
+static constexpr int kDenseLd = kDenseCells + 1;
+static constexpr int kDenseMaxCh = 184;          // (5+C) * 65 * 4 B <= 48 KB
+
+struct Dense2Params {
+    DecodeParams d;
+    float* out;
+    int softmax;
+    int cta_begin[B200_MAX_SCALES + 1];
+    int tiles[B200_MAX_SCALES];
+    // legacy (YOLOLoss) mode: one scale, rows ordered (a, h, w), xy = (sigmoid + grid) * stride, sigmoid classes
+    int legacy, in_w;
+    float stride_w, stride_h;
+    const float* legacy_anchors;                 // device [A][2], scaled
+};
+
+__global__ void __launch_bounds__(256)
+k_decode_dense2(const __grid_constant__ Dense2Params q) {
+    extern __shared__ float dsm[];
+    const DecodeParams& p = q.d;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = p.C, CH = 5 + C;
+    float* tile = dsm;                            // [CH][65]
+    float* part = tile + CH * kDenseLd;           // [4][64] partial max / partial sums
+    float* st_m = part + 4 * kDenseCells;         // [64]
+    float* st_r = st_m + kDenseCells;             // [64] 1 / denominator
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < B200_MAX_SCALES; ++i)
+        if (i < p.num_scales && (int)blockIdx.x >= q.cta_begin[i]) s = i;
+    const ScaleDev& sc = p.sc[s];
+    const int local = blockIdx.x - q.cta_begin[s];
+    const int tl = local % q.tiles[s], ba = local / q.tiles[s];
+    const int a = ba % p.A, b = ba / p.A;
+    const int cell0 = tl * kDenseCells;
+    const int ncell = min(kDenseCells, sc.hw - cell0);
+    const float* src = sc.head + (size_t)ba * (size_t)CH * (size_t)sc.hw + (size_t)cell0;
+
+    // ---- A. stage the tile: one warp per plane row, 2 cells per lane; 4 rows (8 loads) in flight per warp ----
+    for (int r0 = warp; r0 < CH; r0 += 32) {
+        float v[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + 8 * j;
+            const float* row = src + (size_t)r * (size_t)sc.hw;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int c = lane + 32 * k;
+                v[j][k] = (r < CH && c < ncell) ? ldg_stream_f32(row + c) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + 8 * j;
+            if (r < CH) {
+                tile[r * kDenseLd + lane] = v[j][0];
+                tile[r * kDenseLd + lane + 32] = v[j][1];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- B. softmax statistics: thread (quarter, cell) -----------------------------------------------------
+    const bool softmax = q.softmax && !q.legacy;
+    if (softmax) {
+        const int cell = tid & 63, qtr = tid >> 6;
+        float m = -INFINITY;
+        for (int c = qtr; c < C; c += 4) {
+            const float x = p.idf ? __fmul_rn(__ldg(p.idf + c), tile[(5 + c) * kDenseLd + cell]) : tile[(5 + c) * kDenseLd + cell];
+            m = fmaxf(m, x);
+        }
+        part[qtr * kDenseCells + cell] = m;
+        __syncthreads();
+        m = fmaxf(fmaxf(part[cell], part[kDenseCells + cell]), fmaxf(part[2 * kDenseCells + cell], part[3 * kDenseCells + cell]));
+        __syncthreads();
+        float sum = 0.f;
+        for (int c = qtr; c < C; c += 4) {
+            const float x = p.idf ? __fmul_rn(__ldg(p.idf + c), tile[(5 + c) * kDenseLd + cell]) : tile[(5 + c) * kDenseLd + cell];
+            sum = __fadd_rn(sum, ex2_approx(__fmul_rn(__fsub_rn(x, m), kLog2e)));
+        }
+        part[qtr * kDenseCells + cell] = sum;
+        __syncthreads();
+        if (qtr == 0) {
+            const float tot = __fadd_rn(__fadd_rn(part[cell], part[kDenseCells + cell]),
+                                        __fadd_rn(part[2 * kDenseCells + cell], part[3 * kDenseCells + cell]));
+            st_m[cell] = m;
+            st_r[cell] = __fdiv_rn(1.0f, tot);
+        }
+        __syncthreads();
+    }
+
+    // ---- C. box and objectness planes in place: thread = (plane, cell), so a warp runs ONE of the five
+    //      formulas on 32 cells (with lanes across channels the first five lanes would serialise five different
+    //      transcendental sequences for every cell) ------------------------------------------------------------
+    for (int item = tid; item < 5 * kDenseCells; item += 256) {
+        const int ch = item >> 6, cl = item & 63;
+        if (cl >= ncell) continue;
+        const int hw = cell0 + cl;
+        const float t = tile[ch * kDenseLd + cl];
+        float r;
+        if (q.legacy) {
+            if (ch == 0) r = __fmul_rn(__fadd_rn(sigmoid_ref(t), (float)(hw % q.in_w)), q.stride_w);        // yolo_loss.py:97,103
+            else if (ch == 1) r = __fmul_rn(__fadd_rn(sigmoid_ref(t), (float)(hw / q.in_w)), q.stride_h);   // :98
+            else if (ch == 2) r = __fmul_rn(__fmul_rn(expf(t), q.legacy_anchors[2 * a]), q.stride_w);       // :99
+            else if (ch == 3) r = __fmul_rn(__fmul_rn(expf(t), q.legacy_anchors[2 * a + 1]), q.stride_h);   // :100
+            else r = sigmoid_fast(t);
+        } else {
+            if (ch < 2) {
+                const int gy_i = hw / sc.grid, gx_i = hw - gy_i * sc.grid;
+                // xy = (sigmoid(t) + cxy*inw - 0.5) * stride, cxy = (idx + 0.5) / in_w     (yolo_forw.py:104-107,166)
+                const float g = __fmul_rn(__fdiv_rn((float)(ch == 0 ? gx_i : gy_i) + 0.5f, sc.inw), sc.inw);
+                r = __fmul_rn(__fsub_rn(__fadd_rn(sigmoid_ref(t), g), 0.5f), sc.stride);
+            } else if (ch < 4) {
+                // wh = exp(t) * cwh * inw * stride  (left to right)                          (:167)
+                r = __fmul_rn(__fmul_rn(__fmul_rn(expf(t), sc.anc[a][ch - 2]), sc.inw), sc.stride);
+            } else {
+                r = sigmoid_fast(t);
+            }
+        }
+        tile[ch * kDenseLd + cl] = r;
+    }
+    __syncthreads();
+
+    // ---- D. output rows: one warp per cell, lanes across the 5+C channels ---------------------------------
+    for (int cl = warp; cl < ncell; cl += 8) {
+        const int hw = cell0 + cl;
+        float* dst = q.legacy ? q.out + ((size_t)ba * (size_t)sc.hw + (size_t)hw) * (size_t)CH            // n = a*H*W + h*W + w
+                              : q.out + ((size_t)b * (size_t)p.N + (size_t)sc.anchor_off + (size_t)hw * p.A + a) * (size_t)CH;
+        const float m = softmax ? st_m[cl] : 0.f, rinv = softmax ? st_r[cl] : 0.f;
+        for (int ch = lane; ch < CH; ch += 32) {
+            const float t = tile[ch * kDenseLd + cl];
+            float r = t;                                     // planes 0-4 are final already
+            if (ch >= 5) {
+                if (q.legacy) r = sigmoid_fast(t);
+                else {
+                    const float x = p.idf ? __fmul_rn(__ldg(p.idf + (ch - 5)), t) : t;
+                    r = softmax ? __fmul_rn(ex2_approx(__fmul_rn(__fsub_rn(x, m), kLog2e)), rinv) : sigmoid_fast(x);
+                }
+            }
+            dst[ch] = r;
+        }
+    }
+}
+
+static int launch_dense2(Dense2Params& q, cudaStream_t stream) {
+    const DecodeParams& p = q.d;
+    int t = 0;
+    for (int s = 0; s < B200_MAX_SCALES; ++s) {
+        q.cta_begin[s] = t;
+        q.tiles[s] = 1;
+        if (s < p.num_scales) {
+            q.tiles[s] = cdiv(p.sc[s].hw, kDenseCells);
+            t += p.B * p.A * q.tiles[s];
+        }
+    }
+    q.cta_begin[B200_MAX_SCALES] = t;
+    const size_t smem = (size_t)((5 + p.C) * kDenseLd + 6 * kDenseCells) * sizeof(float);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        if (cudaFuncSetAttribute(k_decode_dense2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return B200_ERR_CUDA;
+        attr = smem;
+    }
+    k_decode_dense2<<<t, 256, smem, stream>>>(q);
+    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
+
+// legacy YOLOLoss layer through the same kernel (one scale, own row order and xy/wh formulas)
+int launch_legacy_dense(const float* head, int B, int A, int C, int H, int W, float stride_w, float stride_h,
+                        const float* anchors_dev, float* out, cudaStream_t stream) {
+    if (5 + C > kDenseMaxCh) return 1;
+    Dense2Params q{};
+    q.d.num_scales = 1; q.d.A = A; q.d.C = C; q.d.B = B; q.d.N = A * H * W; q.d.idf = nullptr;
+    q.d.sc[0].head = head; q.d.sc[0].grid = W; q.d.sc[0].hw = H * W; q.d.sc[0].anchor_off = 0;
+    q.d.sc[0].inw = (float)W; q.d.sc[0].stride = stride_w;
+    q.out = out; q.softmax = 0; q.legacy = 1; q.in_w = W; q.stride_w = stride_w; q.stride_h = stride_h;
+    q.legacy_anchors = anchors_dev;
+    return launch_dense2(q, stream);
+}
+
 int launch_decode_dense(const DecodeParams& p, bool softmax, float* out, cudaStream_t stream) {
+    if (5 + p.C <= kDenseMaxCh) {
+        Dense2Params q2{};
+        q2.d = p;
+        q2.out = out;
+        q2.softmax = softmax ? 1 : 0;
+        return launch_dense2(q2, stream);
+    }
     DenseParams q;
     q.d = p;
     q.out = out;

@@ -297,7 +297,9 @@ k_nms_plan(const __grid_constant__ NmsParams P) {
     // ---- coordinate-trick unit, y range of the box centres ------------------------------------
     float unit = 0.f;
     // torchvision.ops.batched_nms: coordinate trick unless boxes.numel() > limit (then per-class "vanilla")
-    if (P.mode == B200_NMS_TV_TRICK || (P.mode == B200_NMS_TV_AUTO && 4ll * n_true <= P.auto_limit)) {
+    if (P.given_unit) {
+        unit = P.given_unit[seg];
+    } else if (P.mode == B200_NMS_TV_TRICK || (P.mode == B200_NMS_TV_AUTO && 4ll * n_true <= P.auto_limit)) {
         float mx = -INFINITY;
         for (int i = tid; i < n; i += kPlanThreads) {
             const float4 b = SLAB ? reinterpret_cast<const float4*>(P.slab + off + i)[0]

@@ -36,6 +36,8 @@ struct NmsParams {
     float thr_f;             // MAJORITY: threshold rounded to fp32 (tensor-vs-scalar compare)
     double thr_d;            // TV modes: compared against (double)iou
     int from_slab;
+    const float* given_unit;  // [S] or nullptr: coordinate-trick units supplied by the caller (segments that are
+                              // slices of one torchvision call share the unit of the whole call)
     long long auto_limit;    // TV_AUTO: segments with 4*n > auto_limit use the per-class arithmetic
     int anchor_space;        // slab path: flat anchor indices are < anchor_space (0 = unknown)
     int num_segments;

@@ -49,8 +49,14 @@ k_legacy_decode(const float* __restrict__ head, int A, int CH, int H, int W, flo
     }
 }
 
+int launch_legacy_dense(const float* head, int B, int A, int C, int H, int W, float stride_w, float stride_h,
+                        const float* anchors_dev, float* out, cudaStream_t stream);
+
 int launch_legacy_decode(const float* head, int B, int A, int C, int H, int W, float stride_w, float stride_h,
                          const float* anchors_dev, float* out, cudaStream_t st) {
+    // the staged 64-cell kernel of decode.cu when the channel count fits in shared memory, else the tiled transpose
+    const int rc = launch_legacy_dense(head, B, A, C, H, W, stride_w, stride_h, anchors_dev, out, st);
+    if (rc != 1) return rc;
     const int CH = 5 + C, HW = H * W;
     dim3 grid(cdiv(HW, 32), cdiv(CH, 32), B * A);
     if (grid.y > 65535 || grid.z > 65535) return B200_ERR_INVALID;

@@ -8,7 +8,8 @@
 //                 (score desc, index asc == Tensor.topk order for tie-free input) and only those
 //                 are decoded / clipped / filtered -- the reference decodes all 268 569 anchors
 //                 first (rpn.py:355).  Survivors are written in order at a fixed stride.
-//  k_rpn_concat : (coordinate-trick strategy only) packs the levels of an image contiguously.
+//  k_rpn_units  : (coordinate-trick strategy) the image's shift unit for its per-level segments (see below).
+//  k_rpn_concat : packs the levels of an image contiguously (single-segment layout, kept for reference runs).
 //  NMS          : the shared per-segment kernel of nms.cu (segments = image x level for the
 //                 vanilla strategy, = image for the coordinate trick).
 //  k_rpn_finish : merges an image's kept lists by score and emits the first post_nms_top_n.
@@ -259,12 +260,39 @@ k_rpn_finish(const __grid_constant__ RpnParams P) {
     if (tid == 0) P.out_count[b] = nout;
 }
 
+// Coordinate-trick arithmetic on per-level segments: torchvision shifts level l by l * (max coordinate of the
+// image's boxes + 1), so boxes of different levels never intersect and the one big NMS over the image decomposes
+// exactly into one NMS per level on the SHIFTED boxes.  This kernel computes the image's unit and hands it to
+// every (image, level) segment; the NMS then runs on L small segments instead of one of up to L*k boxes.
+__global__ void __launch_bounds__(256)
+k_rpn_units(const RpnParams P, float* __restrict__ units) {
+    __shared__ float red[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    float mx = -INFINITY;
+    for (int l = 0; l < P.L; ++l) {
+        const int n = P.seg_count[b * P.L + l];
+        const float4* box = P.box + (size_t)b * P.Ktot + P.level_koff[l];
+        for (int i = tid; i < n; i += 256) {
+            const float4 v = box[i];
+            mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    const float unit = __fadd_rn(mx, 1.0f);
+    for (int l = tid; l < P.L; l += 256) units[b * P.L + l] = unit;
+}
+
 // ------------------------------------------------------------------------------------------ host
 namespace {
 struct RpnWs {
     float4* box; float* score; int* label; int* aidx;
     int* seg_start; int* seg_count; int* img_start; int* img_count;
-    long long* keep; int* keep_count;
+    long long* keep; int* keep_count; float* units;
     void* nms; size_t nms_bytes;
 };
 // NMS scratch must serve either strategy: (B*L segments of <= pre_k) or (B segments of <= L*pre_k)
@@ -284,6 +312,7 @@ size_t rpn_carve(int batch, int levels, int pre_k, void* base, size_t bytes, Rpn
     t.seg_start = (int*)take(4 * (size_t)batch * levels); t.seg_count = (int*)take(4 * (size_t)batch * levels);
     t.img_start = (int*)take(4 * (size_t)batch); t.img_count = (int*)take(4 * (size_t)batch);
     t.keep = (long long*)take(8 * T); t.keep_count = (int*)take(4 * (size_t)batch * levels);
+    t.units = (float*)take(4 * (size_t)batch * levels);
     t.nms_bytes = rpn_nms_bytes(batch, levels, pre_k);
     t.nms = take(t.nms_bytes);
     if (base && used > bytes) return 0;
@@ -339,21 +368,23 @@ int launch_rpn_filter(const float* objectness, const float* deltas, const float*
     NmsParams np{};
     const size_t T = (size_t)batch * P.Ktot;
     const bool trick = nms_mode == B200_NMS_TV_TRICK;
-    const int nseg = trick ? batch : batch * num_levels;
-    const int max_seg = trick ? P.Ktot : kmax;
+    const int nseg = batch * num_levels;             // one segment per (image, level) for either strategy
+    const int max_seg = kmax;
     if (!nms_carve_scratch(&np, T, (size_t)nseg, (size_t)max_seg, w.nms, w.nms_bytes)) return B200_ERR_WORKSPACE;
     np.boxes = reinterpret_cast<const float*>(w.box); np.scores = w.score; np.labels = w.label;
     np.keep = w.keep; np.labels_out = nullptr; np.keep_count = w.keep_count;
     np.thr_f = (float)nms_thr; np.thr_d = nms_thr;
     np.from_slab = 0;
     np.max_seg = max_seg;
+    np.seg_offsets = w.seg_start; np.seg_counts = w.seg_count;
+    P.segs_per_img = num_levels;
     if (trick) {
-        k_rpn_concat<<<batch, 1024, 0, stream>>>(P);
-        np.seg_offsets = w.img_start; np.seg_counts = w.img_count; np.mode = B200_NMS_TV_TRICK;
-        P.segs_per_img = 1;
+        // same segments, torchvision's shifted-coordinate arithmetic (labels = level, unit of the whole image)
+        k_rpn_units<<<batch, 256, 0, stream>>>(P, w.units);
+        np.mode = B200_NMS_TV_TRICK;
+        np.given_unit = w.units;
     } else {
-        np.seg_offsets = w.seg_start; np.seg_counts = w.seg_count; np.mode = B200_NMS_TV;  // one level per segment
-        P.segs_per_img = num_levels;
+        np.mode = B200_NMS_TV;                        // one level per segment
     }
     const int rc = launch_nms(np, nseg, stream);
     if (rc != B200_OK) return rc;
