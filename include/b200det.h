@@ -171,7 +171,7 @@ int b200_debug_set_decode_events(void* ev_begin, void* ev_end);
 /* Profiling hook: three more cudaEvent_t (NULL to disable) recorded by the next NMS launches after the
  * plan, pairs and resolve kernels; with b200_debug_set_decode_events this gives a per-step timeline. */
 int b200_debug_set_timeline(void* after_plan, void* after_pairs, void* after_resolve);
-/* Profiling hook: device buffer int64[segments, 8] that the resolve kernel fills with clock64 stamps at its
+/* Profiling hook: device buffer int64[segments, 16] that the resolve kernel fills with clock64 stamps at its
  * phase boundaries (A stage, B fixed point, C vote, D order, E emit, end) + n and K; NULL to disable. */
 int b200_debug_set_resolve_prof(void* buf);
 

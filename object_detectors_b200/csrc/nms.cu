@@ -44,6 +44,7 @@ static constexpr int kResolveMaxWarps = kResolveMaxThreads / 32;
 #define kResolveThreads ((int)blockDim.x)
 #define kResolveWarps ((int)(blockDim.x >> 5))
 static constexpr int kKeptSmem = 2048;          // slow path: kept boxes sorted in shared memory
+static constexpr int kRankSortMax = 1024;       // kept boxes ordered by counting below this, bitonic network above
 static constexpr int kVoteFlag = 1 << 30;
 static constexpr int kVoteListCap = 128;
 
@@ -613,7 +614,7 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
 
     for (int w = tid; w < nw; w += kResolveThreads) { f.Kset[w] = 0ull; f.Rset[w] = 0ull; }
     __syncthreads();
-    if (P.prof && tid == 0) P.prof[seg * 8 + 0] = clock64();
+    if (P.prof && tid == 0) P.prof[seg * 16 + 0] = clock64();
     // ---- A. stage boxes and the non-zero structure of the mask rows --------------------------------
     for (int p = tid; p < n; p += kResolveThreads) {
         const Item it = load_raw<SLAB>(P, off, perm[p], unit);
@@ -641,7 +642,7 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
     __syncthreads();
     const RowReader R{cw, dom, (size_t)P.max_words};
 
-    if (P.prof && tid == 0) P.prof[seg * 8 + 1] = clock64();
+    if (P.prof && tid == 0) P.prof[seg * 16 + 1] = clock64();
     // ---- B. fixed point over bitsets ----------------------------------------------------------------
     int pending;
     do {
@@ -664,7 +665,7 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
         pending = __syncthreads_count(undecided > 0);
     } while (pending > 0);
 
-    if (P.prof && tid == 0) P.prof[seg * 8 + 2] = clock64();
+    if (P.prof && tid == 0) P.prof[seg * 16 + 2] = clock64();
     if (MODE == B200_NMS_MAJORITY) {
         // ---- C. first suppressor + vote (helper.py:368-369), voters gathered per kept box ---------
         for (int p = tid; p <= n; p += kResolveThreads) f.voff[p] = 0;
@@ -693,7 +694,9 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
             f.sup[j] = s;
         }
         __syncthreads();
+        if (P.prof && tid == 0) P.prof[seg * 16 + 8] = clock64();
         block_exclusive_scan(f.voff, n + 1, f.scan);
+        if (P.prof && tid == 0) P.prof[seg * 16 + 9] = clock64();
         for (int p = tid; p < n; p += kResolveThreads) f.klist[p] = f.voff[p];    // fill cursors
         __syncthreads();
         for (int j = tid; j < n; j += kResolveThreads) {
@@ -701,6 +704,7 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
             if (s >= 0 && (s & kVoteFlag)) f.vlab[atomicAdd(&f.klist[s & ~kVoteFlag], 1)] = f.lab[j];
         }
         __syncthreads();
+        if (P.prof && tid == 0) P.prof[seg * 16 + 10] = clock64();
         // majority relabel (helper.py:370-375): one warp per kept box that has at least two voters
         for (int p = warp; p < n; p += kResolveWarps) {
             if (!get_bit(f.Kset, p)) continue;
@@ -727,28 +731,56 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
         __syncthreads();
     }
 
-    if (P.prof && tid == 0) P.prof[seg * 8 + 3] = clock64();
+    if (P.prof && tid == 0) P.prof[seg * 16 + 3] = clock64();
     // ---- D. kept boxes in (score desc, canonical index asc) order ------------------------------------
-    int running = 0;
-    for (int p0 = 0; p0 < n; p0 += kResolveThreads) {
-        const int p = p0 + tid;
-        const bool kept = p < n && get_bit(f.Kset, p);
-        const int k = block_rank_rt(kept, f.scan, running, kResolveWarps);
-        if (kept) f.klist[k] = p;
+    // rank of a kept box among the kept ones = popcount of the kept bitset below it: one warp prefix-sums the
+    // (<= 64) word popcounts, then every kept position places itself -- no block-wide scans
+    if (warp == 0) {
+        const int w0 = 2 * lane, w1 = 2 * lane + 1;
+        const int c0 = w0 < nw ? __popcll(f.Kset[w0]) : 0, c1 = w1 < nw ? __popcll(f.Kset[w1]) : 0;
+        int incl = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(kFullMask, incl, o); if (lane >= o) incl += u; }
+        const int excl = incl - (c0 + c1);
+        if (w0 < nw) f.voff[w0] = excl;                  // voff (n+1 ints) is free again after the vote phase
+        if (w1 < nw) f.voff[w1] = excl + c0;
+        if (lane == 31) f.scan[0] = incl;
     }
-    const int K = running;
+    __syncthreads();
+    const int K = f.scan[0];
+    for (int p = tid; p < n; p += kResolveThreads) {
+        const unsigned long long word = f.Kset[p >> 6];
+        if ((word >> (p & 63)) & 1ull) f.klist[f.voff[p >> 6] + __popcll(word & ((1ull << (p & 63)) - 1ull))] = p;
+    }
+    if (P.prof && tid == 0) P.prof[seg * 16 + 11] = clock64();
     const int Pk = next_pow2(K);
     unsigned long long* skey = reinterpret_cast<unsigned long long*>(f.u);      // compact rows are dead now
     int* sval = reinterpret_cast<int*>(skey + Pk);
     __syncthreads();
-    for (int t = tid; t < Pk; t += kResolveThreads) {
-        skey[t] = t < K ? f.key[f.klist[t]] : ~0ull;
-        sval[t] = t < K ? f.klist[t] : -1;
+    if (K <= kRankSortMax) {
+        // rank by counting: keys are unique, so the position of a kept box in the sorted order is the number of
+        // kept boxes with a smaller key.  K broadcast reads per thread and ONE barrier instead of the
+        // log2(K)^2 / 2 barrier-separated passes of a bitonic network (36 for K = 200).
+        for (int t = tid; t < K; t += kResolveThreads) skey[t] = f.key[f.klist[t]];
+        __syncthreads();
+        if (P.prof && tid == 0) P.prof[seg * 16 + 12] = clock64();
+        for (int t = tid; t < K; t += kResolveThreads) {
+            const unsigned long long mine = skey[t];
+            int rank = 0;
+            for (int u = 0; u < K; ++u) rank += skey[u] < mine;
+            sval[rank] = f.klist[t];
+        }
+        __syncthreads();
+    } else {
+        for (int t = tid; t < Pk; t += kResolveThreads) {
+            skey[t] = t < K ? f.key[f.klist[t]] : ~0ull;
+            sval[t] = t < K ? f.klist[t] : -1;
+        }
+        __syncthreads();
+        bitonic_sort(skey, sval, Pk);
     }
-    __syncthreads();
-    bitonic_sort(skey, sval, Pk);
 
-    if (P.prof && tid == 0) P.prof[seg * 8 + 4] = clock64();
+    if (P.prof && tid == 0) P.prof[seg * 16 + 4] = clock64();
     // ---- E. emit -----------------------------------------------------------------------------------------
     const int Kout = SLAB ? min(K, P.max_det) : K;
     if (SLAB && P.det_keep) {
@@ -803,8 +835,8 @@ __device__ void resolve_fast(const NmsParams& P, int seg, long long off, int n, 
             if (P.labels_out) P.labels_out[off + t] = lab;
         }
     }
-    if (P.prof && tid == 0) P.prof[seg * 8 + 5] = clock64();
-    if (P.prof && tid == 0) { P.prof[seg * 8 + 6] = n; P.prof[seg * 8 + 7] = K; }
+    if (P.prof && tid == 0) P.prof[seg * 16 + 5] = clock64();
+    if (P.prof && tid == 0) { P.prof[seg * 16 + 6] = n; P.prof[seg * 16 + 7] = K; }
     if (tid == 0) {
         if (SLAB) {
             P.det_count[seg] = Kout;
