@@ -45,11 +45,31 @@ static constexpr int kMatchThreads = 256;
 static constexpr int kMatchItems = 4;    // anchors per thread
 static constexpr int kGtChunk = 128;     // ground-truth boxes staged per pass
 
+// IoU / GIoU of helper.bbox_iou with the per-box terms hoisted out of the pair loop: a1e = w1*h1 + 1e-16 of the
+// ground-truth box and a2 = w2*h2 of the anchor are rounded exactly as in pair_iou (common.cuh), so the result is
+// bit-identical; KIND is a compile-time constant (0 IoU, 1 GIoU), other kinds go through pair_iou.
+template <int KIND>
+__device__ __forceinline__ float match_iou(const Box& p, float a1e, const Box& q, float a2, int kind) {
+    if (KIND < 0) return pair_iou(p, q, kind);
+    const float iw = fmaxf(__fsub_rn(fminf(p.x2, q.x2), fmaxf(p.x1, q.x1)), 0.0f);
+    const float ih = fmaxf(__fsub_rn(fminf(p.y2, q.y2), fmaxf(p.y1, q.y1)), 0.0f);
+    const float inter = __fmul_rn(iw, ih);
+    const float uni = __fsub_rn(__fadd_rn(a1e, a2), inter);               // helper.py:255
+    const float iou = __fdiv_rn(inter, uni);
+    if (KIND == 0) return iou;
+    const float cw = __fsub_rn(fmaxf(p.x2, q.x2), fminf(p.x1, q.x1));
+    const float ch = __fsub_rn(fmaxf(p.y2, q.y2), fminf(p.y1, q.y1));
+    const float c_area = __fadd_rn(__fmul_rn(cw, ch), 1e-16f);            // :259-263
+    return __fsub_rn(iou, __fdiv_rn(__fsub_rn(c_area, uni), c_area));
+}
+
+template <int KIND>
 __global__ void __launch_bounds__(kMatchThreads)
 k_iou_match(const float* __restrict__ gt, const int* __restrict__ gt_count, int max_gt,
             const float* __restrict__ anchors, int N, int kind, float ignore_thr,
             unsigned long long* __restrict__ best_key, uint8_t* __restrict__ noobj) {
     __shared__ Box sgt[kGtChunk];
+    __shared__ float sarea[kGtChunk];
     __shared__ unsigned long long sbest[kGtChunk];
     const int b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -57,6 +77,7 @@ k_iou_match(const float* __restrict__ gt, const int* __restrict__ gt_count, int 
     const int n0 = blockIdx.x * (kMatchThreads * kMatchItems);
 
     Box anc[kMatchItems];
+    float a2[kMatchItems];
     bool valid[kMatchItems], free_[kMatchItems];
 #pragma unroll
     for (int k = 0; k < kMatchItems; ++k) {
@@ -64,29 +85,34 @@ k_iou_match(const float* __restrict__ gt, const int* __restrict__ gt_count, int 
         valid[k] = n < N;
         free_[k] = true;
         anc[k] = valid[k] ? load_box(anchors + 4 * (size_t)n, 1) : Box{0.f, 0.f, 0.f, 0.f};
+        a2[k] = __fmul_rn(__fsub_rn(anc[k].x2, anc[k].x1), __fsub_rn(anc[k].y2, anc[k].y1));
     }
 
     for (int mc = 0; mc < M; mc += kGtChunk) {
         const int mm = min(kGtChunk, M - mc);
         __syncthreads();
         for (int i = tid; i < mm; i += kMatchThreads) {
-            sgt[i] = load_box(gt + ((size_t)b * max_gt + mc + i) * 4, 1);
+            const Box g = load_box(gt + ((size_t)b * max_gt + mc + i) * 4, 1);
+            sgt[i] = g;
+            sarea[i] = __fadd_rn(__fmul_rn(__fsub_rn(g.x2, g.x1), __fsub_rn(g.y2, g.y1)), 1e-16f);
             sbest[i] = 0ull;
         }
         __syncthreads();
         for (int i = 0; i < mm; ++i) {
             const Box g = sgt[i];
+            const float a1e = sarea[i];
             unsigned bk = 0u;          // orderable(best iou) over this thread's anchors
-            unsigned bn = 0xffffffffu; // its anchor index
+            int bkk = -1;              // which of its anchors
 #pragma unroll
             for (int k = 0; k < kMatchItems; ++k) {
                 if (valid[k]) {
-                    const float v = pair_iou(g, anc[k], kind);
+                    const float v = match_iou<KIND>(g, a1e, anc[k], a2[k], kind);
                     free_[k] = free_[k] && (v < ignore_thr);
                     const unsigned ok = orderable(v);
-                    if (ok > bk) { bk = ok; bn = (unsigned)(n0 + k * kMatchThreads + tid); }  // ascending n: first max
+                    if (ok > bk) { bk = ok; bkk = k; }                    // ascending n: first max
                 }
             }
+            const unsigned bn = bkk >= 0 ? (unsigned)(n0 + bkk * kMatchThreads + tid) : 0xffffffffu;
             const unsigned wmax = __reduce_max_sync(kFullMask, bk);
             const unsigned wn = __reduce_min_sync(kFullMask, bk == wmax ? bn : 0xffffffffu);
             if (lane == 0 && wn != 0xffffffffu)
@@ -140,8 +166,12 @@ int launch_iou_match(const float* gt, const int* gt_count, int batch, int max_gt
     if (cudaMemsetAsync(best_key, 0, sizeof(unsigned long long) * (size_t)batch * max_gt, stream) != cudaSuccess)
         return B200_ERR_CUDA;
     dim3 grid(cdiv(n, kMatchThreads * kMatchItems), batch);
-    k_iou_match<<<grid, kMatchThreads, 0, stream>>>(gt, gt_count, max_gt, anchors, n, kind, ignore_thr,
-                                                    best_key, noobj);
+    if (kind == B200_IOU)
+        k_iou_match<0><<<grid, kMatchThreads, 0, stream>>>(gt, gt_count, max_gt, anchors, n, kind, ignore_thr, best_key, noobj);
+    else if (kind == B200_GIOU)
+        k_iou_match<1><<<grid, kMatchThreads, 0, stream>>>(gt, gt_count, max_gt, anchors, n, kind, ignore_thr, best_key, noobj);
+    else
+        k_iou_match<-1><<<grid, kMatchThreads, 0, stream>>>(gt, gt_count, max_gt, anchors, n, kind, ignore_thr, best_key, noobj);
     k_match_finish<<<batch, 128, 0, stream>>>(best_key, gt_count, max_gt, n, best_anchor, noobj);
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }
