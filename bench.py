@@ -362,10 +362,13 @@ def run_b200(args):
     # ---- for the record: the decode kernel alone (one stream, nothing overlapping it), and the other variant ----
     serial[0] = True
     iso_steps = min(args.steps, 200)
+    lib.b200_debug_set_ring(8, 1, 1)       # the stand-alone launch shape: 8 warps per SM, 64-cell tiles
     iso_ms, iso_k, _ = timed_loop(iso_steps, 5)
+    lib.b200_debug_set_ring(*[int(x) for x in args.ring.split(",")])
     serial[0] = False
     isolated = {"kernel_ms": iso_k, "achieved_GBs": algo_bytes / (iso_k * 1e-3) / 1e9,
-                "note": "same kernel, one stream, no other kernel resident; NMS kernels follow it serially"}
+                "note": "ONE launch alone on an idle GPU in its stand-alone shape (8 warps per SM, 64-cell tiles); "
+                        "one stream, the NMS kernels follow it serially"}
     other = "gated" if args.variant != "gated" else "ring"
     lib.b200_set_decode_variant(VARIANTS[other])
     ov_steps = min(args.steps, 400)

@@ -258,6 +258,11 @@ int b200_box_iou(const float* boxes1, int32_t m, const float* boxes2, int32_t n,
 /* element-wise (paired) version: boxes1[K,4] vs boxes2[K,4] -> out[K] (yolo_forw.py:125 shape) */
 int b200_box_iou_paired(const float* boxes1, const float* boxes2, int32_t k, int32_t kind,
                         int32_t xcycwh, float* out, void* stream);
+/* Backward of b200_box_iou_paired for kinds IoU..CIoU (the loss-side call yolo_forw.py:125,143-146 runs under
+ * autograd): grad_boxes{1,2}[k,4] = grad_out[k] * d out / d boxes{1,2}, matching torch autograd on the reference's
+ * expression (ties of min/max split evenly, clamp passes at 0, CIoU alpha constant).  Either output may be NULL. */
+int b200_box_iou_paired_backward(const float* boxes1, const float* boxes2, const float* grad_out, int32_t k,
+                                 int32_t kind, int32_t xcycwh, float* grad_boxes1, float* grad_boxes2, void* stream);
 
 /* Replaces the IoU + reductions of YOLOForw.get_target (yolo/nets/yolo_forw.py:183-201) for a
  * whole batch: gt [B, max_gt, 4] fp32 relative xc,yc,w,h (rows >= gt_count[b] ignored),

@@ -57,6 +57,7 @@ SIGNATURES = {
     "b200_nms": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _f64, _i32, _p, _p, _p, _p, _sz, _p]),
     "b200_box_iou": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _p, _p]),
     "b200_box_iou_paired": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
+    "b200_box_iou_paired_backward": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "b200_iou_match_workspace_bytes": (_sz, [_i32, _i32]),
     "b200_iou_match": (C.c_int, [_p, _p, _i32, _i32, _p, _i32, _i32, _f32, _p, _p, _p, _sz, _p]),
     "b200_rpn_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),

@@ -16,6 +16,7 @@ void ring_set_tile_cells(int tc);
 int launch_decode_dense(const DecodeParams& p, bool softmax, float* out, cudaStream_t stream);
 int launch_box_iou(const float*, int, const float*, int, int, int, float*, cudaStream_t);
 int launch_box_iou_pair(const float*, const float*, int, int, int, float*, cudaStream_t);
+int launch_box_iou_pair_bwd(const float*, const float*, const float*, int, int, int, float*, float*, cudaStream_t);
 int launch_iou_match(const float*, const int*, int, int, const float*, int, int, float, long long*,
                      uint8_t*, unsigned long long*, cudaStream_t);
 int launch_abs_coord(const float* in, long long n, float* out, cudaStream_t st);
@@ -457,6 +458,17 @@ int b200_box_iou_paired(const float* boxes1, const float* boxes2, int32_t k, int
     if (k == 0) return B200_OK;
     if (!boxes1 || !boxes2 || !out || !aligned16(boxes1) || !aligned16(boxes2)) return B200_ERR_INVALID;
     return launch_box_iou_pair(boxes1, boxes2, k, kind, xcycwh, out, static_cast<cudaStream_t>(stream));
+}
+
+int b200_box_iou_paired_backward(const float* boxes1, const float* boxes2, const float* grad_out, int32_t k,
+                                 int32_t kind, int32_t xcycwh, float* grad_boxes1, float* grad_boxes2, void* stream) {
+    if (k < 0 || kind < B200_IOU || kind > B200_CIOU) return B200_ERR_INVALID;
+    if (k == 0) return B200_OK;
+    if (!boxes1 || !boxes2 || !grad_out || (!grad_boxes1 && !grad_boxes2) || !aligned16(boxes1) || !aligned16(boxes2) ||
+        (grad_boxes1 && !aligned16(grad_boxes1)) || (grad_boxes2 && !aligned16(grad_boxes2)))
+        return B200_ERR_INVALID;
+    return launch_box_iou_pair_bwd(boxes1, boxes2, grad_out, k, kind, xcycwh, grad_boxes1, grad_boxes2,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 size_t b200_iou_match_workspace_bytes(int32_t batch, int32_t max_gt) {

@@ -435,11 +435,13 @@ k_decode_filter_ring(const __grid_constant__ RingParams q) {
     }
 }
 
-// Launch configuration knobs (b200_debug_set_ring): warps per CTA, stages per warp, CTAs per SM.
+// Launch configuration knobs (b200_debug_set_ring): warps per CTA, stages per warp, CTAs per SM, tile cells.
+// Default = the best stand-alone launch (8 warps x 64-cell tiles: 93 us for the C2 batch); a caller that keeps
+// several launches in flight (bench.py: three) uses 4 warps x 32-cell tiles per launch instead.
 static int g_ring_warps = 8;
 static int g_ring_slots = 1;
 static int g_ring_ctas_per_sm = 1;
-static int g_ring_tile_cells = 32;
+static int g_ring_tile_cells = 64;
 static const int kStageBudget = 23 * 1024;         // for 64-cell tiles; halves with the tile
 void ring_set_tile_cells(int tc) {
     if (tc == 32 || tc == 64) g_ring_tile_cells = tc;

@@ -41,6 +41,106 @@ k_box_iou_pair(const float* __restrict__ b1, const float* __restrict__ b2, int K
     out[i] = pair_iou(load_box(b1 + 4 * (size_t)i, xcycwh), load_box(b2 + 4 * (size_t)i, xcycwh), kind);
 }
 
+// ------------------------------------------------------------------------------------------
+// backward of the paired IoU family (loss side, yolo_forw.py:125,143-146)
+// ------------------------------------------------------------------------------------------
+// d out / d (both boxes) for out = helper.bbox_iou(b1, b2, kind) on K pairs, derived from the reference's own
+// expression graph (helper.py:244-277) so that it matches what torch autograd produces for it: min/max split
+// the gradient evenly on ties, clamp(min=0) passes it where the argument is >= 0, CIoU's alpha is a constant
+// (computed under no_grad, :273-274).  One thread per pair; plain fp32 (gradients are not threshold inputs).
+struct Corner8 { float ax1, ay1, ax2, ay2, bx1, by1, bx2, by2; };
+
+__device__ __forceinline__ void d_min(float a, float b, float g, float& ga, float& gb) {   // d min(a,b)
+    if (a < b) ga += g; else if (b < a) gb += g; else { ga += 0.5f * g; gb += 0.5f * g; }
+}
+__device__ __forceinline__ void d_max(float a, float b, float g, float& ga, float& gb) {   // d max(a,b)
+    if (a > b) ga += g; else if (b > a) gb += g; else { ga += 0.5f * g; gb += 0.5f * g; }
+}
+
+__global__ void __launch_bounds__(256)
+k_box_iou_pair_bwd(const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ gout,
+                   int K, int kind, int xcycwh, float* __restrict__ g1, float* __restrict__ g2) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= K) return;
+    const Box p = load_box(b1 + 4 * (size_t)i, xcycwh), q = load_box(b2 + 4 * (size_t)i, xcycwh);
+    const float go = gout[i];
+    // forward quantities
+    const float mnx2 = fminf(p.x2, q.x2), mxx1 = fmaxf(p.x1, q.x1), mny2 = fminf(p.y2, q.y2), mxy1 = fmaxf(p.y1, q.y1);
+    const float dw = mnx2 - mxx1, dh = mny2 - mxy1;
+    const float iw = fmaxf(dw, 0.f), ih = fmaxf(dh, 0.f);
+    const float inter = iw * ih;
+    const float w1 = p.x2 - p.x1, h1 = p.y2 - p.y1, w2 = q.x2 - q.x1, h2 = q.y2 - q.y1;
+    const float uni = (w1 * h1 + 1e-16f) + w2 * h2 - inter;
+    const float iou = inter / uni;
+    // adjoints of the scalar intermediates: out = iou [- penalty]
+    float g_inter = go / uni, g_uni = -go * inter / (uni * uni);
+    float g_cw = 0.f, g_ch = 0.f;
+    float gw1 = 0.f, gh1 = 0.f, gw2 = 0.f, gh2 = 0.f;
+    Corner8 g{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float mxx2 = fmaxf(p.x2, q.x2), mnx1 = fminf(p.x1, q.x1), mxy2 = fmaxf(p.y2, q.y2), mny1 = fminf(p.y1, q.y1);
+    const float cw = mxx2 - mnx1, ch = mxy2 - mny1;
+    if (kind == B200_GIOU) {
+        // out = iou - (c - uni) / c = iou - 1 + uni / c
+        const float c = cw * ch + 1e-16f;
+        g_uni += go / c;
+        const float g_c = -go * uni / (c * c);
+        g_cw += g_c * ch; g_ch += g_c * cw;
+    } else if (kind == B200_DIOU || kind == B200_CIOU) {
+        const float c2 = cw * cw + ch * ch + 1e-16f;
+        const float sx = (q.x1 + q.x2) - (p.x1 + p.x2), sy = (q.y1 + q.y2) - (p.y1 + p.y2);
+        const float rho2 = sx * sx * 0.25f + sy * sy * 0.25f;
+        // out -= rho2 / c2
+        const float g_rho = -go / c2, g_c2 = go * rho2 / (c2 * c2);
+        g_cw += g_c2 * 2.f * cw; g_ch += g_c2 * 2.f * ch;
+        const float gsx = g_rho * 0.5f * sx, gsy = g_rho * 0.5f * sy;
+        g.bx1 += gsx; g.bx2 += gsx; g.ax1 -= gsx; g.ax2 -= gsx;
+        g.by1 += gsy; g.by2 += gsy; g.ay1 -= gsy; g.ay2 -= gsy;
+        if (kind == B200_CIOU) {
+            // out -= v * alpha, v = 4/pi^2 (atan(w2/h2) - atan(w1/h1))^2, alpha = v / (1 - iou + v) held constant
+            const float kv = 0.40528473456935116f;
+            const float da = atanf(w2 / h2) - atanf(w1 / h1);
+            const float v = kv * da * da;
+            const float alpha = v / (1.f - iou + v);
+            const float g_da = -go * alpha * kv * 2.f * da;
+            // d atan(w/h) = (h dw - w dh) / (w^2 + h^2)
+            const float n2 = w2 * w2 + h2 * h2, n1 = w1 * w1 + h1 * h1;
+            gw2 += g_da * h2 / n2; gh2 -= g_da * w2 / n2;
+            gw1 -= g_da * h1 / n1; gh1 += g_da * w1 / n1;
+        }
+    }
+    // enclosing box extents
+    d_max(p.x2, q.x2, g_cw, g.ax2, g.bx2);  d_min(p.x1, q.x1, -g_cw, g.ax1, g.bx1);
+    d_max(p.y2, q.y2, g_ch, g.ay2, g.by2);  d_min(p.y1, q.y1, -g_ch, g.ay1, g.by1);
+    // union = w1*h1 + 1e-16 + w2*h2 - inter
+    gw1 += g_uni * h1; gh1 += g_uni * w1; gw2 += g_uni * h2; gh2 += g_uni * w2;
+    g_inter -= g_uni;
+    // inter = clamp(dw, 0) * clamp(dh, 0)
+    const float g_dw = dw >= 0.f ? g_inter * ih : 0.f, g_dh = dh >= 0.f ? g_inter * iw : 0.f;
+    d_min(p.x2, q.x2, g_dw, g.ax2, g.bx2);  d_max(p.x1, q.x1, -g_dw, g.ax1, g.bx1);
+    d_min(p.y2, q.y2, g_dh, g.ay2, g.by2);  d_max(p.y1, q.y1, -g_dh, g.ay1, g.by1);
+    // widths / heights
+    g.ax2 += gw1; g.ax1 -= gw1; g.ay2 += gh1; g.ay1 -= gh1;
+    g.bx2 += gw2; g.bx1 -= gw2; g.by2 += gh2; g.by1 -= gh2;
+    // back to the input format: x1 = xc - w/2, x2 = xc + w/2 (helper.py:203-217)
+    float4 o1, o2;
+    if (xcycwh) {
+        o1 = make_float4(g.ax1 + g.ax2, g.ay1 + g.ay2, 0.5f * (g.ax2 - g.ax1), 0.5f * (g.ay2 - g.ay1));
+        o2 = make_float4(g.bx1 + g.bx2, g.by1 + g.by2, 0.5f * (g.bx2 - g.bx1), 0.5f * (g.by2 - g.by1));
+    } else {
+        o1 = make_float4(g.ax1, g.ay1, g.ax2, g.ay2);
+        o2 = make_float4(g.bx1, g.by1, g.bx2, g.by2);
+    }
+    if (g1) reinterpret_cast<float4*>(g1)[i] = o1;
+    if (g2) reinterpret_cast<float4*>(g2)[i] = o2;
+}
+
+int launch_box_iou_pair_bwd(const float* b1, const float* b2, const float* gout, int K, int kind, int xcycwh,
+                            float* g1, float* g2, cudaStream_t st) {
+    if (K <= 0) return B200_OK;
+    k_box_iou_pair_bwd<<<cdiv(K, 256), 256, 0, st>>>(b1, b2, gout, K, kind, xcycwh, g1, g2);
+    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
+
 static constexpr int kMatchThreads = 256;
 static constexpr int kMatchItems = 4;    // anchors per thread
 static constexpr int kGtChunk = 128;     // ground-truth boxes staged per pass

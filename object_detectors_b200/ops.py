@@ -304,6 +304,40 @@ def box_iou_paired(b1: Tensor, b2: Tensor, kind: int = IOU, xcycwh: bool = False
     return out
 
 
+class _PairedIoU(torch.autograd.Function):
+    """Differentiable paired IoU family: forward = b200_box_iou_paired (bit-identical to the forward-only call),
+    backward = b200_box_iou_paired_backward."""
+
+    @staticmethod
+    def forward(ctx, b1, b2, kind, xcycwh):
+        b1c, b2c = b1.detach().float().contiguous(), b2.detach().float().contiguous()
+        ctx.save_for_backward(b1c, b2c)
+        ctx.kind, ctx.xcycwh = int(kind), bool(xcycwh)
+        return box_iou_paired(b1c, b2c, kind, xcycwh)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        b1, b2 = ctx.saved_tensors
+        lib = _lib.load()
+        go = grad_out.float().contiguous()
+        k = b1.shape[0]
+        g1 = torch.empty_like(b1) if ctx.needs_input_grad[0] else None
+        g2 = torch.empty_like(b2) if ctx.needs_input_grad[1] else None
+        if k:
+            _lib.check(lib.b200_box_iou_paired_backward(_ptr(b1), _ptr(b2), _ptr(go), k, ctx.kind, int(ctx.xcycwh),
+                                                        _ptr(g1), _ptr(g2), _stream()), "b200_box_iou_paired_backward")
+        return g1, g2, None, None
+
+
+def box_iou_paired_autograd(b1: Tensor, b2: Tensor, kind: int = IOU, xcycwh: bool = False) -> Tensor:
+    """``[K,4] x [K,4] -> [K]`` with gradients to either input (kinds IoU / GIoU / DIoU / CIoU)."""
+    b1 = _need_cuda(b1, "boxes1")
+    b2 = _need_cuda(b2, "boxes2")
+    if b1.shape != b2.shape or b1.dim() != 2 or b1.shape[1] != 4:
+        raise RuntimeError("paired IoU needs two [K,4] tensors")
+    return _PairedIoU.apply(b1, b2, int(kind), bool(xcycwh))
+
+
 def iou_match(gt: Tensor, gt_count: Tensor, anchors: Tensor, kind: int = GIOU, ignore_thr: float = 0.5):
     """gt [B, Mmax, 4] rel xc,yc,w,h; gt_count [B] i32; anchors [N,4] (cxypwh).
     -> best_anchor int64 [B, Mmax], noobj bool [B, N]."""

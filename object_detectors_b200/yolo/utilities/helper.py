@@ -50,11 +50,14 @@ def get_abs_coord(box: torch.Tensor) -> torch.Tensor:
 def bbox_iou(bb1: torch.Tensor, bb2: torch.Tensor, iou_type, CUDA: bool = True, xcycwh: bool = True) -> torch.Tensor:
     """IoU (0) / GIoU (1) / DIoU (2) / CIoU (3) with the reference's broadcasting patterns:
     ``[M,1,4] x [1,N,4] -> [M,N]`` (target matching, yolo_forw.py:186) and ``[K,4] x [K,4] -> [K]``
-    (loss side, yolo_forw.py:125).  Inputs that require grad are evaluated with differentiable torch
-    ops in the reference's operation order (the CUDA kernels are forward-only)."""
+    (loss side, yolo_forw.py:125).  The paired form is differentiable in CUDA (forward + backward kernels,
+    SURVEY.md 8f3); broadcast forms that require grad (not used by the reference) are evaluated with
+    differentiable torch ops in the reference's operation order."""
     kind = iou_type if iou_type in (1, 2, 3) else 0
     bb1, bb2 = _to_cuda(bb1), _to_cuda(bb2)
     if bb1.requires_grad or bb2.requires_grad:
+        if bb1.dim() == 2 and bb1.shape == bb2.shape and bb1.shape[1] == 4:
+            return ops.box_iou_paired_autograd(bb1, bb2, kind, xcycwh)
         return _bbox_iou_autograd(bb1, bb2, kind, xcycwh)
     if bb1.dim() == 3 and bb2.dim() == 3 and bb1.shape[1] == 1 and bb2.shape[0] == 1:
         return ops.box_iou(bb1[:, 0].float(), bb2[0].float(), kind, xcycwh)

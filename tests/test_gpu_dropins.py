@@ -292,3 +292,35 @@ def test_roi_postprocess_detections_bound_like_the_reference(tag, loss_name, str
         if strategy == "torchvision":
             np.testing.assert_array_equal(labels[i].cpu().numpy(), gold[f"{tag}_labels_{i}"])
             assert np.all(np.abs(s - gold[f"{tag}_scores_{i}"]) <= 1e-5 * np.abs(gold[f"{tag}_scores_{i}"]) + 1e-12)
+
+
+# ------------------------------------------------------------------- differentiable paired IoU (f3)
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+@pytest.mark.parametrize("xcycwh", [True, False])
+def test_bbox_iou_paired_backward_matches_torch_autograd(kind, xcycwh):
+    """helper.bbox_iou on [K,4] x [K,4] under autograd (yolo_forw.py:125): forward bit-equal to the forward-only
+    kernel, gradients equal to torch autograd on the reference's expression (oracle.yolo_ref.bbox_iou) within
+    1e-4 relative of the largest gradient component of the pair (fp32, different summation order)."""
+    from object_detectors_b200.yolo.utilities import helper
+    g = np.random.Generator(np.random.PCG64(90 + kind))
+    k = 4096
+    c1 = g.uniform(0.2, 0.8, (k, 2)); s1 = np.exp(g.uniform(-3.5, -0.7, (k, 2)))
+    c2 = c1 + g.normal(0, 0.6, (k, 2)) * s1; s2 = s1 * np.exp(g.normal(0, 0.4, (k, 2)))
+    a = np.concatenate([c1, s1], 1).astype(np.float32)
+    b = np.concatenate([c2, s2], 1).astype(np.float32)
+    if not xcycwh:
+        a = np.concatenate([a[:, :2] - a[:, 2:] / 2, a[:, :2] + a[:, 2:] / 2], 1)
+        b = np.concatenate([b[:, :2] - b[:, 2:] / 2, b[:, :2] + b[:, 2:] / 2], 1)
+    a[:8] = b[:8]                                        # identical boxes: min/max ties
+    wgt = g.normal(0, 1, k).astype(np.float32)
+    ta, tb = torch.from_numpy(a).requires_grad_(True), torch.from_numpy(b).requires_grad_(True)
+    ref = yolo_ref.bbox_iou(ta, tb, kind, xcycwh=xcycwh)
+    (ref * torch.from_numpy(wgt)).sum().backward()
+    ga, gb = torch.from_numpy(a).cuda().requires_grad_(True), torch.from_numpy(b).cuda().requires_grad_(True)
+    out = helper.bbox_iou(ga, gb, kind, xcycwh=xcycwh)
+    (out * torch.from_numpy(wgt).cuda()).sum().backward()
+    np.testing.assert_array_equal(out.detach().cpu().numpy(), ref.detach().numpy())
+    for got, want in ((ga.grad, ta.grad), (gb.grad, tb.grad)):
+        got, want = got.cpu().numpy(), want.numpy()
+        scale = np.abs(want).max(axis=1, keepdims=True) + 1e-6
+        assert np.all(np.abs(got - want) <= 1e-4 * scale + 1e-6), float(np.abs((got - want) / scale).max())
