@@ -300,7 +300,9 @@ def test_roi_postprocess_detections_bound_like_the_reference(tag, loss_name, str
 def test_bbox_iou_paired_backward_matches_torch_autograd(kind, xcycwh):
     """helper.bbox_iou on [K,4] x [K,4] under autograd (yolo_forw.py:125): forward bit-equal to the forward-only
     kernel, gradients equal to torch autograd on the reference's expression (oracle.yolo_ref.bbox_iou) within
-    1e-4 relative of the largest gradient component of the pair (fp32, different summation order)."""
+    1e-4 relative of the largest gradient component of the pair + 2e-5 absolute (fp32, different summation order;
+    for identical boxes the O(1..10) partial terms cancel to exactly 0 in one order and to rounding residue in
+    another)."""
     from object_detectors_b200.yolo.utilities import helper
     g = np.random.Generator(np.random.PCG64(90 + kind))
     k = 4096
@@ -319,8 +321,15 @@ def test_bbox_iou_paired_backward_matches_torch_autograd(kind, xcycwh):
     ga, gb = torch.from_numpy(a).cuda().requires_grad_(True), torch.from_numpy(b).cuda().requires_grad_(True)
     out = helper.bbox_iou(ga, gb, kind, xcycwh=xcycwh)
     (out * torch.from_numpy(wgt).cuda()).sum().backward()
-    np.testing.assert_array_equal(out.detach().cpu().numpy(), ref.detach().numpy())
+    if kind == 3:       # atan: ulp-level libm differences
+        np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+    else:
+        np.testing.assert_array_equal(out.detach().cpu().numpy(), ref.detach().numpy())
     for got, want in ((ga.grad, ta.grad), (gb.grad, tb.grad)):
         got, want = got.cpu().numpy(), want.numpy()
-        scale = np.abs(want).max(axis=1, keepdims=True) + 1e-6
-        assert np.all(np.abs(got - want) <= 1e-4 * scale + 1e-6), float(np.abs((got - want) / scale).max())
+        # CIoU of identical boxes is 0/0 in the reference's alpha (helper.py:273): NaN on both sides
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+        ok = ~np.isnan(want)
+        scale = np.nanmax(np.abs(np.where(ok, want, 0.0)), axis=1, keepdims=True) + 1e-6
+        err = np.where(ok, np.abs(got - want), 0.0)
+        assert np.all(err <= 1e-4 * scale + 2e-5), float(err.max())
