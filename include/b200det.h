@@ -174,6 +174,9 @@ int b200_debug_set_timeline(void* after_plan, void* after_pairs, void* after_res
 /* Profiling hook: device buffer int64[segments, 16] that the resolve kernel fills with clock64 stamps at its
  * phase boundaries (A stage, B fixed point, C vote, D order, E emit, end) + n and K; NULL to disable. */
 int b200_debug_set_resolve_prof(void* buf);
+/* Tuning hook: launch shape of the NMS resolve CTAs (threads: multiple of 32 in 64..1024, dynamic shared memory
+ * in KB 16..200; out-of-range values keep the current setting).  Default 1024 threads, 112 KB. */
+int b200_debug_set_resolve(int threads, int smem_kb);
 
 /* Variants of the fused decode+filter kernel.  All produce identical candidates; they differ in how the
  * head tensors are fetched (process-wide setting, default B200_DECODE_RING):

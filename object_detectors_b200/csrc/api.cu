@@ -98,7 +98,7 @@ static __global__ void k_pack(const float* __restrict__ det, const int* __restri
 }
 }  // namespace b200
 
-namespace b200 { extern cudaEvent_t g_nms_timeline[3]; extern long long* g_resolve_prof; extern long long g_batched_nms_auto_limit; }
+namespace b200 { extern cudaEvent_t g_nms_timeline[3]; extern long long* g_resolve_prof; extern long long g_batched_nms_auto_limit; extern int g_resolve_threads, g_resolve_smem_kb; }
 using namespace b200;
 
 extern "C" {
@@ -168,6 +168,11 @@ int b200_debug_set_timeline(void* after_plan, void* after_pairs, void* after_res
 int b200_set_batched_nms_auto_limit(int64_t numel) {
     if (numel < 0) return B200_ERR_INVALID;
     b200::g_batched_nms_auto_limit = numel;
+    return B200_OK;
+}
+int b200_debug_set_resolve(int threads, int smem_kb) {
+    if (threads >= 64 && threads <= 1024 && (threads & 31) == 0) b200::g_resolve_threads = threads;
+    if (smem_kb >= 16 && smem_kb <= 200) b200::g_resolve_smem_kb = smem_kb;
     return B200_OK;
 }
 int b200_debug_set_resolve_prof(void* buf) { b200::g_resolve_prof = static_cast<long long*>(buf); return B200_OK; }

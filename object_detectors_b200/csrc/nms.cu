@@ -23,8 +23,6 @@
 //                applies the majority relabel (helper.py:368-375) and emits.
 //  k_nms_canon   (YOLO stage API only) sorts the unordered candidate slab by flat anchor index and
 //                writes the reference's ascending-anchor candidate list (test_one_epoch.py:27-28).
-#include <stdlib.h>
-
 #include "decode.cuh"
 #include "nms.cuh"
 
@@ -1107,7 +1105,11 @@ bool nms_carve_scratch(NmsParams* P, size_t total, size_t segments, size_t max_s
 cudaEvent_t g_nms_timeline[3] = {nullptr, nullptr, nullptr};
 long long* g_resolve_prof = nullptr;
 
-long long g_batched_nms_auto_limit = 100000;   // torchvision 0.26 on CUDA (4000 on CPU)
+long long g_batched_nms_auto_limit = 100000;
+// launch shape of the resolve CTAs (b200_debug_set_resolve): 1024 threads at <= 32 registers and 112 KB leave room
+// for a decode CTA on the same SM; 112 KB stage every segment of up to ~1200 boxes in shared memory
+int g_resolve_threads = 1024;
+int g_resolve_smem_kb = 112;   // torchvision 0.26 on CUDA (4000 on CPU)
 
 int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
     P.auto_limit = g_batched_nms_auto_limit;
@@ -1144,18 +1146,8 @@ int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
     P.prof = g_resolve_prof;
     // Resolve CTAs (one per segment) are latency bound; they are kept small enough (threads, shared memory) to
     // share an SM with the streaming decode kernel of the next pipeline stage instead of waiting for it.
-    static int resolve_threads = 0;
-    static size_t resolve_smem = 0;
-    if (resolve_threads == 0) {
-        const char* e = getenv("B200_RESOLVE_THREADS");
-        int t = e ? atoi(e) : 1024;
-        if (t < 64 || t > kResolveMaxThreads || (t & 31)) t = 1024;
-        const char* k = getenv("B200_RESOLVE_SMEM_KB");
-        int kb = k ? atoi(k) : 112;
-        if (kb < 16 || kb > 200) kb = 200;
-        resolve_smem = (size_t)kb * 1024;
-        resolve_threads = t;
-    }
+    const int resolve_threads = g_resolve_threads;
+    const size_t resolve_smem = (size_t)g_resolve_smem_kb * 1024;
     const size_t slow_bytes = slow_smem_bytes(P.max_words);
     const size_t smem = resolve_smem > slow_bytes ? resolve_smem : slow_bytes;
     if (smem > 227 * 1024) return B200_ERR_INVALID;   // max_seg beyond ~1.4M boxes

@@ -9,7 +9,6 @@
 //                 are decoded / clipped / filtered -- the reference decodes all 268 569 anchors
 //                 first (rpn.py:355).  Survivors are written in order at a fixed stride.
 //  k_rpn_units  : (coordinate-trick strategy) the image's shift unit for its per-level segments (see below).
-//  k_rpn_concat : packs the levels of an image contiguously (single-segment layout, kept for reference runs).
 //  NMS          : the shared per-segment kernel of nms.cu (segments = image x level for the
 //                 vanilla strategy, = image for the coordinate trick).
 //  k_rpn_finish : merges an image's kept lists by score and emits the first post_nms_top_n.
@@ -38,8 +37,6 @@ struct RpnParams {
     int* aidx;
     int* seg_start;   // [B*L]
     int* seg_count;   // [B*L]
-    int* img_start;   // [B]   (coordinate trick)
-    int* img_count;   // [B]
     long long* keep;  // [B*Ktot] NMS output (relative to segment start)
     int* keep_count;  // [B*L] or [B]
     int segs_per_img;
@@ -194,30 +191,6 @@ k_rpn_select(const __grid_constant__ RpnParams P) {
     }
 }
 
-// coordinate-trick strategy: NMS runs over all levels of an image at once -> pack them
-__global__ void __launch_bounds__(1024, 1)
-k_rpn_concat(const __grid_constant__ RpnParams P) {
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const size_t base = (size_t)b * P.Ktot;
-    int cum = 0;
-    for (int l = 0; l < P.L; ++l) {
-        const int cnt = P.seg_count[b * P.L + l];
-        const int src0 = P.level_koff[l];
-        if (src0 != cum) {
-            for (int r0 = 0; r0 < cnt; r0 += 1024) {   // dst index <= src index: move in rounds
-                const int r = r0 + tid;
-                float4 bx; float sc = 0.f; int lb = 0, ai = 0;
-                if (r < cnt) { bx = P.box[base + src0 + r]; sc = P.score[base + src0 + r]; lb = P.label[base + src0 + r]; ai = P.aidx[base + src0 + r]; }
-                __syncthreads();
-                if (r < cnt) { P.box[base + cum + r] = bx; P.score[base + cum + r] = sc; P.label[base + cum + r] = lb; P.aidx[base + cum + r] = ai; }
-                __syncthreads();
-            }
-        }
-        cum += cnt;
-    }
-    if (tid == 0) { P.img_start[b] = (int)base; P.img_count[b] = cum; }
-}
-
 // merge the kept lists of an image by score, emit the first post_k (rpn.py:272-278)
 __global__ void __launch_bounds__(1024, 1)
 k_rpn_finish(const __grid_constant__ RpnParams P) {
@@ -228,7 +201,7 @@ k_rpn_finish(const __grid_constant__ RpnParams P) {
     const size_t base = (size_t)b * P.Ktot;
     if (tid == 0) s_total = 0;
     __syncthreads();
-    const int* starts = P.segs_per_img == 1 ? P.img_start : P.seg_start;
+    const int* starts = P.seg_start;
     for (int s = 0; s < P.segs_per_img; ++s) {
         const int seg = b * P.segs_per_img + s;
         const int kc = P.keep_count[seg];
@@ -243,7 +216,7 @@ k_rpn_finish(const __grid_constant__ RpnParams P) {
         __syncthreads();
     }
     const int total = s_total;
-    if (P.segs_per_img > 1) {   // single segment: the NMS output is already in score order
+    {
         int Ppad = 1;
         while (Ppad < total) Ppad <<= 1;
         for (int i = total + tid; i < Ppad; i += 1024) key[i] = ~0ull;
@@ -291,16 +264,14 @@ k_rpn_units(const RpnParams P, float* __restrict__ units) {
 namespace {
 struct RpnWs {
     float4* box; float* score; int* label; int* aidx;
-    int* seg_start; int* seg_count; int* img_start; int* img_count;
+    int* seg_start; int* seg_count;
     long long* keep; int* keep_count; float* units;
     void* nms; size_t nms_bytes;
 };
-// NMS scratch must serve either strategy: (B*L segments of <= pre_k) or (B segments of <= L*pre_k)
+// NMS scratch: B*L segments of <= pre_k boxes for either batched_nms strategy
 size_t rpn_nms_bytes(int batch, int levels, int pre_k) {
     const size_t T = (size_t)batch * levels * pre_k;
-    const size_t a = nms_scratch_bytes(T, (size_t)batch * levels, (size_t)pre_k);
-    const size_t b = nms_scratch_bytes(T, (size_t)batch, (size_t)levels * pre_k);
-    return a > b ? a : b;
+    return nms_scratch_bytes(T, (size_t)batch * levels, (size_t)pre_k);
 }
 size_t rpn_carve(int batch, int levels, int pre_k, void* base, size_t bytes, RpnWs* w) {
     const size_t T = (size_t)batch * levels * pre_k;   // worst case rows (>= B*Ktot)
@@ -310,7 +281,6 @@ size_t rpn_carve(int batch, int levels, int pre_k, void* base, size_t bytes, Rpn
     RpnWs t;
     t.box = (float4*)take(16 * T); t.score = (float*)take(4 * T); t.label = (int*)take(4 * T); t.aidx = (int*)take(4 * T);
     t.seg_start = (int*)take(4 * (size_t)batch * levels); t.seg_count = (int*)take(4 * (size_t)batch * levels);
-    t.img_start = (int*)take(4 * (size_t)batch); t.img_count = (int*)take(4 * (size_t)batch);
     t.keep = (long long*)take(8 * T); t.keep_count = (int*)take(4 * (size_t)batch * levels);
     t.units = (float*)take(4 * (size_t)batch * levels);
     t.nms_bytes = rpn_nms_bytes(batch, levels, pre_k);
@@ -351,7 +321,7 @@ int launch_rpn_filter(const float* objectness, const float* deltas, const float*
     RpnWs w;
     if (!rpn_carve(batch, num_levels, pre_k, workspace, workspace_bytes, &w)) return B200_ERR_WORKSPACE;
     P.box = w.box; P.score = w.score; P.label = w.label; P.aidx = w.aidx;
-    P.seg_start = w.seg_start; P.seg_count = w.seg_count; P.img_start = w.img_start; P.img_count = w.img_count;
+    P.seg_start = w.seg_start; P.seg_count = w.seg_count;
     P.keep = w.keep; P.keep_count = w.keep_count;
     P.out_boxes = out_boxes; P.out_scores = out_scores; P.out_index = out_index; P.out_count = out_count;
 
