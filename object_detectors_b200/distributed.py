@@ -49,6 +49,13 @@ def unpack_detections(gathered: torch.Tensor, world: int, batch: int, max_det: i
     return [rows[i, 1:1 + 6 * k].reshape(k, 6) for i, k in enumerate(counts)]
 
 
+def unpack_bucket(gathered: torch.Tensor, world: int, steps: int, batch: int, max_det: int) -> List[List[List[torch.Tensor]]]:
+    """A gathered bucket ``[world, steps, message_len]`` -> ``lists[rank][step][image]`` of ``[k, 6]`` tensors."""
+    n = message_len(batch, max_det)
+    g = gathered.reshape(world, steps, n)
+    return [[unpack_detections(g[r, s], 1, batch, max_det) for s in range(steps)] for r in range(world)]
+
+
 class DetectionExchange:
     """The path's one exchange step for a fixed (batch, max_det): pack kernel + all-gather, enqueued on the
     caller's stream with plain ctypes calls (~5 us of host time; ``all_gather_into_tensor`` costs ~10x that in
@@ -67,12 +74,16 @@ class DetectionExchange:
 
     NCCL_FLOAT = 7
 
-    def __init__(self, batch: int, max_det: int, device, bucket: int = 1):
+    def __init__(self, batch: int, max_det: int, device, bucket: int = 1, pack_fn=None):
+        """``pack_fn(det, det_count, dst_message_view, stream)``: replaces the CUDA pack kernel; it exists so that
+        the bucket / flush / gather bookkeeping can be tested on the CPU with gloo (tests/test_dist_gloo.py)."""
         import ctypes as C
-        from . import _lib
-        self.lib = _lib.load()
         self.batch, self.max_det, self.bucket = batch, max_det, max(1, int(bucket))
         self.dev = torch.device(device)
+        self.pack_fn = pack_fn
+        if pack_fn is None:
+            from . import _lib
+            self.lib = _lib.load()
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
         self.n = message_len(batch, max_det)
@@ -81,7 +92,7 @@ class DetectionExchange:
         self.out = [torch.zeros((self.world * self.bucket * self.n,), dtype=torch.float32, device=self.dev) for _ in range(2)]
         self.fill, self.cur, self.gathers = 0, 0, 0
         self.nccl, self.comm = None, None
-        if self.world > 1:
+        if self.world > 1 and self.dev.type == "cuda":
             try:
                 self._init_nccl(C)
             except Exception as e:      # keep working through c10d
@@ -120,23 +131,28 @@ class DetectionExchange:
                                              self.comm, C.c_void_p(stream.cuda_stream))
                 if rc != 0:
                     raise RuntimeError(f"ncclAllGather failed ({rc})")
-            else:
+            elif self.dev.type == "cuda":
                 with torch.cuda.stream(stream):
                     dist.all_gather_into_tensor(out[:self.world * count], msg[:count])
+            else:
+                dist.all_gather_into_tensor(out[:self.world * count], msg[:count])
         self.gathers += 1
         self.fill, self.cur = 0, self.cur ^ 1
-        return out if self.world > 1 else msg
+        return out[:self.world * count] if self.world > 1 else msg[:count]
 
     def __call__(self, det: torch.Tensor, det_count: torch.Tensor, stream: torch.cuda.Stream):
         """Packs one step's detections into the current bucket on ``stream``; when the bucket is full the whole
         bucket is all-gathered on the same stream and the gathered buffer is returned
         (``[world, steps, message_len]``, rank-major), else ``None``."""
-        import ctypes as C
-        from . import _lib
-        dst = self.msg[self.cur].data_ptr() + 4 * self.fill * self.n
-        _lib.check(self.lib.b200_pack_detections(C.c_void_p(det.data_ptr()), C.c_void_p(det_count.data_ptr()), self.batch,
-                                                 self.max_det, C.c_void_p(dst), C.c_void_p(stream.cuda_stream)),
-                   "b200_pack_detections")
+        if self.pack_fn is not None:
+            self.pack_fn(det, det_count, self.msg[self.cur][self.fill * self.n:(self.fill + 1) * self.n], stream)
+        else:
+            import ctypes as C
+            from . import _lib
+            dst = self.msg[self.cur].data_ptr() + 4 * self.fill * self.n
+            _lib.check(self.lib.b200_pack_detections(C.c_void_p(det.data_ptr()), C.c_void_p(det_count.data_ptr()),
+                                                     self.batch, self.max_det, C.c_void_p(dst),
+                                                     C.c_void_p(stream.cuda_stream)), "b200_pack_detections")
         self.fill += 1
         if self.fill == self.bucket:
             return self._gather(stream, self.bucket)

@@ -71,3 +71,46 @@ def test_single_process_is_identity():
     lists = b200_dist.unpack_detections(out, 1, BATCH, MAX_DET)
     for got, w in zip(lists, _fake(0)):
         np.testing.assert_array_equal(got.numpy(), w)
+
+
+# ------------------------------------------------------------------ bucketed exchange (DetectionExchange)
+def _fake_step(rank, step):
+    g = np.random.Generator(np.random.PCG64(1000 + 17 * rank + step))
+    return [g.random((int(g.integers(0, MAX_DET + 1)), 6)).astype(np.float32) for _ in range(BATCH)]
+
+
+def _bucket_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def pack(det, det_count, dst, stream):        # host stand-in for the CUDA pack kernel, same layout
+            dst.copy_(_pack_host(det, MAX_DET))
+        ex = b200_dist.DetectionExchange(BATCH, MAX_DET, "cpu", bucket=2, pack_fn=pack)
+        outs = []
+        for step in range(3):                          # one full bucket (2 steps) + a partial one
+            r = ex(_fake_step(rank, step), None, None)
+            if r is not None:
+                outs.append((r.clone(), 2, step - 1))
+        r = ex.flush(None)
+        assert r is not None and ex.flush(None) is None
+        outs.append((r.clone(), 1, 2))
+        assert ex.gathers == 2
+        for gathered, steps, first in outs:
+            lists = b200_dist.unpack_bucket(gathered, world, steps, BATCH, MAX_DET)
+            for rr in range(world):
+                for s in range(steps):
+                    for got, want in zip(lists[rr][s], _fake_step(rr, first + s)):
+                        np.testing.assert_array_equal(got.numpy(), want)
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_exchange_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_bucket_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret.get(0) and ret.get(1)
