@@ -126,7 +126,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     args = ap.parse_args()
-    rows = [c3_lvis(max(args.reps // 4, 3))] + c4_match(args.reps) + c5_rpn(args.reps) + dense_decode(args.reps) + roi_heads(args.reps)
+    rows = [c3_lvis(max(args.reps // 4, 3)), c3_lvis(max(args.reps // 4, 3), batch=32)] + c4_match(args.reps) + c5_rpn(args.reps) + dense_decode(args.reps) + roi_heads(args.reps)
     for r in rows:
         print(json.dumps(r), flush=True)
 
