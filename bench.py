@@ -51,7 +51,7 @@ CAPACITY = 4096        # candidate slab rows per image (overflow is reported, ne
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_decode_filter launch on this workload, from the
 # `ncu --set full` captures summarised in profiles/r01_kernels_ring.txt / r01_kernels_gated.txt / r01_decode_stream.txt
-NCU_TRAFFIC_BYTES = {"ring": 494937600 + 4668160, "gated": 168146944 + 8370432, "stream": 495031552 + 14940160, "bulk": None}
+NCU_TRAFFIC_BYTES = {"ring": 494937856 + 4787200, "gated": 168146944 + 8370432, "stream": 495031552 + 14940160, "bulk": None}
 ROOFLINE_NOTE = {
     "ring": "default variant: persistent TMA ring (cp.async.bulk.tensor.2d + mbarrier), every byte of the head tensors "
             "is read exactly once whatever the input (traffic == algorithmic bytes).  All durations are CUDA events on "
@@ -62,8 +62,8 @@ ROOFLINE_NOTE = {
             "period; isolated = the same kernel alone on an idle GPU",
     "gated": "reads the objectness plane of every cell but class/box planes only for lanes that "
              "hold a cell with sigmoid(obj) > conf_thr (score <= conf), so DRAM traffic is input dependent and below "
-             "the algorithmic bytes; kernel_ms is measured while the NMS kernels of other steps overlap it "
-             "(3-stream software pipeline). `stream_variant` gives the input-independent streaming kernel.",
+             "the algorithmic bytes (which is why it is reported beside the headline, not as it); kernel_ms as for "
+             "the default variant",
     "stream": "every byte of the head tensors is read once (traffic == algorithmic bytes)",
     "bulk": "TMA bulk-copy staging, every byte read once",
 }

@@ -21,6 +21,33 @@ namespace b200 {
 static constexpr unsigned kFullMask = 0xffffffffu;
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device.  Function attributes live in the
+// device's context, so the "already raised" cache is per (call site, device): a process that drives several GPUs
+// (the reference spawns one process per GPU, but nothing forbids it) gets the attribute set on each of them.
+struct SmemOptIn {
+    size_t have[32] = {};
+    template <typename Kernel>
+    cudaError_t ensure(Kernel kernel, size_t bytes) {
+        if (bytes <= 48 * 1024) return cudaSuccess;
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const int slot = dev & 31;
+        if (bytes <= have[slot]) return cudaSuccess;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess) have[slot] = bytes;
+        return e;
+    }
+};
+// number of SMs of the current device (148 if the query fails)
+inline int current_sm_count() {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+        return v;
+    return 148;
+}
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------- streaming loads (read-once)

@@ -439,17 +439,12 @@ int launch_decode_filter_bulk(const DecodeParams& p, bool softmax, cudaStream_t 
     for (int s = p.num_scales; s <= B200_MAX_SCALES; ++s) q.cta_begin[s] = cta;
     if (!any_bulk) return 1;
     const bool idf = p.idf != nullptr;
-    static size_t attr[4] = {0, 0, 0, 0};
+    static SmemOptIn optin[4];
     const int which = (softmax ? 2 : 0) + (idf ? 1 : 0);
-    if (smem > 48 * 1024 && smem > attr[which]) {
-        cudaError_t e;
-        if (softmax) e = idf ? cudaFuncSetAttribute(k_decode_filter_bulk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                             : cudaFuncSetAttribute(k_decode_filter_bulk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        else         e = idf ? cudaFuncSetAttribute(k_decode_filter_bulk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                             : cudaFuncSetAttribute(k_decode_filter_bulk<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return B200_ERR_CUDA;
-        attr[which] = smem;
-    }
+    cudaError_t e;
+    if (softmax) e = idf ? optin[which].ensure(k_decode_filter_bulk<true, true>, smem) : optin[which].ensure(k_decode_filter_bulk<true, false>, smem);
+    else         e = idf ? optin[which].ensure(k_decode_filter_bulk<false, true>, smem) : optin[which].ensure(k_decode_filter_bulk<false, false>, smem);
+    if (e != cudaSuccess) return B200_ERR_CUDA;
     if (softmax) {
         if (idf) k_decode_filter_bulk<true, true><<<cta, kBulkCells, smem, stream>>>(q);
         else     k_decode_filter_bulk<true, false><<<cta, kBulkCells, smem, stream>>>(q);
@@ -745,12 +740,8 @@ static int launch_dense2(Dense2Params& q, cudaStream_t stream) {
     }
     q.cta_begin[B200_MAX_SCALES] = t;
     const size_t smem = (size_t)((5 + p.C) * kDenseLd + 6 * kDenseCells) * sizeof(float);
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        if (cudaFuncSetAttribute(k_decode_dense2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return B200_ERR_CUDA;
-        attr = smem;
-    }
+    static SmemOptIn optin;
+    if (optin.ensure(k_decode_dense2, smem) != cudaSuccess) return B200_ERR_CUDA;
     k_decode_dense2<<<t, 256, smem, stream>>>(q);
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }

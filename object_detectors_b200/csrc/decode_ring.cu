@@ -540,12 +540,7 @@ int launch_decode_filter_ring(const DecodeParams& p, bool softmax, int* tile_cou
     const size_t smem = (size_t)warps * q.slots_per_warp * q.stage_bytes + align_up((size_t)p.C * sizeof(float), 16) +
                         (size_t)warps * 9 * TC * sizeof(float) + 1024;
     if (smem > 220 * 1024) return 1;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0, v = 0;
-        sms = (cudaGetDevice(&dev) == cudaSuccess &&
-               cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : 148;
-    }
+    const int sms = current_sm_count();
     int ctas = sms * g_ring_ctas_per_sm;
     if (ctas > q.total_tiles) ctas = q.total_tiles;
     const bool idf = p.idf != nullptr;
@@ -555,13 +550,9 @@ int launch_decode_filter_ring(const DecodeParams& p, bool softmax, int* tile_cou
         k_decode_filter_ring<true, false, 32>,  k_decode_filter_ring<true, true, 32>,
         k_decode_filter_ring<false, false, 64>, k_decode_filter_ring<false, true, 64>,
         k_decode_filter_ring<true, false, 64>,  k_decode_filter_ring<true, true, 64>};
-    static size_t attr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static SmemOptIn optin[8];
     const int which = (TC == 64 ? 4 : 0) + (softmax ? 2 : 0) + (idf ? 1 : 0);
-    if (smem > 48 * 1024 && smem > attr[which]) {
-        if (cudaFuncSetAttribute(kerns[which], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return B200_ERR_CUDA;
-        attr[which] = smem;
-    }
+    if (optin[which].ensure(kerns[which], smem) != cudaSuccess) return B200_ERR_CUDA;
     kerns[which]<<<ctas, threads, smem, stream>>>(q);
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }

@@ -1129,15 +1129,7 @@ int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
         k_nms_canon<<<num_segments, kCanonThreads, 0, stream>>>(P);
         return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
     }
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-            sms = v;
-        else
-            sms = 148;
-    }
+    const int sms = current_sm_count();
     if (cudaMemsetAsync(P.work_count, 0, 2 * sizeof(int), stream) != cudaSuccess) return B200_ERR_CUDA;
     if (P.from_slab) k_nms_plan<true><<<num_segments, kPlanThreads, 0, stream>>>(P);
     else             k_nms_plan<false><<<num_segments, kPlanThreads, 0, stream>>>(P);
@@ -1155,14 +1147,9 @@ int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
     const size_t slow_bytes = slow_smem_bytes(P.max_words);
     const size_t smem = resolve_smem > slow_bytes ? resolve_smem : slow_bytes;
     if (smem > 227 * 1024) return B200_ERR_INVALID;   // max_seg beyond ~1.4M boxes
-    static size_t attr_bytes[2] = {0, 0};
-    if (smem > attr_bytes[P.from_slab ? 1 : 0]) {
-        const cudaError_t e = P.from_slab
-            ? cudaFuncSetAttribute(k_nms_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-            : cudaFuncSetAttribute(k_nms_resolve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return B200_ERR_CUDA;
-        attr_bytes[P.from_slab ? 1 : 0] = smem;
-    }
+    static SmemOptIn optin[2];
+    if ((P.from_slab ? optin[1].ensure(k_nms_resolve<true>, smem) : optin[0].ensure(k_nms_resolve<false>, smem)) != cudaSuccess)
+        return B200_ERR_CUDA;
     if (P.from_slab) k_nms_resolve<true><<<num_segments, resolve_threads, smem, stream>>>(P, (unsigned)smem);
     else             k_nms_resolve<false><<<num_segments, resolve_threads, smem, stream>>>(P, (unsigned)smem);
     if (g_nms_timeline[2]) cudaEventRecord(g_nms_timeline[2], stream);

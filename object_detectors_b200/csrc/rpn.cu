@@ -328,11 +328,8 @@ int launch_rpn_filter(const float* objectness, const float* deltas, const float*
     int pp = 1;
     while (pp < kmax) pp <<= 1;
     const size_t sel_smem = sizeof(unsigned long long) * (size_t)pp;
-    static bool attr1 = false, attr2 = false;
-    if (!attr1) {
-        if (cudaFuncSetAttribute(k_rpn_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8) != cudaSuccess) return B200_ERR_CUDA;
-        attr1 = true;
-    }
+    static SmemOptIn optin1, optin2;
+    if (optin1.ensure(k_rpn_select, 8192 * 8) != cudaSuccess) return B200_ERR_CUDA;
     k_rpn_select<<<dim3(num_levels, batch), kSelThreads, sel_smem, stream>>>(P);
 
     NmsParams np{};
@@ -360,10 +357,7 @@ int launch_rpn_filter(const float* objectness, const float* deltas, const float*
     if (rc != B200_OK) return rc;
     int fp = 1;
     while (fp < P.Ktot) fp <<= 1;
-    if (!attr2) {
-        if (cudaFuncSetAttribute(k_rpn_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8) != cudaSuccess) return B200_ERR_CUDA;
-        attr2 = true;
-    }
+    if (optin2.ensure(k_rpn_finish, 16384 * 8) != cudaSuccess) return B200_ERR_CUDA;
     k_rpn_finish<<<batch, 1024, sizeof(unsigned long long) * (size_t)fp, stream>>>(P);
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }
