@@ -333,3 +333,27 @@ def test_bbox_iou_paired_backward_matches_torch_autograd(kind, xcycwh):
         scale = np.nanmax(np.abs(np.where(ok, want, 0.0)), axis=1, keepdims=True) + 1e-6
         err = np.where(ok, np.abs(got - want), 0.0)
         assert np.all(err <= 1e-4 * scale + 2e-5), float(err.max())
+
+
+def test_roi_postprocess_edge_cases():
+    """Images without proposals, images where nothing passes the score threshold, and slab overflow."""
+    from object_detectors_b200 import ops
+    c = 7
+    logits, regs, props = syn.roi_inputs(61, [40, 0, 25], c, 480, 640)
+    logits[40:] = -20.0                      # third image: every foreground probability ~ 0
+    logits[40:, 0] = 20.0
+    lg, rg = torch.from_numpy(logits).cuda(), torch.from_numpy(regs).cuda()
+    pr = [torch.from_numpy(p).cuda() for p in props]
+    shapes = [(480, 640)] * 3
+    det, keep, dcnt, ccnt, status = ops.roi_postprocess(lg, rg, pr, shapes, None, ops.ROI_SOFTMAX, nms_mode=ops.NMS_TV_CLASS)
+    ref = tv_ref.roi_postprocess(torch.from_numpy(logits), torch.from_numpy(regs), [torch.from_numpy(p) for p in props],
+                                 shapes, torch.ones(c), "ce", strategy="vanilla")
+    assert int(status.item()) & 1 == 0
+    assert dcnt.tolist()[1:] == [0, 0] and ccnt.tolist()[1:] == [0, 0]
+    assert int(dcnt[0]) == ref[0][0].shape[0] and ref[1][0].shape[0] == 0 and ref[2][0].shape[0] == 0
+    np.testing.assert_array_equal(det[0, :int(dcnt[0]), 5].cpu().numpy(), ref[0][2].numpy().astype(np.float32))
+    np.testing.assert_array_equal(keep[0, :int(dcnt[0])].cpu().numpy(), ref[0][3].numpy().astype(np.int32))
+    # a slab that is too small must say so (status bit 0), never drop candidates silently
+    _, _, _, ccnt2, status2 = ops.roi_postprocess(lg, rg, pr, shapes, None, ops.ROI_SOFTMAX, nms_mode=ops.NMS_TV_CLASS,
+                                                  capacity=max(1, int(ccnt[0]) // 2))
+    assert int(status2.item()) & 1 == 1 and int(ccnt2[0]) == int(ccnt[0])
