@@ -323,6 +323,11 @@ int b200_abs_coord(const float* boxes, int64_t n, float* out, void* stream);
  * boxes [n,4] -> out [n, 4*k]; weights_host = (wx, wy, ww, wh); xform_clip = log(1000/16). */
 int b200_boxcoder_decode(const float* rel_codes, const float* boxes, int64_t n, int32_t boxes_per_row,
                          const float* weights_host, float xform_clip, float* out, void* stream);
+/* Replaces encode_boxes / BoxCoder.encode_single (torchvision_models/tvision/_utils.py:80-125,160-166):
+ * out[n,4] = (wx*(gx-ex)/ew, wy*(gy-ey)/eh, ww*log(gw/ew), wh*log(gh/eh)) for matched pairs
+ * reference_boxes[n,4], proposals[n,4] (xyxy).  weights_host: 4 host floats (x, y, w, h). */
+int b200_boxcoder_encode(const float* reference_boxes, const float* proposals, int64_t n, const float* weights_host,
+                         float* out, void* stream);
 
 /* Matcher.__call__ (tvision/_utils.py:271-344) on a dense [M,N] quality matrix: matches [N] int64 =
  * argmax over M (first maximum), -1 below low_thr, -2 between the thresholds; with

@@ -22,6 +22,8 @@ int launch_iou_match(const float*, const int*, int, int, const float*, int, int,
 int launch_abs_coord(const float* in, long long n, float* out, cudaStream_t st);
 int launch_boxcoder(const float* rel, const float* boxes, long long n, int k, const float* weights, float clip,
                     float* out, cudaStream_t st);
+int launch_boxcoder_encode(const float* ref, const float* prop, long long n, const float* weights, float* out,
+                           cudaStream_t st);
 int launch_matcher(const float* q, int M, int N, float high, float low, int allow_low_quality, long long* matches,
                    long long* all_matches_ws, cudaStream_t st);
 int launch_rpn_filter(const float* objectness, const float* deltas, const float* anchors, const float* proposals, int batch,
@@ -560,6 +562,15 @@ int b200_boxcoder_decode(const float* rel_codes, const float* boxes, int64_t n, 
         return B200_ERR_INVALID;
     return launch_boxcoder(rel_codes, boxes, n, boxes_per_row, weights_host, xform_clip, out,
                            static_cast<cudaStream_t>(stream));
+}
+
+int b200_boxcoder_encode(const float* reference_boxes, const float* proposals, int64_t n, const float* weights_host,
+                         float* out, void* stream) {
+    if (n < 0 || !weights_host) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;
+    if (!reference_boxes || !proposals || !out || !aligned16(reference_boxes) || !aligned16(proposals) || !aligned16(out))
+        return B200_ERR_INVALID;
+    return launch_boxcoder_encode(reference_boxes, proposals, n, weights_host, out, static_cast<cudaStream_t>(stream));
 }
 
 int b200_matcher(const float* quality, int32_t m, int32_t n, float high_thr, float low_thr,

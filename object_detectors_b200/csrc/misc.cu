@@ -1,6 +1,7 @@
 // misc.cu -- small element-wise / reduction kernels that complete the drop-in surface (sm_100a):
 //   k_abs_coord      helper.get_abs_coord                      (yolo/utilities/helper.py:203-217)
 //   k_boxcoder       BoxCoder.decode_single                    (tvision/_utils.py:186-223)
+//   k_boxcoder_encode encode_boxes / BoxCoder.encode_single    (tvision/_utils.py:80-125, 160-166)
 //   k_matcher_*      Matcher.__call__ incl. low-quality ties   (tvision/_utils.py:271-344)
 // All are memory-bound one-pass kernels; arithmetic follows the reference operation by operation.
 #include "common.cuh"
@@ -33,6 +34,32 @@ k_boxcoder(const float4* __restrict__ rel, const float4* __restrict__ boxes, lon
     const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
     out[e] = make_float4(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), __fsub_rn(pcy, __fmul_rn(0.5f, ph)),
                          __fadd_rn(pcx, __fmul_rn(0.5f, pw)), __fadd_rn(pcy, __fmul_rn(0.5f, ph)));
+}
+
+// encode_boxes (tvision/_utils.py:80-125): regression targets of proposals w.r.t. their matched reference boxes
+__global__ void __launch_bounds__(256)
+k_boxcoder_encode(const float4* __restrict__ ref, const float4* __restrict__ prop, long long n, float wx, float wy,
+                  float ww, float wh, float4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = prop[i], g = ref[i];
+    const float ew = __fsub_rn(p.z, p.x), eh = __fsub_rn(p.w, p.y);                          // :108-109
+    const float ex = __fadd_rn(p.x, __fmul_rn(0.5f, ew)), ey = __fadd_rn(p.y, __fmul_rn(0.5f, eh));
+    const float gw = __fsub_rn(g.z, g.x), gh = __fsub_rn(g.w, g.y);                          // :113-114
+    const float gx = __fadd_rn(g.x, __fmul_rn(0.5f, gw)), gy = __fadd_rn(g.y, __fmul_rn(0.5f, gh));
+    out[i] = make_float4(__fdiv_rn(__fmul_rn(wx, __fsub_rn(gx, ex)), ew),                   // :118-121
+                         __fdiv_rn(__fmul_rn(wy, __fsub_rn(gy, ey)), eh),
+                         __fmul_rn(ww, logf(__fdiv_rn(gw, ew))),
+                         __fmul_rn(wh, logf(__fdiv_rn(gh, eh))));
+}
+
+int launch_boxcoder_encode(const float* ref, const float* prop, long long n, const float* weights, float* out,
+                           cudaStream_t st) {
+    if (n <= 0) return B200_OK;
+    k_boxcoder_encode<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(ref), reinterpret_cast<const float4*>(prop), n, weights[0], weights[1], weights[2],
+        weights[3], reinterpret_cast<float4*>(out));
+    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }
 
 // column pass: matched_vals, matches = quality.max(dim=0) (first maximum), then the thresholds

@@ -443,6 +443,24 @@ def boxcoder_decode(rel_codes: Tensor, boxes: Tensor, weights=(1.0, 1.0, 1.0, 1.
     return out
 
 
+def boxcoder_encode(reference_boxes: Tensor, proposals: Tensor, weights=(1.0, 1.0, 1.0, 1.0)) -> Tensor:
+    """reference_boxes [n,4], proposals [n,4] -> regression targets [n,4] (BoxCoder.encode_single)."""
+    lib = _lib.load()
+    ref = _need_cuda(reference_boxes, "reference_boxes").to(torch.float32).contiguous()
+    prop = _need_cuda(proposals, "proposals").to(torch.float32).contiguous()
+    if ref.shape != prop.shape or ref.dim() != 2 or ref.shape[1] != 4:
+        raise RuntimeError("encode needs two [n,4] tensors")
+    if ref.data_ptr() % 16:
+        ref = ref.clone()
+    if prop.data_ptr() % 16:
+        prop = prop.clone()
+    out = torch.empty_like(ref)
+    w = (C.c_float * 4)(*[float(v) for v in weights])
+    _lib.check(lib.b200_boxcoder_encode(_ptr(ref), _ptr(prop), ref.shape[0], w, _ptr(out), _stream()),
+               "b200_boxcoder_encode")
+    return out
+
+
 def matcher(quality: Tensor, high: float, low: float, allow_low_quality: bool = False) -> Tensor:
     """[M,N] quality -> int64 [N] matches (Matcher.__call__)."""
     lib = _lib.load()

@@ -1,7 +1,7 @@
 """Drop-ins for ``torchvision_models/tvision/_utils.py`` (reference): ``BoxCoder.decode`` /
 ``decode_single`` (:168-223) and ``Matcher.__call__`` (:271-344) with the reference's constructor
-arguments and return layouts, backed by libb200det.so.  ``encode`` and the samplers are training
-glue outside the hot path and are not provided."""
+arguments and return layouts, plus ``BoxCoder.encode`` / ``encode_single`` (:80-125,144-166), backed by
+libb200det.so.  The samplers (``randperm``-based training glue) are not provided."""
 from __future__ import annotations
 
 import math
@@ -18,6 +18,14 @@ class BoxCoder:
     def __init__(self, weights: Tuple[float, float, float, float], bbox_xform_clip: float = math.log(1000.0 / 16)):
         self.weights = weights
         self.bbox_xform_clip = bbox_xform_clip
+
+    def encode(self, reference_boxes: List[Tensor], proposals: List[Tensor]):
+        boxes_per_image = [len(b) for b in reference_boxes]
+        targets = self.encode_single(torch.cat(reference_boxes, dim=0), torch.cat(proposals, dim=0))
+        return targets.split(boxes_per_image, 0)
+
+    def encode_single(self, reference_boxes: Tensor, proposals: Tensor) -> Tensor:
+        return ops.boxcoder_encode(reference_boxes, proposals, self.weights)
 
     def decode(self, rel_codes: Tensor, boxes: List[Tensor]) -> Tensor:
         assert isinstance(boxes, (list, tuple))

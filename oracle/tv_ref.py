@@ -115,6 +115,22 @@ def decode_single(rel_codes: Tensor, boxes: Tensor,
     return torch.stack((pcx - half * pw, pcy - half * ph, pcx + half * pw, pcy + half * ph), dim=1)
 
 
+def encode_boxes(reference_boxes: Tensor, proposals: Tensor,
+                 weights: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)) -> Tensor:
+    """encode_boxes (_utils.py:80-125): regression targets of ``proposals`` w.r.t. ``reference_boxes``."""
+    wts = torch.as_tensor(weights, dtype=reference_boxes.dtype)
+    ew = proposals[:, 2:3] - proposals[:, 0:1]
+    eh = proposals[:, 3:4] - proposals[:, 1:2]
+    ex = proposals[:, 0:1] + 0.5 * ew
+    ey = proposals[:, 1:2] + 0.5 * eh
+    gw = reference_boxes[:, 2:3] - reference_boxes[:, 0:1]
+    gh = reference_boxes[:, 3:4] - reference_boxes[:, 1:2]
+    gx = reference_boxes[:, 0:1] + 0.5 * gw
+    gy = reference_boxes[:, 1:2] + 0.5 * gh
+    return torch.cat((wts[0] * (gx - ex) / ew, wts[1] * (gy - ey) / eh,
+                      wts[2] * torch.log(gw / ew), wts[3] * torch.log(gh / eh)), dim=1)
+
+
 def decode_multi(rel_codes: Tensor, boxes: Tensor,
                  weights: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)) -> Tensor:
     """BoxCoder.decode_single with k boxes per row: rel_codes [n, 4k] -> [n, 4k] (_utils.py:186-223)."""

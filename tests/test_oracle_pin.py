@@ -1,5 +1,7 @@
 """Pin the restated torchvision box ops (oracle/tv_ref.py, oracle/boxops_ref.c) to the installed
 torchvision CPU kernels -- the third-party dependency the reference calls."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -57,3 +59,21 @@ def test_box_iou_matches_torchvision():
 def test_versions_recorded():
     # the oracle is pinned against THIS torchvision; a different wheel must re-run the pin
     assert torchvision.__version__.startswith("0.26"), torchvision.__version__
+
+
+def test_encode_boxes_matches_reference_utils():
+    """oracle.tv_ref.encode_boxes == the reference's vendored BoxCoder.encode_single (tvision/_utils.py:80-125,160-166);
+    skipped on the GPU box, where /root/reference does not exist (the installed torchvision copy is used there)."""
+    import sys
+    g = np.random.Generator(np.random.PCG64(8))
+    c = g.uniform(50, 500, (200, 2)); s = np.exp(g.uniform(2, 5, (200, 2)))
+    prop = torch.from_numpy(np.concatenate([c - s / 2, c + s / 2], 1).astype(np.float32))
+    c2 = c + g.normal(0, 5, (200, 2)); s2 = s * np.exp(g.normal(0, 0.2, (200, 2)))
+    ref = torch.from_numpy(np.concatenate([c2 - s2 / 2, c2 + s2 / 2], 1).astype(np.float32))
+    if os.path.isdir("/root/reference/torchvision_models"):
+        sys.path.insert(0, "/root/reference/torchvision_models")
+        from tvision import _utils as ref_utils
+    else:
+        from torchvision.models.detection import _utils as ref_utils
+    want = ref_utils.BoxCoder((10.0, 10.0, 5.0, 5.0)).encode_single(ref, prop)
+    np.testing.assert_array_equal(tv_ref.encode_boxes(ref, prop, (10.0, 10.0, 5.0, 5.0)).numpy(), want.numpy())
