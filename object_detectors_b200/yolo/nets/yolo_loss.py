@@ -36,36 +36,38 @@ class YOLOLoss(nn.Module):
                                       self.img_size)
 
     def get_target(self, targets, anchors, in_w, in_h, ignore_threshold=0.5):
-        """yolo_loss.py:107-161 with the same return tuple; ``anchors`` are the scaled anchors of the head."""
+        """Anchor-shape matching of yolo_loss.py:107-161, same return tuple (mask, noobj_mask, tx, ty, tw, th, tconf,
+        tcls); ``anchors`` are the head's scaled anchors.  The reference loops over images and ground-truth boxes; here
+        every ground-truth box of the batch goes through ONE [M, A] shape-IoU call and the dense target tensors are
+        filled by batched scatters (duplicate cells resolve like the reference's index assignments: last write)."""
         bs, na, dev = len(targets), len(anchors), self.device
-        z = lambda *shape: torch.zeros(*shape, device=dev)      # noqa: E731
-        mask, noobj_mask = z(bs, na, in_h, in_w), torch.ones(bs, na, in_h, in_w, device=dev)
-        tx, ty, tw, th, tconf = (z(bs, na, in_h, in_w) for _ in range(5))
-        tcls = z(bs, na, in_h, in_w, self.num_classes)
+        dense = lambda *tail: torch.zeros((bs, na, in_h, in_w) + tail, device=dev)      # noqa: E731
+        mask, noobj_mask = dense(), torch.ones((bs, na, in_h, in_w), device=dev)
+        tx, ty, tw, th, tconf, tcls = dense(), dense(), dense(), dense(), dense(), dense(self.num_classes)
+        counts = [int(t["bbox"].shape[0]) for t in targets]
+        if sum(counts) == 0:
+            return mask, noobj_mask, tx, ty, tw, th, tconf, tcls
+        gt = torch.cat([t["bbox"].reshape(-1, 4) for t in targets]).to(dev).float()
+        cls = torch.cat([t["category_id"].reshape(-1) for t in targets]).to(dev).long()
+        img = torch.repeat_interleave(torch.arange(bs, device=dev), torch.tensor(counts, device=dev))
+        scale = torch.tensor([in_w, in_h, in_w, in_h], dtype=torch.float32, device=dev)
+        g = gt * scale                                                     # centre and size in grid units (:121-127)
+        gx = g[:, 0].clamp(0, in_w - 1e-4)
+        gy = g[:, 1].clamp(0, in_h - 1e-4)
+        col, row = gx.long(), gy.long()
         anc = torch.tensor(anchors, dtype=torch.float32, device=dev)
-        anchor_shapes = torch.cat([torch.zeros((na, 2), device=dev), anc], 1)
-        for b, target in enumerate(targets):
-            bbox = target["bbox"].to(dev)
-            categories = target["category_id"].to(dev)
-            if bbox.shape[0] == 0:
-                continue
-            gx = torch.clamp(bbox[:, 0] * in_w, 0, in_w - 1e-4)
-            gy = torch.clamp(bbox[:, 1] * in_h, 0, in_h - 1e-4)
-            gw, gh = bbox[:, 2] * in_w, bbox[:, 3] * in_h
-            gi, gj = gx.long(), gy.long()
-            gt_box = torch.zeros(bbox.shape, dtype=torch.float32, device=dev)
-            gt_box[:, 2], gt_box[:, 3] = gw, gh
-            anch_ious = boxes.box_iou(gt_box, anchor_shapes)              # b200_box_iou (torchvision flavour)
-            over = anch_ious > ignore_threshold                           # [M, A]
-            m_idx, a_idx = torch.nonzero(over, as_tuple=True)
-            noobj_mask[b, a_idx, gj[m_idx], gi[m_idx]] = 0
-            best_n = torch.max(anch_ious, axis=1)[1]
-            mask[b, best_n, gj, gi] = 1
-            noobj_mask[b, best_n, gj, gi] = 0
-            tx[b, best_n, gj, gi] = gx - gi
-            ty[b, best_n, gj, gi] = gy - gj
-            tw[b, best_n, gj, gi] = torch.log(gw / anc[best_n][:, 0] + 1e-16)
-            th[b, best_n, gj, gi] = torch.log(gh / anc[best_n][:, 1] + 1e-16)
-            tconf[b, best_n, gj, gi] = 1
-            tcls[b, best_n, gj, gi, categories] = 1
+        as_shape = lambda wh: torch.cat([torch.zeros_like(wh), wh], 1)     # noqa: E731  (0, 0, w, h) boxes (:132-138)
+        shape_iou = boxes.box_iou(as_shape(g[:, 2:4]), as_shape(anc))      # b200_box_iou, torchvision flavour
+        m_ign, a_ign = torch.nonzero(shape_iou > ignore_threshold, as_tuple=True)
+        noobj_mask[img[m_ign], a_ign, row[m_ign], col[m_ign]] = 0          # :143-144
+        best = shape_iou.max(dim=1)[1]                                     # first maximum (:146)
+        at = (img, best, row, col)
+        mask[at] = 1
+        noobj_mask[at] = 0
+        tx[at] = gx - col
+        ty[at] = gy - row
+        tw[at] = torch.log(g[:, 2] / anc[best, 0] + 1e-16)
+        th[at] = torch.log(g[:, 3] / anc[best, 1] + 1e-16)
+        tconf[at] = 1
+        tcls[img, best, row, col, cls] = 1
         return mask, noobj_mask, tx, ty, tw, th, tconf, tcls
