@@ -76,3 +76,15 @@ def test_product_does_not_import_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), \
                     f"{f} imports the oracle: product code must never route through it"
+
+
+def test_header_is_plain_c():
+    """include/b200det.h is the drop-in boundary: it must compile as C99 on its own (no C++ or CUDA types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(ROOT, "include", "b200det.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
