@@ -15,7 +15,7 @@ from ._lib import (CIOU, DIOU, GIOU, IOU, IOU_TV, NMS_MAJORITY, NMS_TV, NMS_TV_C
 
 Tensor = torch.Tensor
 
-_scratch: Dict[Tuple[int, str], Tensor] = {}
+_scratch: Dict[Tuple[int, int, str], Tensor] = {}
 
 # Candidate rows kept per image unless the caller says otherwise.  The reference has no cap; a slab
 # overflow is never silent (device status word -> RuntimeError) and the drop-ins retry with the
@@ -40,8 +40,11 @@ def _need_cuda(t: Tensor, name: str, dtype=None) -> Tensor:
 
 
 def workspace(nbytes: int, device: torch.device, tag: str = "ws") -> Tensor:
-    """Grow-only byte buffer per (device, tag); torch's allocator returns >= 512 B alignment."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    """Grow-only byte buffer per (device, current stream, tag); torch's allocator returns >= 512 B alignment.
+    Keyed by stream because the kernels that use it are asynchronous: two streams must never share scratch, and a
+    buffer that is replaced by a larger one is then only ever reused in stream order."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream, tag)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
