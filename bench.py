@@ -150,10 +150,10 @@ def cpu_reference_pass(heads_cpu, idf):
     return sum(int(r["keep"].numel()) for r in recs)
 
 
-def time_cpu(sample_batch: int, reps: int, warm: int = 1):
+def time_cpu(sample_batch: int, reps: int, warm: int = 1, heads_np=None):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    heads = [torch.from_numpy(h) for h in make_heads(1000, sample_batch)]
+    heads = [torch.from_numpy(h) for h in (heads_np if heads_np is not None else make_heads(1000, sample_batch))]
     idf = load_idf()
     for _ in range(warm):
         cpu_reference_pass(heads, idf)
@@ -166,25 +166,30 @@ def time_cpu(sample_batch: int, reps: int, warm: int = 1):
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU code path (oracle port, all host threads) on the same workload.
+    Each step processes a bounded sample of the 64-image batch, sized so that the whole run (warm-up + steps) is
+    about a minute of CPU work at the ~80 images/s this path reaches on the GPU boxes' hosts."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 16
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    warm = max(args.warmup, 1)
+    sample = max(1, min(BATCH, 4800 // max(args.steps + warm, 1)))
     heads = [torch.from_numpy(h) for h in make_heads(1000, sample)]
     idf = load_idf()
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(warm):
         cpu_reference_pass(heads, idf)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_reference_pass(heads, idf)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
-    desc = f"{sample} images of the {BATCH}-image 608/COCO batch per step (clustered synthetic heads, seed 1000)"
+    desc = (f"{sample} images of the {BATCH}-image 608/COCO batch per step (clustered synthetic heads, seed 1000), "
+            f"{args.steps} steps")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps,
+        "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": "C2: YOLOv3-608 COCO-80 decode + conf filter + nms_majority, 22743 anchors/image",
                    "sample_batch": sample, "threads": cores, "engine": "oracle port of the reference (torch CPU ops)"},
@@ -410,7 +415,7 @@ def run_b200(args):
     if rank == 0:
         peak, peak_src = _peaks()
         achieved = algo_bytes / (k_busy * 1e-3) / 1e9
-        cpu_v, cores, cpu_ts = time_cpu(sample_batch=16, reps=3)
+        cpu_v, cores, cpu_ts = time_cpu(sample_batch=BATCH, reps=12, heads_np=heads_np)
         line = {
             "metric": METRIC, "value": world * BATCH * args.steps / (ms_total * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -436,8 +441,8 @@ def run_b200(args):
                          "step_rate_GBs": algo_bytes / (ms_total / args.steps * 1e-3) / 1e9,
                          "isolated": isolated, "note": ROOFLINE_NOTE[args.variant]},
             "cpu_baseline": {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": "16 images of the same 608/COCO workload, 3 timed passes, oracle port "
-                                       "(torch CPU ops, all host threads)"},
+                             "sample": f"the {BATCH}-image 608/COCO batch, 12 timed passes (median; ~10 s of CPU work), "
+                                       "oracle port (torch CPU ops, all host threads)"},
             "e2e": {"value": world * BATCH * e2e_steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": args.steps * (4 + (1 if world > 1 else 0)) +
