@@ -32,7 +32,7 @@
 
 namespace b200 {
 
-static constexpr int kMaxTileCells = 64;           // tiles are TC = 32 or 64 cells (template parameter)
+// tiles are TC = 32 or 64 cells (template parameter of the kernel)
 static constexpr int kBoxCells = 32;               // one TMA box: 32 cells (128 B) x R rows
 // 1-D mode: floats per staged row = TC cells + <=3 floats of alignment shift, padded to a 16 B multiple
 __host__ __device__ constexpr int row_stride_b(int tc) { return tc + 4; }
