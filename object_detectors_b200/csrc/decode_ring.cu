@@ -103,8 +103,10 @@ __device__ __forceinline__ TileMeta tile_geom(const RingParams& q, int tile, int
     g.tile = tile;
     g.s = q.order[k];
     const unsigned local = (unsigned)(tile - q.tile_begin[k]);
-    const unsigned magic = q.tpb_magic[k];            // ceil(2^32 / tiles_per_ba), 0 when tiles_per_ba == 1
-    g.ba = magic ? (int)__umulhi(local, magic) : (int)local;
+    // local / tiles_per_ba: multiply-high by ceil(2^32 / d) is exact while local * d < 2^32 (checked on the host,
+    // true for every realistic shape); 0 = (d == 1), 1 = fall back to the division
+    const unsigned magic = q.tpb_magic[k];
+    g.ba = magic > 1u ? (int)__umulhi(local, magic) : magic == 1u ? (int)(local / (unsigned)q.tiles_per_ba[g.s]) : (int)local;
     g.cell0 = ((int)local - g.ba * q.tiles_per_ba[g.s]) * tile_cells;
     return g;
 }
@@ -513,7 +515,8 @@ int launch_decode_filter_ring(const DecodeParams& p, bool softmax, int* tile_cou
             const int s = idx[k];
             q.order[k] = s;
             q.tiles_per_ba[s] = cdiv(p.sc[s].hw, TC);
-            q.tpb_magic[k] = q.tiles_per_ba[s] > 1 ? (unsigned)((0x100000000ull + q.tiles_per_ba[s] - 1) / q.tiles_per_ba[s]) : 0u;
+            const unsigned long long d = (unsigned long long)q.tiles_per_ba[s], n_max = (unsigned long long)p.B * p.A * d;
+            q.tpb_magic[k] = d <= 1 ? 0u : (n_max * d < 0x100000000ull ? (unsigned)((0x100000000ull + d - 1) / d) : 1u);
             t += p.B * p.A * q.tiles_per_ba[s];
         }
     }
