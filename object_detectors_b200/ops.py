@@ -497,6 +497,11 @@ def yolo_legacy_decode(head: Tensor, anchors_px, num_classes: int, img_size) -> 
 
 
 ROI_SOFTMAX, ROI_GOMBIT, ROI_SIGMOID = 0, 1, 2
+# Default candidate slab rows per image for the ROI post-process.  The worst case is rows x (classes - 1) (90 000
+# for COCO, 1.2 M for LVIS) but the NMS bitmask scratch grows with capacity^2 / 8 bytes per image, and after the
+# score threshold an image holds a few thousand candidates; overflow sets status bit 0 and `cand_count` holds the
+# true counts, so a caller can retry with exactly what is needed (tvision/roi_heads.py does).
+ROI_DEFAULT_CAPACITY = 16384
 
 
 def roi_postprocess(class_logits: Tensor, box_regression: Tensor, proposals: Sequence[Tensor], image_shapes,
@@ -520,7 +525,7 @@ def roi_postprocess(class_logits: Tensor, box_regression: Tensor, proposals: Seq
     hw = torch.tensor([[float(h), float(w)] for h, w in image_shapes], dtype=torch.float32, device=dev)
     if tfidf is not None:
         tfidf = torch.as_tensor(tfidf, dtype=torch.float32, device=dev).expand(c).contiguous()
-    cap = int(capacity or max(1, max(rows) * (c - 1)))
+    cap = int(capacity or max(1, min(max(rows) * (c - 1), ROI_DEFAULT_CAPACITY)))
     d = int(detections_per_img)
     det = torch.empty((b, d, 6), dtype=torch.float32, device=dev)
     keep = torch.empty((b, d), dtype=torch.int32, device=dev)

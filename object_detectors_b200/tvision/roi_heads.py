@@ -36,14 +36,20 @@ def postprocess_detections(self, class_logits: Tensor, box_regression: Tensor, p
     # "torchvision": batched_nms's own per-image switch between the coordinate trick and the per-class loop
     mode = {"torchvision": ops.NMS_TV_AUTO, "vanilla": ops.NMS_TV_CLASS, "coordinate_trick": ops.NMS_TV_TRICK}[strategy]
     tfidf = getattr(self, "tfidf_post", None)
-    det, _, dcnt, _, status = ops.roi_postprocess(
-        class_logits, box_regression, proposals, image_shapes, tfidf=tfidf,
-        activation=_activation(getattr(self, "loss_function_name", "ce")), weights=self.box_coder.weights,
-        xform_clip=self.box_coder.bbox_xform_clip, score_thresh=self.score_thresh, nms_thresh=self.nms_thresh,
-        detections_per_img=self.detections_per_img, nms_mode=mode)
+    kwargs = dict(tfidf=tfidf, activation=_activation(getattr(self, "loss_function_name", "ce")),
+                  weights=self.box_coder.weights, xform_clip=self.box_coder.bbox_xform_clip,
+                  score_thresh=self.score_thresh, nms_thresh=self.nms_thresh,
+                  detections_per_img=self.detections_per_img, nms_mode=mode)
+    det, _, dcnt, ccnt, status = ops.roi_postprocess(class_logits, box_regression, proposals, image_shapes, **kwargs)
     counts = dcnt.tolist()                                          # the one sync of the batch
     if int(status.item()) & 1:
-        raise RuntimeError("candidate slab overflow in b200_roi_postprocess")
+        # more candidates than the default slab holds: cand_count has the true numbers, run again with room for them
+        need = int(ccnt.max().item())
+        det, _, dcnt, ccnt, status = ops.roi_postprocess(class_logits, box_regression, proposals, image_shapes,
+                                                         capacity=need, **kwargs)
+        counts = dcnt.tolist()
+        if int(status.item()) & 1:
+            raise RuntimeError("candidate slab overflow in b200_roi_postprocess")
     all_boxes, all_scores, all_labels = [], [], []
     for i, k in enumerate(counts):
         all_boxes.append(det[i, :k, :4])
