@@ -88,3 +88,15 @@ def test_header_is_plain_c():
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
                         os.path.join(ROOT, "include", "b200det.h")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_every_python_file_compiles():
+    """bench.py, __graft_entry__.py, benchmarks/ and the package parse (guards the scripts that only run on a GPU box)."""
+    import py_compile
+    for top in ("bench.py", "__graft_entry__.py"):
+        py_compile.compile(os.path.join(ROOT, top), doraise=True)
+    for sub in ("benchmarks", "object_detectors_b200", "oracle", "profiles"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith(".py"):
+                    py_compile.compile(os.path.join(dirpath, f), doraise=True)
