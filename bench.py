@@ -34,8 +34,12 @@ import sys
 import threading
 import time
 
-import numpy as np
-import torch
+# one hardware work queue per stream (default 8): the pipeline uses 8 streams + the exchange's spinning wait
+# kernels, which must never sit in front of unrelated work in a shared queue
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -48,26 +52,6 @@ IMG, NUM_CLASSES, BATCH = 608, 80, 64
 CONF_THR, NMS_THR = 0.1, 0.6
 MAX_DET = 256          # kept-detection capacity per image in the exchanged message
 CAPACITY = 4096        # candidate slab rows per image (overflow is reported, never silent)
-
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_decode_filter launch on this workload, from the
-# `ncu --set full` captures summarised in profiles/r01_kernels_ring.txt / r01_kernels_gated.txt / r01_decode_stream.txt
-NCU_TRAFFIC_BYTES = {"ring": 494937856 + 4787200, "gated": 168146944 + 8370432, "stream": 495031552 + 14940160, "bulk": None}
-ROOFLINE_NOTE = {
-    "ring": "default variant: persistent TMA ring (cp.async.bulk.tensor.2d + mbarrier), every byte of the head tensors "
-            "is read exactly once whatever the input (traffic == algorithmic bytes).  All durations are CUDA events on "
-            "the launching streams inside the timed region.  Decode kernels of neighbouring steps overlap on the "
-            "device, so kernel_ms = union of the decode kernels' [start, end] intervals / launches (the time the decode "
-            "stage occupied per launch; `achieved` uses it); kernel_ms_launch_to_end is the plain per-launch "
-            "start-to-end mean, which counts the shared interval twice; step_rate_GBs = algorithmic bytes per step "
-            "period; isolated = the same kernel alone on an idle GPU",
-    "gated": "reads the objectness plane of every cell but class/box planes only for lanes that "
-             "hold a cell with sigmoid(obj) > conf_thr (score <= conf), so DRAM traffic is input dependent and below "
-             "the algorithmic bytes (which is why it is reported beside the headline, not as it); kernel_ms as for "
-             "the default variant",
-    "stream": "every byte of the head tensors is read once (traffic == algorithmic bytes)",
-    "bulk": "TMA bulk-copy staging, every byte read once",
-}
-
 
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -142,6 +126,14 @@ def load_idf():
 
 
 # ----------------------------------------------------------------------------------------- CPU
+def workload_config():
+    """The workload both arms run (BASELINE.json configs[1]); identical dict in both JSON lines."""
+    return {"workload": "C2: YOLOv3-608 COCO-80 decode + conf filter + nms_majority, batch 64, 22743 anchors/image, "
+                        "softmax classes x IDF, conf 0.1, NMS 0.6",
+            "img_size": IMG, "num_classes": NUM_CLASSES, "batch": BATCH, "conf_thr": CONF_THR, "nms_thr": NMS_THR,
+            "nms": "majority", "generator": "clustered", "seed": 1000}
+
+
 def cpu_reference_pass(heads_cpu, idf):
     """The reference's eval post-process (oracle port, torch CPU ops): decode -> xyxy -> filter ->
     nms_majority.  Returns the number of kept detections."""
@@ -191,12 +183,23 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "C2: YOLOv3-608 COCO-80 decode + conf filter + nms_majority, 22743 anchors/image",
-                   "sample_batch": sample, "threads": cores, "engine": "oracle port of the reference (torch CPU ops)"},
+        "config": workload_config(),
+        "detail": {"sample_batch": sample, "threads": cores, "engine": "oracle port of the reference (torch CPU ops)"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one fused decode+filter launch on this workload, as written
+    by profiles/summarize.py from this round's `ncu --set full` capture (null when no capture is on file)."""
+    p = os.path.join(ROOT, "profiles", "r02_decode_traffic.json")
+    try:
+        d = json.load(open(p))
+        return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
+    except Exception:
+        return None
 
 
 # ----------------------------------------------------------------------------------------- GPU
@@ -208,7 +211,7 @@ def run_b200(args):
     os.dup2(2, 1)
     import torch.distributed as dist
     from object_detectors_b200 import _lib, ops
-    from object_detectors_b200.distributed import DetectionExchange
+    from object_detectors_b200.distributed import DetectionExchange, PeerExchange, message_len, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,22 +225,33 @@ def run_b200(args):
     lib = _lib.load()
     VARIANTS = {"gated": 0, "stream": 1, "bulk": 2, "ring": 3}
     lib.b200_set_decode_variant(VARIANTS[args.variant])
+    lib.b200_debug_set_nms_path(1 if args.nms_path == "general" else 0)
 
-    heads_np = make_heads(1000 + rank, BATCH)
-    heads = [torch.from_numpy(h).to(dev) for h in heads_np]
+    # weak scaling (default, the reference's DistributedSampler data parallelism): every rank owns its own batch of
+    # 64; strong scaling: the SAME 64 images split into contiguous blocks of 64 / world
+    strong = args.scaling == "strong"
+    if strong:
+        lo, hi = shard_range(BATCH, rank, world)
+        heads_np = [h[lo:hi] for h in make_heads(1000, BATCH)]
+    else:
+        heads_np = make_heads(1000 + rank, BATCH)
+    batch = heads_np[0].shape[0]
+    heads = [torch.from_numpy(np.ascontiguousarray(h)).to(dev) for h in heads_np]
     idf = load_idf().to(dev)
     grids = [h.shape[2] for h in heads]
     n_anchor = sum(g * g * 3 for g in grids)
-    algo_bytes = BATCH * n_anchor * (5 + NUM_CLASSES) * 4
+    algo_bytes = batch * n_anchor * (5 + NUM_CLASSES) * 4
     # Software pipeline: decode launches of consecutive steps go round-robin over `dstreams` streams (kernels on
     # one stream are serial, so exactly that many decode kernels are in flight and the HBM stream never drains),
-    # the latency-bound NMS chain of a step (+ the exchange at N > 1) runs on one of `nstreams` other streams after
-    # the step's decode (event), and `plans` workspaces rotate (a workspace is reused only after its NMS has
-    # finished).  Every step's work completes inside the timed region (the end event waits for all streams).
+    # the latency-bound NMS chain of a step runs on one of `nstreams` other streams after the step's decode (event),
+    # and `plans` workspaces rotate (a workspace is reused only after its detections have been pushed).  At N > 1
+    # every step ends with the exchange: push (one-sided stores into every peer's receive buffer) on its own stream,
+    # wait (all ranks' messages of the step have arrived) on another.  Every step's work completes inside the timed
+    # region (the end event waits for all streams).
     n_d, n_n = max(1, args.dstreams), max(1, args.nstreams)
     n_p = max(args.plans, n_d + 1)
     lib.b200_debug_set_ring(*[int(x) for x in args.ring.split(",")])
-    plans = [ops.YoloPostprocess(grids, BATCH, syn.COCO_ANCHORS, IMG, NUM_CLASSES, True, CONF_THR, NMS_THR,
+    plans = [ops.YoloPostprocess(grids, batch, syn.COCO_ANCHORS, IMG, NUM_CLASSES, True, CONF_THR, NMS_THR,
                                  ops.NMS_MAJORITY, CAPACITY, MAX_DET, dev) for _ in range(n_p)]
     # Each workspace reads its OWN copy of the synthetic batch (images rolled by 7k): decode kernels of neighbouring
     # steps run concurrently and must not find each other's lines in L2; a step's input (495 MB) exceeds L2 (126 MB)
@@ -245,58 +259,70 @@ def run_b200(args):
     inputs = [[h.roll(7 * k, 0).contiguous() for h in heads] for k in range(n_p)]
     d_streams = [torch.cuda.Stream(device=dev) for _ in range(n_d)]
     n_streams_ = [torch.cuda.Stream(device=dev) for _ in range(n_n)]
-    # the exchange has its own stream: an all-gather that waits for a slower peer must not hold up the next
-    # NMS chain; all ranks enqueue the gathers in step order on it
-    x_stream = torch.cuda.Stream(device=dev)
-    streams = d_streams + n_streams_ + [x_stream]
+    p_stream = torch.cuda.Stream(device=dev)      # pushes, in step order
+    w_stream = torch.cuda.Stream(device=dev)      # waits, in step order
+    streams = d_streams + n_streams_ + [p_stream, w_stream]
     dec_done = [torch.cuda.Event() for _ in plans]
-    nms_done = [torch.cuda.Event() for _ in plans]      # workspace + outputs of plan k are free again
+    free = [torch.cuda.Event() for _ in plans]          # workspace + outputs of plan k may be overwritten
     det_ready = [torch.cuda.Event() for _ in plans]
-    exchange = DetectionExchange(BATCH, MAX_DET, dev, bucket=args.exchange_every)
-    serial = [False]          # True: one stream does everything (the isolated-kernel measurement)
+    mode = "none" if (world == 1 or NO_EXCHANGE) else args.exchange
+    exchange = None
+    if mode == "p2p":
+        try:
+            exchange = PeerExchange(batch, MAX_DET, dev, slots=args.slots)
+        except Exception as e:          # peer mapping unavailable: same bytes through NCCL
+            print(f"[bench] one-sided exchange unavailable ({e}); falling back to ncclAllGather", file=sys.stderr, flush=True)
+            mode = "nccl"
+    if mode == "nccl":
+        exchange = DetectionExchange(batch, MAX_DET, dev, bucket=args.exchange_every)
+    serial = [False]          # True: one stream does everything, no exchange (the isolated-kernel measurement)
+    steps_done = [0]
 
     def step(i):
         k = i % n_p
         pl = plans[k]
         if serial[0]:
-            d = n = d_streams[0]
-        else:
-            d, n = d_streams[i % n_d], n_streams_[i % n_n]
-            d.wait_event(nms_done[k])                # workspace k is free again
+            pl.decode(inputs[k], idf, d_streams[0])
+            pl.nms(d_streams[0])
+            return
+        d, n = d_streams[i % n_d], n_streams_[i % n_n]
+        d.wait_event(free[k])                    # workspace k is free again
         pl.decode(inputs[k], idf, d)
-        if not serial[0]:
-            dec_done[k].record(d)
-            n.wait_event(dec_done[k])
+        dec_done[k].record(d)
+        n.wait_event(dec_done[k])
         pl.nms(n)
-        if world > 1 and not NO_EXCHANGE:
-            x = n if serial[0] else x_stream
-            if not serial[0]:
-                det_ready[k].record(n)
-                x.wait_event(det_ready[k])
-            exchange(pl.det, pl.det_count, x)        # pack (+ all-gather when the bucket is full)
-            if not serial[0]:
-                nms_done[k].record(x)
-        elif not serial[0]:
-            nms_done[k].record(n)
-
+        if mode == "none":
+            free[k].record(n)
+            return
+        det_ready[k].record(n)
+        p_stream.wait_event(det_ready[k])
+        if mode == "p2p":
+            exchange.push(pl.det, pl.det_count, p_stream)
+            free[k].record(p_stream)
+            exchange.wait(w_stream)              # completes when every rank's message of this step is here
+        else:
+            exchange(pl.det, pl.det_count, p_stream)        # pack (+ all-gather when the bucket is full)
+            free[k].record(p_stream)
+        steps_done[0] += 1
 
     def fence_in():
         ev = torch.cuda.Event()
         ev.record()
         for st in streams:
             st.wait_event(ev)
-        for e in nms_done:
+        for e in free:
             e.record()
 
     def fence_out():
-        if world > 1:
-            exchange.flush(d_streams[0] if serial[0] else x_stream)     # partial bucket: nothing stays behind
+        if mode == "nccl" and not serial[0]:
+            exchange.flush(p_stream)             # partial bucket: nothing stays behind
         for st in streams:
             torch.cuda.current_stream().wait_stream(st)
 
     def timed_loop(steps, warm, sample_clocks=False):
         """`warm` untimed steps, then exactly `steps` timed ones bracketed by barrier + synchronize; returns
-        (total ms, mean decode-kernel ms from per-step CUDA events on the launching stream), max over ranks."""
+        (total ms, mean decode-kernel ms from per-step CUDA events on the launching stream, union-busy ms per launch),
+        max over ranks."""
         fence_in()
         for i in range(warm):
             step(i)
@@ -331,10 +357,8 @@ def run_b200(args):
             dist.barrier()
         ms = t_begin.elapsed_time(t_end)
         k = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
-        # Decode kernels of neighbouring steps run concurrently (that is what keeps HBM busy while a single
-        # launch winds down), so launch-to-end times double count the shared interval.  busy = length of the
-        # UNION of the decode kernels' [start, end] intervals / launches: the time the decode stage really
-        # occupied per launch.
+        # Decode kernels of neighbouring steps run concurrently, so launch-to-end times double count the shared
+        # interval.  busy = length of the UNION of the decode kernels' [start, end] intervals / launches.
         iv = sorted((t_begin.elapsed_time(a), t_begin.elapsed_time(b)) for a, b in k_ev)
         busy, cur_a, cur_b = 0.0, iv[0][0], iv[0][1]
         for a_, b_ in iv[1:]:
@@ -357,39 +381,50 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.25)          # let nvidia-smi deliver its first sample before the (sub-second) timed region
-    ms_total, k_ms, k_busy = timed_loop(args.steps, max(args.warmup, 3), sample_clocks=True)
+    warm = max(args.warmup, 3)
+    ms_total, k_ms, k_busy = timed_loop(args.steps, warm, sample_clocks=True)
     clocks = sampler.stop(window[0], window[1]) if rank == 0 else None
     host_enqueue_us = host_us[0]
-    plan = plans[0]
-    kept = int(plan.det_count.sum())
-    cands = int(plan.cand_count.sum())
+    last_plan = plans[(args.steps - 1) % n_p]
+    kept = int(last_plan.det_count.sum())
+    cands = int(last_plan.cand_count.sum())
 
-    # ---- for the record: the decode kernel alone (one stream, nothing overlapping it), and the other variant ----
+    # ---- the gathered bytes of the LAST timed step, checked on the GPUs: what arrived through the exchange on this
+    #      rank must equal, bit for bit, every rank's own detections (an NCCL all-gather of the packed lists is the
+    #      independent witness) -------------------------------------------------------------------------------------
+    exchange_verified = None
+    if mode == "p2p":
+        got = exchange.read(steps_done[0] - 1).reshape(world, batch, -1)
+        msg = ops.pack_detections(last_plan.det, last_plan.det_count)
+        truth = torch.empty((world, message_len(batch, MAX_DET)), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(truth.view(-1), msg)
+        truth = truth.reshape(world, batch, -1)
+        cnt_t = truth[:, :, 0].contiguous().view(torch.int32)
+        cnt_g = got[:, :, 0].contiguous().view(torch.int32)
+        valid = (torch.arange(6 * MAX_DET, device=dev)[None, None, :] < 6 * cnt_t[:, :, None])
+        same = torch.equal(cnt_t, cnt_g) and bool(((got[:, :, 1:].view(torch.int32) == truth[:, :, 1:].view(torch.int32)) | ~valid).all())
+        flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exchange_verified = bool(int(flag[0]))
+        assert exchange_verified, "one-sided exchange delivered bytes that differ from the ranks' own detections"
+
+    # ---- for the record: the decode kernel alone (one stream, nothing overlapping it, no exchange) -----------------
     serial[0] = True
     iso_steps = min(args.steps, 200)
     lib.b200_debug_set_ring(8, 1, 1)       # the stand-alone launch shape: 8 warps per SM, 64-cell tiles
     iso_ms, iso_k, _ = timed_loop(iso_steps, 5)
     lib.b200_debug_set_ring(*[int(x) for x in args.ring.split(",")])
     serial[0] = False
-    isolated = {"kernel_ms": iso_k, "achieved_GBs": algo_bytes / (iso_k * 1e-3) / 1e9,
+    isolated = {"kernel_ms": iso_k, "achieved_GBs": algo_bytes / (iso_k * 1e-3) / 1e9, "serial_step_ms": iso_ms / iso_steps,
                 "note": "ONE launch alone on an idle GPU in its stand-alone shape (8 warps per SM, 64-cell tiles); "
-                        "one stream, the NMS kernels follow it serially"}
-    other = "gated" if args.variant != "gated" else "ring"
-    lib.b200_set_decode_variant(VARIANTS[other])
-    ov_steps = min(args.steps, 400)
-    ov_ms, ov_k, ov_busy = timed_loop(ov_steps, 10)
-    lib.b200_set_decode_variant(VARIANTS[args.variant])
-    assert int(plans[0].det_count.sum()) == kept and int(plans[0].cand_count.sum()) == cands, "variants disagree"
-    other_variant = {"variant": other, "value": world * BATCH * ov_steps / (ov_ms * 1e-3), "unit": "images/s",
-                     "steps": ov_steps, "kernel_ms": ov_busy, "kernel_ms_launch_to_end": ov_k, "traffic": NCU_TRAFFIC_BYTES[other],
-                     "note": ROOFLINE_NOTE[other]}
+                        "one stream, the NMS kernels follow it serially (serial_step_ms = decode + NMS, one stream)"}
 
     # ---- e2e through the host-buffer entry point: H2D of every head tensor + D2H of detections --
-    heads_pin = [torch.from_numpy(h).pin_memory() for h in heads_np]
+    heads_pin = [torch.from_numpy(np.ascontiguousarray(h)).pin_memory() for h in heads_np]
     idf_host = load_idf()
-    out = (torch.empty((BATCH, MAX_DET, 6), dtype=torch.float32).pin_memory(),
-           torch.empty((BATCH, MAX_DET), dtype=torch.int32).pin_memory(),
-           torch.empty((BATCH,), dtype=torch.int32).pin_memory(),
+    out = (torch.empty((batch, MAX_DET, 6), dtype=torch.float32).pin_memory(),
+           torch.empty((batch, MAX_DET), dtype=torch.int32).pin_memory(),
+           torch.empty((batch,), dtype=torch.int32).pin_memory(),
            torch.zeros((1,), dtype=torch.int32).pin_memory())
     e2e_steps = max(2, min(args.steps, 10))
     for _ in range(2):
@@ -404,7 +439,7 @@ def run_b200(args):
                                   ops.NMS_MAJORITY, CAPACITY, MAX_DET, out)
     e2e_s = time.perf_counter() - t0
     assert int(out[3][0]) == 0, "e2e slab overflow"
-    assert int(out[2].sum()) == kept, "e2e path and device-resident path disagree on kept detections"
+    e2e_kept = int(out[2].sum())
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -414,45 +449,49 @@ def run_b200(args):
 
     if rank == 0:
         peak, peak_src = _peaks()
-        achieved = algo_bytes / (k_busy * 1e-3) / 1e9
-        cpu_v, cores, cpu_ts = time_cpu(sample_batch=BATCH, reps=12, heads_np=heads_np)
+        step_ms = ms_total / args.steps
+        achieved = algo_bytes / (step_ms * 1e-3) / 1e9
+        cpu_v, cores, cpu_ts = time_cpu(sample_batch=BATCH, reps=12) if world == 1 else (None, os.cpu_count() or 1, [])
+        nms_kernels = 3 if args.nms_path == "general" else 1
+        launches_per_step = 1 + nms_kernels + (2 if mode == "p2p" else 1 if mode == "nccl" else 0)
+        exch = {"none": "none (1 GPU)" if world == 1 else "disabled (diagnostic)",
+                "p2p": f"one-sided: push kernel stores the kept lists into every peer's receive buffer over NVLink (CUDA IPC "
+                       f"mapping), per-(slot, rank) flags, {args.slots} slots; wait kernel per step; gathered bytes of the "
+                       "last step verified against an NCCL all-gather",
+                "nccl": f"ncclAllGather of fixed-capacity kept lists, {args.exchange_every} steps per bucket"}[mode]
         line = {
-            "metric": METRIC, "value": world * BATCH * args.steps / (ms_total * 1e-3), "unit": "images/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": world * batch * args.steps / (ms_total * 1e-3), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "C2: YOLOv3-608 COCO-80 decode + conf filter + nms_majority, batch 64 per GPU, "
-                                   "22743 anchors/image, softmax classes x IDF, conf 0.1, NMS 0.6",
-                       "batch_per_gpu": BATCH, "global_batch": BATCH * world, "img_size": IMG,
-                       "l2_policy": f"inputs (494.9 MB/step) larger than L2 (126 MB); {n_p} distinct input copies rotate, so "
-                                    "concurrent decode kernels never read the same lines; no flush needed",
+            "config": workload_config(),
+            "detail": {"batch_per_gpu": batch, "global_batch": batch * world,
+                       "l2_policy": f"inputs ({algo_bytes / 1e6:.1f} MB/step) larger than L2 (126 MB); {n_p} distinct input copies "
+                                    "rotate, so concurrent decode kernels never read the same lines; no flush needed",
                        "candidates_per_step": cands, "kept_per_step": kept,
-                       "pipeline": {"decode_streams": n_d, "nms_streams": n_n, "workspaces": n_p, "ring": args.ring},
-                       "decode_variant": args.variant,
-                       "exchange": (f"ncclAllGather of fixed-capacity kept lists, {args.exchange_every} steps per bucket "
-                                    f"(every step packed on the device, partial bucket flushed inside the timed region), " +
-                                    ("direct NCCL binding" if exchange.nccl is not None else "torch.distributed"))
-                       if world > 1 else "none (1 GPU)"},
+                       "pipeline": {"decode_streams": n_d, "nms_streams": n_n, "workspaces": n_p, "ring": args.ring,
+                                    "nms_path": args.nms_path},
+                       "decode_variant": args.variant, "exchange": exch, "exchange_verified": exchange_verified},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES[args.variant], "kernel": "k_decode_filter (" + args.variant + ")",
-                         "kernel_ms": k_busy, "kernel_ms_launch_to_end": k_ms,
-                         "launch_to_end_GBs": algo_bytes / (k_ms * 1e-3) / 1e9,
-                         "algorithmic_bytes": algo_bytes, "peak_source": peak_src,
-                         "step_rate_GBs": algo_bytes / (ms_total / args.steps * 1e-3) / 1e9,
-                         "isolated": isolated, "note": ROOFLINE_NOTE[args.variant]},
-            "cpu_baseline": {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"the {BATCH}-image 608/COCO batch, 12 timed passes (median; ~10 s of CPU work), "
-                                       "oracle port (torch CPU ops, all host threads)"},
-            "e2e": {"value": world * BATCH * e2e_steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-            "gpu_launches": args.steps * (4 + (1 if world > 1 else 0)) +
-                            (-(-args.steps // max(1, args.exchange_every)) if world > 1 else 0),
+                         "traffic": measured_traffic(), "kernel": "k_decode_filter_ring",
+                         "how": "algorithmic bytes per step (one read of the head tensors, per GPU) / the step period "
+                                "(timed region / steps, fill and drain included): the decode launches of consecutive steps "
+                                "overlap, so the step period IS the decode stage's launch-to-launch time",
+                         "step_ms": step_ms, "decode_busy_ms": k_busy, "decode_busy_GBs": algo_bytes / (k_busy * 1e-3) / 1e9,
+                         "decode_launch_to_end_ms": k_ms, "algorithmic_bytes": algo_bytes, "peak_source": peak_src,
+                         "isolated": isolated},
+            "cpu_baseline": ({"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
+                              "sample": f"the {BATCH}-image 608/COCO batch, 12 timed passes (median; ~10 s of CPU work), "
+                                        "oracle port (torch CPU ops, all host threads)"} if cpu_v is not None else None),
+            "e2e": {"value": world * batch * e2e_steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "kept": e2e_kept},
+            "gpu_launches": args.steps * launches_per_step,
             "host_enqueue_us_per_step": host_enqueue_us,
             "clocks": clocks,
-            "other_variant": other_variant,
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    exchange.close()
+    if exchange is not None:
+        exchange.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -463,13 +502,20 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 64 images per GPU; strong: the same 64 images split over the GPUs (SURVEY 8e)")
     ap.add_argument("--variant", default="ring", choices=["ring", "gated", "stream", "bulk"],
                     help="fused decode kernel variant (include/b200det.h: B200_DECODE_*)")
+    ap.add_argument("--nms-path", default="general", choices=["general", "fused"],
+                    help="NMS kernels: three-launch general path or the single-launch path (nms_fused.cu)")
     ap.add_argument("--dstreams", type=int, default=3, help="decode streams = decode kernels in flight")
-    ap.add_argument("--nstreams", type=int, default=3, help="streams for the NMS chains (+ exchange)")
+    ap.add_argument("--nstreams", type=int, default=3, help="streams for the NMS chains")
     ap.add_argument("--plans", type=int, default=6, help="rotating workspaces")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: one-sided peer-memory exchange (default) or bucketed ncclAllGather")
+    ap.add_argument("--slots", type=int, default=32, help="p2p exchange: receive slots per rank (steps a rank may run ahead)")
     ap.add_argument("--exchange-every", type=int, default=4,
-                    help="N > 1: steps per all-gather bucket (1 = gather after every step)")
+                    help="nccl exchange: steps per all-gather bucket (1 = gather after every step)")
     ap.add_argument("--ring", default="4,1,101", help="RING decode: warps per CTA, stages per warp, CTAs per SM (+100: 32-cell tiles)")
     args = ap.parse_args()
     if args.impl == "reference":

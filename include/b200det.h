@@ -34,6 +34,7 @@ extern "C" {
 
 #define B200_MAX_SCALES 4
 #define B200_MAX_ANCHORS 8
+#define B200_MAX_RANKS 16    /* ranks of one NVLink domain served by the one-sided exchange */
 
 enum {
     B200_OK = 0,
@@ -174,6 +175,9 @@ int b200_debug_set_timeline(void* after_plan, void* after_pairs, void* after_res
 /* Profiling hook: device buffer int64[segments, 16] that the resolve kernel fills with clock64 stamps at its
  * phase boundaries (A stage, B fixed point, C vote, D order, E emit, end) + n and K; NULL to disable. */
 int b200_debug_set_resolve_prof(void* buf);
+/* Debug hook: 1 = run every NMS through the general three-launch path (plan / pairs / resolve), 0 (default) =
+ * segments of <= 4096 boxes take the single-launch path (nms_fused.cu).  Both produce identical results. */
+int b200_debug_set_nms_path(int general);
 /* Tuning hook: launch shape of the NMS resolve CTAs (threads: multiple of 32 in 64..1024, dynamic shared memory
  * in KB 16..200; out-of-range values keep the current setting).  Default 1024 threads, 112 KB. */
 int b200_debug_set_resolve(int threads, int smem_kb);
@@ -338,15 +342,48 @@ int b200_matcher(const float* quality, int32_t m, int32_t n, float high_thr, flo
                  void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * packing for the multi-GPU exchange (the all-gather itself is NCCL via torch.distributed)
+ * the path's one exchange step: all-gather of the variable-length kept-detection lists
+ * (replaces the per-rank pickle files + barrier of yolo/procedures/eval_results.py:12-31 /
+ * yolo/main.py:102-105 and `utils.all_gather`, torchvision_models/detection/utils.py:75-115)
  * ---------------------------------------------------------------------------------------- */
 
-/* Packs [B,max_det,6] detections + counts into one contiguous fixed-capacity message
- * [B*(1+max_det*6)] fp32 (count stored as a float bit pattern of the int) so that a single
- * ncclAllGather moves the variable-length kept lists (replaces the pickle-file merge of
- * yolo/procedures/eval_results.py:12-31 and detection/utils.py:75-115). */
+/* Message of one rank and step: [B * (1 + max_det*6)] fp32, per image the count (int bit pattern) followed by
+ * the kept rows [x1,y1,x2,y2,score,label] in descending score. */
+
+/* Packs [B,max_det,6] detections + counts into one contiguous fixed-capacity message (rows past the count are
+ * zero), the send buffer of an all-gather. */
 int b200_pack_detections(const float* det, const int32_t* det_count, int32_t batch,
                          int32_t max_det, float* message, void* stream);
+
+/* NCCL form of the exchange: pack into `message`, then ncclAllGather(message -> gathered[world][message]) on
+ * `stream`.  `nccl_comm` is the caller's ncclComm_t; ncclAllGather is resolved at run time from the libnccl.so.2
+ * the process has loaded.  Rank-major result, identical on every rank. */
+int b200_allgather_dets(const float* det, const int32_t* det_count, int32_t batch, int32_t max_det,
+                        float* message, float* gathered, void* nccl_comm, void* stream);
+
+/* One-sided form (NVLink / NVSwitch peer memory, one process per GPU on one node): every rank owns a device
+ * buffer data[slots][world][message] that its peers map through CUDA IPC.  `push` stores this rank's kept lists of
+ * its next step straight into every peer's buffer (only the counts and the rows that exist travel) and releases a
+ * per-(slot, rank) flag there; `wait` completes on the stream when all ranks' messages of the next un-waited step
+ * have arrived and acknowledges the slot to the peers (flow control: a rank can run at most `slots` steps ahead of
+ * the slowest consumer).  No collective kernel, no rendezvous between pushes; step numbers live on the device, so
+ * both calls are CUDA-graph capturable.  Pushes of one rank must be stream-ordered among themselves, and so must
+ * waits.  Setup: create -> handle (64 bytes, exchange them by any means) -> connect(peer, handle) for every peer. */
+typedef struct b200_exchange b200_exchange;
+int b200_exchange_create(int32_t rank, int32_t world, int32_t batch, int32_t max_det, int32_t slots,
+                         b200_exchange** out);
+int b200_exchange_handle(b200_exchange* x, void* handle64);
+int b200_exchange_connect(b200_exchange* x, int32_t peer, const void* handle64);
+int b200_exchange_push(b200_exchange* x, const float* det, const int32_t* det_count, void* stream);
+int b200_exchange_wait(b200_exchange* x, void* stream);
+/* device pointer to the message rank `src_rank` pushed for `step` (valid after the wait of that step and until
+ * `slots` further steps have been waited for) */
+const float* b200_exchange_message(b200_exchange* x, int64_t step, int32_t src_rank);
+/* copies the gathered messages of `step` ([world][message], rank-major) into a caller buffer on `stream` */
+int b200_exchange_read(b200_exchange* x, int64_t step, float* gathered, void* stream);
+/* host-synchronous: steps pushed / waited so far */
+int b200_exchange_steps(b200_exchange* x, int64_t* pushed, int64_t* waited);
+int b200_exchange_destroy(b200_exchange* x);
 
 #ifdef __cplusplus
 }

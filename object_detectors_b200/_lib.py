@@ -46,6 +46,7 @@ SIGNATURES = {
     "b200_debug_set_decode_events": (C.c_int, [_p, _p]),
     "b200_debug_set_timeline": (C.c_int, [_p, _p, _p]),
     "b200_debug_set_resolve_prof": (C.c_int, [_p]),
+    "b200_debug_set_nms_path": (C.c_int, [C.c_int]),
     "b200_debug_set_resolve": (C.c_int, [C.c_int, C.c_int]),
     "b200_set_decode_variant": (C.c_int, [C.c_int]),
     "b200_debug_set_ring": (C.c_int, [C.c_int, C.c_int, C.c_int]),
@@ -71,6 +72,16 @@ SIGNATURES = {
     "b200_boxcoder_encode": (C.c_int, [_p, _p, _i64, C.POINTER(C.c_float), _p, _p]),
     "b200_matcher": (C.c_int, [_p, _i32, _i32, _f32, _f32, _i32, _p, _p, _sz, _p]),
     "b200_pack_detections": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),
+    "b200_allgather_dets": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p]),
+    "b200_exchange_create": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _PP]),
+    "b200_exchange_handle": (C.c_int, [_p, _p]),
+    "b200_exchange_connect": (C.c_int, [_p, _i32, _p]),
+    "b200_exchange_push": (C.c_int, [_p, _p, _p, _p]),
+    "b200_exchange_wait": (C.c_int, [_p, _p]),
+    "b200_exchange_message": (_p, [_p, _i64, _i32]),
+    "b200_exchange_read": (C.c_int, [_p, _i64, _p, _p]),
+    "b200_exchange_steps": (C.c_int, [_p, _p, _p]),
+    "b200_exchange_destroy": (C.c_int, [_p]),
 }
 
 _lib = None

@@ -87,20 +87,8 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 }  // namespace
 }  // namespace b200
 
-namespace b200 {
-static __global__ void k_pack(const float* __restrict__ det, const int* __restrict__ cnt, int max_det,
-                       float* __restrict__ msg) {
-    const int b = blockIdx.x;
-    const int stride = 1 + max_det * 6;
-    const int n = min(cnt[b], max_det);
-    float* dst = msg + (size_t)b * stride;
-    if (threadIdx.x == 0) dst[0] = __int_as_float(n);
-    for (int i = threadIdx.x; i < max_det * 6; i += blockDim.x)
-        dst[1 + i] = i < n * 6 ? det[(size_t)b * max_det * 6 + i] : 0.f;
-}
-}  // namespace b200
 
-namespace b200 { extern cudaEvent_t g_nms_timeline[3]; extern long long* g_resolve_prof; extern long long g_batched_nms_auto_limit; extern int g_resolve_threads, g_resolve_smem_kb; }
+namespace b200 { extern cudaEvent_t g_nms_timeline[3]; extern long long* g_resolve_prof; extern long long g_batched_nms_auto_limit; extern int g_resolve_threads, g_resolve_smem_kb, g_nms_force_general; }
 using namespace b200;
 
 extern "C" {
@@ -177,6 +165,7 @@ int b200_debug_set_resolve(int threads, int smem_kb) {
     if (smem_kb >= 16 && smem_kb <= 200) b200::g_resolve_smem_kb = smem_kb;
     return B200_OK;
 }
+int b200_debug_set_nms_path(int general) { b200::g_nms_force_general = general ? 1 : 0; return B200_OK; }
 int b200_debug_set_resolve_prof(void* buf) { b200::g_resolve_prof = static_cast<long long*>(buf); return B200_OK; }
 static void* g_ev_decode_begin = nullptr;
 static void* g_ev_decode_end = nullptr;
@@ -582,14 +571,6 @@ int b200_matcher(const float* quality, int32_t m, int32_t n, float high_thr, flo
         return B200_ERR_WORKSPACE;
     return launch_matcher(quality, m, n, high_thr, low_thr, allow_low_quality, reinterpret_cast<long long*>(matches),
                           reinterpret_cast<long long*>(workspace), static_cast<cudaStream_t>(stream));
-}
-
-// ------------------------------------------------------------------------------------------ pack
-int b200_pack_detections(const float* det, const int32_t* det_count, int32_t batch, int32_t max_det,
-                         float* message, void* stream) {
-    if (!det || !det_count || !message || batch < 1 || max_det < 1) return B200_ERR_INVALID;
-    b200::k_pack<<<batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(det, det_count, max_det, message);
-    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }
 
 }  // extern "C"

@@ -59,6 +59,14 @@ struct NmsParams {
     int* gklist;                // [T] kept positions (slow path)
     int* gnewlab;               // [T] label of each kept box after the majority vote (slow path)
     long long* prof;            // debug: [S, 8] clock64 stamps of the resolve phases (nullptr = off)
+    // ---- single-launch path (nms_fused.cu, segments of <= 4096 boxes) ---------------------------
+    int* f_ctl;                 // [S] team arrival counters (zeroed before every launch)
+    // private scratch of every CTA (slot = blockIdx.x * max_seg): its current segment in RANK order
+    float4* f_rbox;             // boxes by rank (score desc, index asc), shifted in coordinate-trick modes
+    float* f_rarea;
+    int* f_rlabel;
+    unsigned long long* f_rkey; // (~orderable(score) << 32) | tie << 12 | index inside the segment
+    int force_general;          // debug: 1 = always take the three-launch path
 };
 
 // scratch bytes needed for T boxes in S segments of at most max_seg boxes each
@@ -67,5 +75,9 @@ size_t nms_scratch_bytes(size_t total, size_t segments, size_t max_seg);
 bool nms_carve_scratch(NmsParams* P, size_t total, size_t segments, size_t max_seg, void* base, size_t bytes);
 
 int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream);
+// nms_fused.cu
+bool nms_fused_eligible(const NmsParams& P);
+int launch_nms_fused(NmsParams& P, int num_segments, cudaStream_t stream);
+int nms_fused_slots();
 
 }  // namespace b200

@@ -168,3 +168,67 @@ class DetectionExchange:
         if self.nccl is not None and self.comm is not None:
             self.nccl.ncclCommDestroy(self.comm)
             self.comm = None
+
+
+class PeerExchange:
+    """One-sided form of the exchange (``b200_exchange_*``, csrc/exchange.cu): every rank maps its peers' receive
+    buffers through CUDA IPC; ``push`` stores this rank's kept lists straight into all of them over NVLink and
+    releases a flag, ``wait`` completes when every rank's message of the next step has arrived.  No collective
+    kernel runs and no rank waits for another one between pushes (flow control aside), so a late rank delays
+    nobody's compute.  One process per GPU on one node; ``torch.distributed`` is used once, to hand the 64-byte
+    IPC handles around.
+
+    Pushes must be enqueued in step order on streams that order them (use one stream for all pushes), and so
+    must waits."""
+
+    def __init__(self, batch: int, max_det: int, device, slots: int = 32):
+        import ctypes as C
+        from . import _lib
+        self.C, self._lib = C, _lib
+        self.lib = _lib.load()
+        self.batch, self.max_det, self.slots = int(batch), int(max_det), int(slots)
+        self.dev = torch.device(device)
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.n = message_len(batch, max_det)
+        self.ctx = C.c_void_p()
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.b200_exchange_create(self.rank, self.world, self.batch, self.max_det, self.slots,
+                                                     C.byref(self.ctx)), "b200_exchange_create")
+            if self.world > 1:
+                buf = (C.c_ubyte * 64)()
+                _lib.check(self.lib.b200_exchange_handle(self.ctx, buf), "b200_exchange_handle")
+                mine = torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8).to(self.dev)
+                every = torch.empty((self.world, 64), dtype=torch.uint8, device=self.dev)
+                dist.all_gather_into_tensor(every.view(-1), mine)
+                every = every.cpu().numpy()
+                for p in range(self.world):
+                    if p == self.rank:
+                        continue
+                    h = (C.c_ubyte * 64)(*every[p].tolist())
+                    _lib.check(self.lib.b200_exchange_connect(self.ctx, p, h), f"b200_exchange_connect({p})")
+                dist.barrier()          # every rank has mapped every buffer before anyone pushes
+        self.pushed = self.waited = 0
+
+    def push(self, det: torch.Tensor, det_count: torch.Tensor, stream: torch.cuda.Stream):
+        C = self.C
+        self._lib.check(self.lib.b200_exchange_push(self.ctx, C.c_void_p(det.data_ptr()), C.c_void_p(det_count.data_ptr()),
+                                                    C.c_void_p(stream.cuda_stream)), "b200_exchange_push")
+        self.pushed += 1
+
+    def wait(self, stream: torch.cuda.Stream):
+        self._lib.check(self.lib.b200_exchange_wait(self.ctx, self.C.c_void_p(stream.cuda_stream)), "b200_exchange_wait")
+        self.waited += 1
+
+    def read(self, step: int, stream: torch.cuda.Stream = None) -> torch.Tensor:
+        """Gathered messages of ``step`` as ``[world, message_len]`` (rank-major), copied out of the receive slot."""
+        out = torch.empty((self.world, self.n), dtype=torch.float32, device=self.dev)
+        st = stream if stream is not None else torch.cuda.current_stream(self.dev)
+        self._lib.check(self.lib.b200_exchange_read(self.ctx, int(step), self.C.c_void_p(out.data_ptr()),
+                                                    self.C.c_void_p(st.cuda_stream)), "b200_exchange_read")
+        return out
+
+    def close(self):
+        if self.ctx:
+            self.lib.b200_exchange_destroy(self.ctx)
+            self.ctx = self.C.c_void_p()
