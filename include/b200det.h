@@ -376,8 +376,8 @@ int b200_exchange_handle(b200_exchange* x, void* handle64);
 int b200_exchange_connect(b200_exchange* x, int32_t peer, const void* handle64);
 int b200_exchange_push(b200_exchange* x, const float* det, const int32_t* det_count, void* stream);
 int b200_exchange_wait(b200_exchange* x, void* stream);
-/* device pointer to the message rank `src_rank` pushed for `step` (valid after the wait of that step and until
- * `slots` further steps have been waited for) */
+/* device pointer to the message rank `src_rank` pushed for `step`: valid from the completion of that step's wait
+ * until the NEXT b200_exchange_wait runs on the stream (readers enqueue their work between the two waits) */
 const float* b200_exchange_message(b200_exchange* x, int64_t step, int32_t src_rank);
 /* copies the gathered messages of `step` ([world][message], rank-major) into a caller buffer on `stream` */
 int b200_exchange_read(b200_exchange* x, int64_t step, float* gathered, void* stream);

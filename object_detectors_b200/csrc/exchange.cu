@@ -12,7 +12,8 @@
 //     of the 6 KB fixed-capacity record) -- and, once a peer's copy is complete (system-scope fence, last CTA),
 //     releases flags[step % slots][rank] = step + 1 in that peer's memory;
 //   * b200_exchange_wait   (one warp) completes on the stream when the flags of all ranks for the next un-waited step
-//     have arrived, then tells every peer (acks[rank] = step + 1) that the slot may be reused `slots` steps later.
+//     have arrived, and tells every peer (acks[rank] = step) that the slots of all EARLIER steps may be reused: what
+//     the rank enqueued on the wait stream before this wait -- its reads of the previous step -- has completed.
 // The step numbers live on the device (the kernels advance them), so both calls can be captured in CUDA graphs.
 // A rank never waits for a peer except (i) in b200_exchange_wait, which is the semantics of a gather, and (ii) in
 // b200_exchange_push when a peer is more than `slots` steps behind (flow control).
@@ -96,7 +97,10 @@ k_exchange_wait(const __grid_constant__ ExchangeDev X) {
     }
     __threadfence_system();                                        // acquire: the messages behind the flags
     __syncwarp();
-    if (p < X.world) st_sys(X.acks[p] + X.rank, step + 1ull);      // rank p may reuse this slot `slots` steps later
+    // Everything this rank enqueued on this stream before this launch has finished, in particular its reads of the
+    // PREVIOUS step's messages: steps < `step` are consumed, rank p may overwrite their slots.  (The message of
+    // `step` itself stays valid until the next wait runs.)
+    if (p < X.world) st_sys(X.acks[p] + X.rank, step);
     if (p == 0) *X.wait_step = step + 1ull;
 }
 

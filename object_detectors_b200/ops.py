@@ -198,7 +198,11 @@ class YoloPostprocess:
         return self.det, self.det_keep, self.det_anchor, self.det_count, self.cand_count
 
     def check_status(self):
+        """Raises if a batch since the last check overflowed the slab or `max_det`; the status word is sticky on the
+        device (kernels only OR into it), so it is cleared here once it has been reported."""
         st = int(self.status.item())
+        if st:
+            self.status.zero_()
         if st & 1:
             raise RuntimeError("candidate slab overflow: raise `capacity`")
         if st & 2:

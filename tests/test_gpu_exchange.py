@@ -68,61 +68,13 @@ def test_exchange_single_rank_slot_reuse():
         x.close()
 
 
-def _two_rank_worker(rank, world, port, q):
-    try:
-        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-        sys.path.insert(0, ROOT)
-        import torch.distributed as dist
-        from object_detectors_b200 import ops, synthetic as syn
-        from object_detectors_b200.distributed import PeerExchange, message_len
-        torch.cuda.set_device(rank)
-        dev = torch.device("cuda", rank)
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-        batch, img, c, max_det = 4, 416, 80, 128
-        heads = [torch.from_numpy(h).to(dev) for h in syn.yolo_heads(700 + rank, batch, img, c, syn.COCO_ANCHORS, "clustered")]
-        plan = ops.YoloPostprocess([h.shape[2] for h in heads], batch, syn.COCO_ANCHORS, img, c, True, 0.1, 0.6,
-                                   ops.NMS_MAJORITY, 2048, max_det, dev)
-        x = PeerExchange(batch, max_det, dev, slots=3)
-        st = torch.cuda.Stream(device=dev)
-        ok = True
-        for step in range(7):                       # > slots: receive slots are reused
-            hs = [h.roll(step, 0).contiguous() for h in heads]
-            plan(hs, None)
-            plan.check_status()
-            st.wait_stream(torch.cuda.current_stream(dev))
-            x.push(plan.det, plan.det_count, st)
-            x.wait(st)
-            got = x.read(step, st)
-            st.synchronize()
-            # independent witness: NCCL all-gather of the packed message
-            msg = ops.pack_detections(plan.det, plan.det_count)
-            truth = torch.empty((world, message_len(batch, max_det)), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(truth.view(-1), msg)
-            g, t = got.cpu().numpy().reshape(world, batch, -1), truth.cpu().numpy().reshape(world, batch, -1)
-            for r in range(world):
-                for i in range(batch):
-                    k = int(t[r, i, :1].view(np.int32)[0])
-                    ok &= int(g[r, i, :1].view(np.int32)[0]) == k and k > 0
-                    ok &= np.array_equal(g[r, i, 1:1 + 6 * k].view(np.int32), t[r, i, 1:1 + 6 * k].view(np.int32))
-        x.close()
-        dist.destroy_process_group()
-        q.put((rank, bool(ok), ""))
-    except Exception as e:      # pragma: no cover
-        import traceback
-        q.put((rank, False, traceback.format_exc()))
-
-
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
 def test_exchange_two_ranks_bit_exact():
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_two_rank_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    results = [q.get(timeout=300) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-    for rank, ok, err in results:
-        assert ok, f"rank {rank}: {err or 'gathered bytes differ from the NCCL all-gather'}"
+    """Two processes, one GPU each, launched with torch.distributed.run (tests/helpers/exchange_two_rank.py)."""
+    import subprocess
+    port = 29600 + (os.getpid() % 300)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "helpers", "exchange_two_rank.py")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert r.stdout.count("EXCHANGE_OK") == 2, r.stdout[-3000:]
