@@ -342,6 +342,23 @@ int b200_matcher(const float* quality, int32_t m, int32_t n, float high_thr, flo
                  void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * result emission (the step right after the path)
+ * ---------------------------------------------------------------------------------------- */
+
+/* yolo/procedures/test_one_epoch.py:41-66 + yolo/utilities/helper.py:16-24 for a whole batch in one kernel:
+ * det [B,max_det,6] / det_count [B] (b200_yolo_postprocess) -> packed records in image order,
+ *   records [sum K, 6] = x, y, w, h (pixels of the original image: coord / inp_dim * size), area = w*h, score
+ *   category [sum K]   = class_map[label] (COCO: the 80 -> 91 table) or label + 1 when class_map == NULL
+ *   image    [sum K]   = image_id of the owning image;   total[0] = sum K
+ * img_hw [B,2] = (height, width) of the original images, image_id [B] int64.  strict_reference != 0 reproduces the
+ * reference's list semantics: images without detections are dropped before the list is matched with `targets` by
+ * position, so the k-th non-empty image takes size and id of targets[k].  Outputs sized for B*max_det rows. */
+int b200_emit_results(const float* det, const int32_t* det_count, int32_t batch, int32_t max_det,
+                      const float* img_hw, const int64_t* image_id, float inp_dim, const int32_t* class_map,
+                      int32_t num_map, int32_t strict_reference, float* records, int32_t* category,
+                      int64_t* image, int32_t* total, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * the path's one exchange step: all-gather of the variable-length kept-detection lists
  * (replaces the per-rank pickle files + barrier of yolo/procedures/eval_results.py:12-31 /
  * yolo/main.py:102-105 and `utils.all_gather`, torchvision_models/detection/utils.py:75-115)

@@ -71,6 +71,7 @@ SIGNATURES = {
     "b200_boxcoder_decode": (C.c_int, [_p, _p, _i64, _i32, C.POINTER(C.c_float), _f32, _p, _p]),
     "b200_boxcoder_encode": (C.c_int, [_p, _p, _i64, C.POINTER(C.c_float), _p, _p]),
     "b200_matcher": (C.c_int, [_p, _i32, _i32, _f32, _f32, _i32, _p, _p, _sz, _p]),
+    "b200_emit_results": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _f32, _p, _i32, _i32, _p, _p, _p, _p, _p]),
     "b200_pack_detections": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),
     "b200_allgather_dets": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p]),
     "b200_exchange_create": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _PP]),

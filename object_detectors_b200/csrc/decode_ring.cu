@@ -231,10 +231,18 @@ k_decode_filter_ring(const __grid_constant__ RingParams q) {
             const size_t hw = (size_t)sc.hw;
             const float* base = sc.head + (size_t)ig.ba * (size_t)CH * hw + (size_t)ig.cell0;
             const int nr = min(R, CH - r0);
+            // A row copy starts at the 16 B aligned address below the row and ends at the aligned address above it.
+            // For the first row of the tensor that start lies before the buffer, for the last row the end lies behind
+            // it: those (at most two) rows are copied with ordinary loads instead, so that nothing outside the
+            // caller's buffer is ever touched.
+            const uintptr_t t_lo = reinterpret_cast<uintptr_t>(sc.head);
+            const uintptr_t t_hi = t_lo + (size_t)p.B * (size_t)p.A * (size_t)CH * hw * sizeof(float);
             unsigned bytes = 0;
             for (int r = lane; r < nr; r += 32) {
                 const uintptr_t addr = reinterpret_cast<uintptr_t>(base + (size_t)(r0 + r) * hw);
-                bytes += ((unsigned)(addr & 15u) + (unsigned)ncell * 4u + 15u) & ~15u;
+                const unsigned nb = ((unsigned)(addr & 15u) + (unsigned)ncell * 4u + 15u) & ~15u;
+                const uintptr_t lo = addr & ~(uintptr_t)15u;
+                if (lo >= t_lo && lo + nb <= t_hi) bytes += nb;
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(kFullMask, bytes, o);
@@ -244,10 +252,17 @@ k_decode_filter_ring(const __grid_constant__ RingParams q) {
             }
             __syncwarp();
             for (int r = lane; r < nr; r += 32) {
-                const uintptr_t addr = reinterpret_cast<uintptr_t>(base + (size_t)(r0 + r) * hw);
+                const float* row = base + (size_t)(r0 + r) * hw;
+                const uintptr_t addr = reinterpret_cast<uintptr_t>(row);
                 const unsigned nb = ((unsigned)(addr & 15u) + (unsigned)ncell * 4u + 15u) & ~15u;
-                bulk_g2s(dst0 + (unsigned)r * (row_stride_b(TC) * 4u), reinterpret_cast<const void*>(addr & ~(uintptr_t)15u),
-                         nb, bar, policy);
+                const uintptr_t lo = addr & ~(uintptr_t)15u;
+                if (lo >= t_lo && lo + nb <= t_hi) {
+                    bulk_g2s(dst0 + (unsigned)r * (row_stride_b(TC) * 4u), reinterpret_cast<const void*>(lo), nb, bar, policy);
+                } else {
+                    float* drow = reinterpret_cast<float*>(my_ring + (size_t)slot * q.stage_bytes) + r * row_stride_b(TC) +
+                                  (int)((addr & 15u) >> 2);
+                    for (int c = 0; c < ncell; ++c) drow[c] = ldg_stream_f32(row + c);
+                }
             }
         }
         i_chunk = i_chunk + 1 == q.chunks ? 0 : i_chunk + 1;

@@ -27,6 +27,33 @@ def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _first_cuda_tensor(obj):
+    if isinstance(obj, Tensor):
+        return obj if obj.is_cuda else None
+    if isinstance(obj, (list, tuple)):
+        for o in obj:
+            t = _first_cuda_tensor(o)
+            if t is not None:
+                return t
+    return None
+
+
+def _device_guard(fn):
+    """Runs ``fn`` with the device of its first CUDA tensor argument current: the library launches on the current
+    device's stream and never calls cudaSetDevice itself, so a tensor that lives on another GPU than the current one
+    must not be launched from here (one process per GPU is the supported layout, like the reference's mp.spawn)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = _first_cuda_tensor(list(args) + list(kwargs.values()))
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def _ptr(t: Optional[Tensor]) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
@@ -102,6 +129,7 @@ def _idf_arg(idf: Optional[Tensor], num_classes: int, device) -> Optional[Tensor
     return idf
 
 
+@_device_guard
 def yolo_decode_dense(heads, anchors, img_size, num_classes, idf=None, softmax=True) -> Tensor:
     """-> [B, N, 5+C]  (YOLOForw.forward inference branch)."""
     lib = _lib.load()
@@ -113,6 +141,7 @@ def yolo_decode_dense(heads, anchors, img_size, num_classes, idf=None, softmax=T
     return out
 
 
+@_device_guard
 def yolo_decode_filter(heads, anchors, img_size, num_classes, idf=None, softmax=True,
                        conf_thr: float = 0.1, capacity: Optional[int] = None):
     """-> dict(box [B,cap,4], score [B,cap], label [B,cap] i32, anchor [B,cap] i32, count [B] i32)."""
@@ -166,6 +195,9 @@ class YoloPostprocess:
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.dev)
 
     def __call__(self, heads: Sequence[Tensor], idf: Optional[Tensor] = None):
+        if self.dev.index is not None and self.dev.index != torch.cuda.current_device():
+            with torch.cuda.device(self.dev):
+                return self.__call__(heads, idf)
         for h, shp in zip(heads, self.head_shapes):
             if tuple(h.shape) != shp or not h.is_cuda or h.dtype != torch.float32 or not h.is_contiguous():
                 raise RuntimeError(f"head tensor {tuple(h.shape)} does not match the plan {shp} "
@@ -209,6 +241,7 @@ class YoloPostprocess:
             raise RuntimeError("more detections than `max_det`")
 
 
+@_device_guard
 def yolo_postprocess(heads, anchors, img_size, num_classes, idf=None, softmax=True, conf_thr=0.1,
                      nms_thr=0.6, nms_mode=NMS_MAJORITY, capacity=None, max_det=None):
     hs, lay, arr, n = _heads_args(heads, anchors, img_size, num_classes, softmax)
@@ -252,6 +285,7 @@ def yolo_postprocess_host(heads_host: Sequence[Tensor], anchors, img_size, num_c
 
 
 # ---------------------------------------------------------------------------------------- NMS
+@_device_guard
 def nms_segments(boxes: Tensor, scores: Tensor, labels: Optional[Tensor], seg_offsets: Tensor,
                  iou_thr: float, mode: int, max_segment: int = 0):
     """Batched NMS.  -> (keep int64 [T], keep_count int32 [S], labels_out int32 [T]).
@@ -279,6 +313,7 @@ def nms_segments(boxes: Tensor, scores: Tensor, labels: Optional[Tensor], seg_of
 
 
 # ---------------------------------------------------------------------------------------- IoU
+@_device_guard
 def box_iou(b1: Tensor, b2: Tensor, kind: int = IOU, xcycwh: bool = False) -> Tensor:
     lib = _lib.load()
     b1 = _need_cuda(b1, "boxes1", torch.float32)
@@ -294,6 +329,7 @@ def box_iou(b1: Tensor, b2: Tensor, kind: int = IOU, xcycwh: bool = False) -> Te
     return out
 
 
+@_device_guard
 def box_iou_paired(b1: Tensor, b2: Tensor, kind: int = IOU, xcycwh: bool = False) -> Tensor:
     lib = _lib.load()
     b1 = _need_cuda(b1, "boxes1", torch.float32)
@@ -345,6 +381,7 @@ def box_iou_paired_autograd(b1: Tensor, b2: Tensor, kind: int = IOU, xcycwh: boo
     return _PairedIoU.apply(b1, b2, int(kind), bool(xcycwh))
 
 
+@_device_guard
 def iou_match(gt: Tensor, gt_count: Tensor, anchors: Tensor, kind: int = GIOU, ignore_thr: float = 0.5):
     """gt [B, Mmax, 4] rel xc,yc,w,h; gt_count [B] i32; anchors [N,4] (cxypwh).
     -> best_anchor int64 [B, Mmax], noobj bool [B, N]."""
@@ -366,6 +403,7 @@ def iou_match(gt: Tensor, gt_count: Tensor, anchors: Tensor, kind: int = GIOU, i
 
 
 # ---------------------------------------------------------------------------------------- RPN
+@_device_guard
 def rpn_filter(objectness: Tensor, deltas: Tensor, anchors: Tensor, level_sizes: Sequence[int],
                image_hw: Tensor, pre_nms_top_n: int, post_nms_top_n: int, nms_thr: float = 0.7,
                score_thr: float = 0.0, min_size: float = 1e-3, nms_mode: int = NMS_TV_CLASS):
@@ -393,6 +431,7 @@ def rpn_filter(objectness: Tensor, deltas: Tensor, anchors: Tensor, level_sizes:
     return boxes, scores, index, count
 
 
+@_device_guard
 def rpn_filter_proposals(objectness: Tensor, proposals: Tensor, level_sizes: Sequence[int], image_hw: Tensor,
                          pre_nms_top_n: int, post_nms_top_n: int, nms_thr: float = 0.7, score_thr: float = 0.0,
                          min_size: float = 1e-3, nms_mode: int = NMS_TV_CLASS):
@@ -420,6 +459,7 @@ def rpn_filter_proposals(objectness: Tensor, proposals: Tensor, level_sizes: Seq
 
 
 # ------------------------------------------------------------------------------- element-wise
+@_device_guard
 def abs_coord(box: Tensor) -> Tensor:
     """[..., 4] xc,yc,w,h -> x1,y1,x2,y2 (helper.get_abs_coord)."""
     lib = _lib.load()
@@ -431,6 +471,7 @@ def abs_coord(box: Tensor) -> Tensor:
     return out
 
 
+@_device_guard
 def boxcoder_decode(rel_codes: Tensor, boxes: Tensor, weights=(1.0, 1.0, 1.0, 1.0),
                     xform_clip: float = 4.135166556742356) -> Tensor:
     """rel_codes [n, 4k], boxes [n,4] -> [n, 4k] (BoxCoder.decode_single)."""
@@ -450,6 +491,7 @@ def boxcoder_decode(rel_codes: Tensor, boxes: Tensor, weights=(1.0, 1.0, 1.0, 1.
     return out
 
 
+@_device_guard
 def boxcoder_encode(reference_boxes: Tensor, proposals: Tensor, weights=(1.0, 1.0, 1.0, 1.0)) -> Tensor:
     """reference_boxes [n,4], proposals [n,4] -> regression targets [n,4] (BoxCoder.encode_single)."""
     lib = _lib.load()
@@ -468,6 +510,7 @@ def boxcoder_encode(reference_boxes: Tensor, proposals: Tensor, weights=(1.0, 1.
     return out
 
 
+@_device_guard
 def matcher(quality: Tensor, high: float, low: float, allow_low_quality: bool = False) -> Tensor:
     """[M,N] quality -> int64 [N] matches (Matcher.__call__)."""
     lib = _lib.load()
@@ -481,6 +524,7 @@ def matcher(quality: Tensor, high: float, low: float, allow_low_quality: bool = 
     return matches
 
 
+@_device_guard
 def yolo_legacy_decode(head: Tensor, anchors_px, num_classes: int, img_size) -> Tensor:
     """One head of the legacy YOLOLoss layer (yolo/nets/yolo_loss.py:34-105, inference branch):
     [B, A*(5+C), H, W] -> [B, A*H*W, 5+C], rows ordered (a, h, w)."""
@@ -508,6 +552,7 @@ ROI_SOFTMAX, ROI_GOMBIT, ROI_SIGMOID = 0, 1, 2
 ROI_DEFAULT_CAPACITY = 16384
 
 
+@_device_guard
 def roi_postprocess(class_logits: Tensor, box_regression: Tensor, proposals: Sequence[Tensor], image_shapes,
                     tfidf: Optional[Tensor] = None, activation: int = ROI_SOFTMAX,
                     weights=(10.0, 10.0, 5.0, 5.0), xform_clip: float = 4.135166556742356,
@@ -546,6 +591,32 @@ def roi_postprocess(class_logits: Tensor, box_regression: Tensor, proposals: Seq
     return det, keep, dcnt, ccnt, status
 
 
+@_device_guard
+def emit_results(det: Tensor, det_count: Tensor, img_hw: Tensor, image_id: Tensor, inp_dim: float,
+                 class_map: Optional[Tensor] = None, strict_reference: bool = True):
+    """b200_emit_results: packed evaluation records of a whole batch.  -> (records [B*max_det, 6] fp32,
+    category [B*max_det] i32, image [B*max_det] i64, total [1] i32); only the first ``total`` rows are defined."""
+    lib = _lib.load()
+    det = _need_cuda(det, "det", torch.float32)
+    det_count = _need_cuda(det_count, "det_count", torch.int32)
+    img_hw = _need_cuda(img_hw, "img_hw", torch.float32)
+    image_id = _need_cuda(image_id, "image_id", torch.int64)
+    b, max_det = det.shape[0], det.shape[1]
+    dev = det.device
+    rec = torch.empty((b * max_det, 6), dtype=torch.float32, device=dev)
+    cat = torch.empty((b * max_det,), dtype=torch.int32, device=dev)
+    img = torch.empty((b * max_det,), dtype=torch.int64, device=dev)
+    total = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if class_map is not None:
+        class_map = _need_cuda(class_map, "class_map", torch.int32)
+    _lib.check(lib.b200_emit_results(_ptr(det), _ptr(det_count), b, max_det, _ptr(img_hw), _ptr(image_id),
+                                     float(np.float32(inp_dim)), _ptr(class_map), 0 if class_map is None else class_map.numel(),
+                                     int(bool(strict_reference)), _ptr(rec), _ptr(cat), _ptr(img), _ptr(total), _stream()),
+               "b200_emit_results")
+    return rec, cat, img, total
+
+
+@_device_guard
 def pack_detections(det: Tensor, det_count: Tensor) -> Tensor:
     lib = _lib.load()
     b, max_det = det.shape[0], det.shape[1]

@@ -69,6 +69,7 @@ class YOLOForw(nn.Module):
                 self.idf_logits = self.idf_logits / torch.norm(self.idf_logits, p=self.tfidf_norm)   # :63-67
             self.idf_logits = self.idf_logits.to(self.device)
         self._table_cache = {}
+        self._plans = {}
 
     # ---------------------------------------------------------------------------------- inference
     def forward(self, input, targets=None):
@@ -83,17 +84,41 @@ class YOLOForw(nn.Module):
     def postprocess(self, input, conf_thr: float = 0.1, nms_thr: float = 0.6, nms_mode: int = ops.NMS_MAJORITY,
                     capacity: Optional[int] = None, max_det: Optional[int] = None):
         """Fused decode -> xyxy -> score filter -> NMS (what test_one_epoch.py:22-36 computes).
-        Retries once with the worst-case capacity if the candidate slab overflows."""
-        heads = [t.to(self.device, non_blocking=True).float() for t in input]
-        try:
-            return ops.yolo_postprocess(heads, self.anchors, self.img_size, self.num_classes, self.idf_logits,
-                                        self.softmax, conf_thr, nms_thr, nms_mode, capacity, max_det)
-        except RuntimeError as e:
-            if "overflow" not in str(e) and "max_det" not in str(e):
-                raise
-            n = sum(h.shape[2] * h.shape[3] * len(self.anchors[0]) for h in heads)
-            return ops.yolo_postprocess(heads, self.anchors, self.img_size, self.num_classes, self.idf_logits,
-                                        self.softmax, conf_thr, nms_thr, nms_mode, n, n)
+
+        The plan (outputs + workspace) is cached per (grids, batch, capacity, ...) on the module, so a steady stream of
+        batches allocates nothing.  If the candidate slab or ``max_det`` overflows, the call is repeated once with
+        exactly what the batch needs -- the kernels report the TRUE per-image candidate counts -- rounded up to a
+        multiple of 256, not with the worst case N (whose NMS scratch grows with capacity^2 / 8 bytes per image)."""
+        heads = [t.to(self.device, non_blocking=True).float().contiguous() for t in input]
+        grids = tuple(int(h.shape[2]) for h in heads)
+        batch = int(heads[0].shape[0])
+        n = sum(g * g * len(self.anchors[0]) for g in grids)
+
+        def plan_for(cap, md):
+            key = (grids, batch, cap, md, float(conf_thr), float(nms_thr), int(nms_mode), float(self.img_size))
+            plan = self._plans.get(key)
+            if plan is None:
+                if len(self._plans) >= 4:                 # a module sees few distinct shapes; do not hoard workspaces
+                    self._plans.pop(next(iter(self._plans)))
+                plan = ops.YoloPostprocess(list(grids), batch, self.anchors, self.img_size, self.num_classes, self.softmax,
+                                           conf_thr, nms_thr, nms_mode, cap, md, self.device)
+                self._plans[key] = plan
+            return plan
+
+        cap = int(capacity or min(n, ops.DEFAULT_CAPACITY))
+        md = int(max_det or cap)
+        plan = plan_for(cap, md)
+        out = plan(heads, self.idf_logits)
+        st = int(plan.status.item())
+        if st:
+            plan.status.zero_()
+            need = int(plan.cand_count.max().item())
+            cap = min(n, max(cap, -(-need // 256) * 256))
+            md = cap if (st & 2) or max_det is None else md
+            plan = plan_for(cap, md)
+            out = plan(heads, self.idf_logits)
+            plan.check_status()
+        return out
 
     # ---------------------------------------------------------------------------- target assignment
     def grid_table(self, grid_sizes):

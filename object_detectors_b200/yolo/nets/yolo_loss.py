@@ -39,7 +39,8 @@ class YOLOLoss(nn.Module):
         """Anchor-shape matching of yolo_loss.py:107-161, same return tuple (mask, noobj_mask, tx, ty, tw, th, tconf,
         tcls); ``anchors`` are the head's scaled anchors.  The reference loops over images and ground-truth boxes; here
         every ground-truth box of the batch goes through ONE [M, A] shape-IoU call and the dense target tensors are
-        filled by batched scatters (duplicate cells resolve like the reference's index assignments: last write)."""
+        filled by batched scatters (cells shared by several boxes resolve like the reference's index assignments: the last
+        box writes the regression targets)."""
         bs, na, dev = len(targets), len(anchors), self.device
         dense = lambda *tail: torch.zeros((bs, na, in_h, in_w) + tail, device=dev)      # noqa: E731
         mask, noobj_mask = dense(), torch.ones((bs, na, in_h, in_w), device=dev)
@@ -61,13 +62,20 @@ class YOLOLoss(nn.Module):
         m_ign, a_ign = torch.nonzero(shape_iou > ignore_threshold, as_tuple=True)
         noobj_mask[img[m_ign], a_ign, row[m_ign], col[m_ign]] = 0          # :143-144
         best = shape_iou.max(dim=1)[1]                                     # first maximum (:146)
-        at = (img, best, row, col)
-        mask[at] = 1
-        noobj_mask[at] = 0
-        tx[at] = gx - col
-        ty[at] = gy - row
-        tw[at] = torch.log(g[:, 2] / anc[best, 0] + 1e-16)
-        th[at] = torch.log(g[:, 3] / anc[best, 1] + 1e-16)
-        tconf[at] = 1
-        tcls[img, best, row, col, cls] = 1
+        mask[img, best, row, col] = 1
+        noobj_mask[img, best, row, col] = 0
+        tconf[img, best, row, col] = 1
+        tcls[img, best, row, col, cls] = 1                                 # one-hot bits accumulate over shared cells
+        # Several GT boxes may share a cell; the reference's index assignment (:150-155) keeps the LAST one.  A scatter
+        # with duplicate indices is unordered on the GPU, so only the last GT box of every cell writes its regression
+        # targets.
+        lin = ((img * na + best) * in_h + row) * in_w + col
+        order = torch.arange(lin.numel(), device=dev)
+        last = torch.full((bs * na * in_h * in_w,), -1, dtype=torch.long, device=dev).scatter_reduce_(0, lin, order, "amax")
+        w = last[lin] == order
+        at = (img[w], best[w], row[w], col[w])
+        tx[at] = (gx - col)[w]
+        ty[at] = (gy - row)[w]
+        tw[at] = torch.log(g[w, 2] / anc[best[w], 0] + 1e-16)
+        th[at] = torch.log(g[w, 3] / anc[best[w], 1] + 1e-16)
         return mask, noobj_mask, tx, ty, tw, th, tconf, tcls

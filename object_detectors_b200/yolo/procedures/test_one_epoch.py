@@ -4,7 +4,7 @@
 Lines 22-36 of the reference (decode, xyxy, score, mask, per-image gather, nms_majority) are one
 fused call; the result emission (reference :41-66: rescale to the original image, 80->91 class ids,
 xywh + area) is done for the whole batch at once with a single device->host transfer instead of
-several ``.tolist()`` round trips per image.
+several ``.tolist()`` round trips per image: one kernel (``b200_emit_results``) writes packed records.
 
 Reference behaviours kept on purpose:
   * ``cfg.yolo.inf_iou_threshold`` is read but the threshold actually used is nms_majority's default
@@ -18,34 +18,33 @@ from __future__ import annotations
 
 import torch
 
+from ... import ops
 from ..utilities import helper
 
 NMS_IOU = 0.6   # helper.nms_majority's default, the value the reference really runs with
 
 
+_map_cache = {}
+
+
 def _emit(det, det_count, targets, inp_dim, dset_name, strict_reference):
-    counts = det_count.tolist()                                   # the one sync of the batch
-    kept_images = [b for b, k in enumerate(counts) if k > 0]
-    if not kept_images:
-        return []
+    """Reference :41-66 for the whole batch: ONE kernel (b200_emit_results) writes packed records, one device->host
+    transfer brings them over."""
     dev = det.device
-    rows = torch.cat([det[b, :counts[b]] for b in kept_images], dim=0)                     # [sumK, 6]
-    # position in the filtered list (reference) or true image index
-    owner_of = {b: (i if strict_reference else b) for i, b in enumerate(kept_images)}
-    owner = torch.cat([torch.full((counts[b],), owner_of[b], dtype=torch.long, device=dev) for b in kept_images])
-    size_hw = torch.stack([t["img_size"].to(dev, torch.float32) for t in targets])         # [B, 2] (h, w)
-    image_ids = torch.stack([t["image_id"].reshape(()).to(dev) for t in targets])
-    sw, sh = size_hw[owner, 1], size_hw[owner, 0]
-    x1 = rows[:, 0] / inp_dim * sw
-    y1 = rows[:, 1] / inp_dim * sh
-    x2 = rows[:, 2] / inp_dim * sw
-    y2 = rows[:, 3] / inp_dim * sh
-    w, h = x2 - x1, y2 - y1
-    cls = rows[:, 5].long()
-    cat = helper.torch80_to_91(cls) if dset_name == "coco" else cls + 1
-    packed = torch.stack((x1, y1, w, h, w * h, rows[:, 4]), dim=1).cpu().tolist()
-    cat = cat.cpu().tolist()
-    ids = image_ids[owner].cpu().tolist()
+    size_hw = torch.stack([t["img_size"].to(dev, torch.float32).reshape(2) for t in targets])     # [B, 2] (h, w)
+    image_ids = torch.stack([t["image_id"].reshape(()).to(dev, torch.int64) for t in targets])
+    cmap = None
+    if dset_name == "coco":
+        cmap = _map_cache.get(dev)
+        if cmap is None:
+            cmap = _map_cache[dev] = torch.tensor(helper._COCO91, dtype=torch.int32, device=dev)
+    rec, cat, img, total = ops.emit_results(det, det_count, size_hw, image_ids, inp_dim, cmap, strict_reference)
+    n = int(total.item())                                         # the one sync of the batch
+    if n == 0:
+        return []
+    packed = rec[:n].cpu().tolist()
+    cat = cat[:n].cpu().tolist()
+    ids = img[:n].cpu().tolist()
     return [{"bbox": p[:4], "area": p[4], "category_id": c, "score": p[5], "image_id": i}
             for p, c, i in zip(packed, cat, ids)]
 

@@ -4,6 +4,7 @@ reference under /root/reference is run here, in the build container, on seeded s
 outputs are committed).
 
   legacy_yolo_loss.npz : YOLOLoss.forward(input) of yolo/nets/yolo_loss.py (inference branch), two heads
+  legacy_get_target.npz: YOLOLoss.get_target of yolo/nets/yolo_loss.py:107-161 (mask, noobj_mask, tx, ty, tw, th, tconf, tcls)
   roi_postprocess.npz  : RoIHeads.postprocess_detections of torchvision_models/tvision/roi_heads.py for the three
                          activations (ce / gombit / sigmoid), tfidf on, COCO-91 shaped head
 
@@ -48,6 +49,27 @@ def legacy():
     np.savez_compressed(os.path.join(HERE, "legacy_yolo_loss.npz"), **pack)
 
 
+def legacy_get_target():
+    """The reference's anchor-shape matching on seeded ground truth (two heads, incl. duplicate cells)."""
+    mg._install()
+    from nets import yolo_loss
+    yolo_loss.torch = mg._TorchProxy()
+    pack = {}
+    for tag, (grid, head_idx, img, seed, bsz, max_gt) in {"h26": (26, 1, 416, 33, 2, 12), "h19": (19, 0, 608, 34, 3, 40)}.items():
+        cfg = dict(anchors=[[list(a) for a in s] for s in syn.COCO_ANCHORS], classes=80, img_size=img,
+                   ignore_threshold=0.5, lambda_xy=1, lambda_wh=1, lambda_conf=1, lambda_no_conf=1, lambda_cls=1)
+        layer = yolo_loss.YOLOLoss(cfg, head_idx)
+        targets = [{k: torch.from_numpy(v) for k, v in t.items()} for t in syn.gt_targets(seed, bsz, 80, max_gt=max_gt)]
+        stride = img / grid
+        scaled = [(a_w / stride, a_h / stride) for a_w, a_h in syn.COCO_ANCHORS[head_idx]]
+        out = layer.get_target(targets, scaled, grid, grid, 0.5)
+        for name, t in zip(("mask", "noobj", "tx", "ty", "tw", "th", "tconf"), out[:7]):
+            pack[f"{tag}_{name}"] = t.numpy()
+        pack[f"{tag}_tcls_idx"] = torch.nonzero(out[7]).numpy().astype(np.int32)      # one-hot tensor, stored sparse
+        pack[f"{tag}_args"] = np.array([grid, head_idx, img, seed, bsz, max_gt])
+    np.savez_compressed(os.path.join(HERE, "legacy_get_target.npz"), **pack)
+
+
 def roi():
     sys.path.insert(0, os.path.join(REF, "torchvision_models"))
     from tvision import roi_heads as ref_roi
@@ -77,6 +99,7 @@ def roi():
 
 if __name__ == "__main__":
     legacy()
+    legacy_get_target()
     roi()
-    for f in ("legacy_yolo_loss.npz", "roi_postprocess.npz"):
+    for f in ("legacy_yolo_loss.npz", "legacy_get_target.npz", "roi_postprocess.npz"):
         print(f"  {f:32s} {os.path.getsize(os.path.join(HERE, f)):>9d} B")

@@ -377,3 +377,64 @@ def test_boxcoder_encode_matches_oracle():
     parts = coder.encode([ref[:1000].cuda(), ref[1000:].cuda()], [prop[:1000].cuda(), prop[1000:].cuda()])
     assert [p.shape[0] for p in parts] == [1000, 2000]
     np.testing.assert_array_equal(torch.cat(parts).cpu().numpy(), got)
+
+
+def test_emit_results_kernel_bit_exact():
+    """b200_emit_results against the reference's arithmetic (test_one_epoch.py:41-66) in numpy fp32, operation by
+    operation: x / inp_dim * size, w = x2 - x1, area = w * h; COCO 80 -> 91 ids; empty images shift the owner."""
+    from object_detectors_b200 import ops
+    g = np.random.default_rng(9)
+    b, max_det, inp = 7, 33, np.float32(608)
+    det = (g.random((b, max_det, 6)) * 600).astype(np.float32)
+    det[..., 5] = g.integers(0, 80, size=(b, max_det)).astype(np.float32)
+    cnt = g.integers(0, max_det + 1, size=(b,)).astype(np.int32)
+    cnt[2] = 0; cnt[5] = 0; cnt[0] = max_det
+    hw = np.stack([g.integers(300, 900, size=b), g.integers(300, 900, size=b)], 1).astype(np.float32)
+    ids = (np.arange(b) * 7 + 100000000000).astype(np.int64)
+    coco91 = np.array([c for c in range(1, 91) if c not in (12, 26, 29, 30, 45, 66, 68, 69, 71, 83)], np.int32)
+    for strict in (True, False):
+        for cmap in (coco91, None):
+            rec, cat, img, total = ops.emit_results(torch.from_numpy(det).cuda(), torch.from_numpy(cnt).cuda(),
+                                                    torch.from_numpy(hw).cuda(), torch.from_numpy(ids).cuda(), float(inp),
+                                                    None if cmap is None else torch.from_numpy(cmap).cuda(), strict)
+            n = int(total.item())
+            assert n == int(cnt.sum())
+            want_rec, want_cat, want_img = [], [], []
+            owner = 0
+            for i in range(b):
+                if cnt[i] == 0:
+                    continue
+                o = owner if strict else i
+                owner += 1
+                d = det[i, :cnt[i]]
+                x1 = d[:, 0] / inp * hw[o, 1]; y1 = d[:, 1] / inp * hw[o, 0]
+                x2 = d[:, 2] / inp * hw[o, 1]; y2 = d[:, 3] / inp * hw[o, 0]
+                w, h = x2 - x1, y2 - y1
+                want_rec.append(np.stack([x1, y1, w, h, w * h, d[:, 4]], 1))
+                lab = d[:, 5].astype(np.int64)
+                want_cat.append(cmap[lab] if cmap is not None else (lab + 1).astype(np.int32))
+                want_img.append(np.full(cnt[i], ids[o]))
+            np.testing.assert_array_equal(rec[:n].cpu().numpy(), np.concatenate(want_rec).astype(np.float32))
+            np.testing.assert_array_equal(cat[:n].cpu().numpy(), np.concatenate(want_cat))
+            np.testing.assert_array_equal(img[:n].cpu().numpy(), np.concatenate(want_img))
+
+
+def test_yoloforw_postprocess_retries_with_the_true_candidate_count():
+    """A slab that is too small is reported, never silent, and the drop-in repeats the call with what the batch needs
+    (the kernels return the true per-image candidate counts) -- same detections as a roomy call; plans are cached."""
+    from object_detectors_b200.yolo.nets.yolo_forw import YOLOForw
+    cfg = _cfg(416, 80, syn.COCO_ANCHORS, "coco", 1, [0, 0])
+    yolo = YOLOForw(cfg, idf_logits=_idf("coco"))
+    heads = [torch.from_numpy(h).cuda() for h in syn.yolo_heads(3, 2, 416, 80, syn.COCO_ANCHORS, "clustered")]
+    roomy = [t.clone() for t in yolo.postprocess(heads, capacity=4096)]
+    tight = yolo.postprocess(heads, capacity=32)
+    assert int(roomy[3].max()) > 32
+    k = roomy[3]
+    np.testing.assert_array_equal(tight[3].cpu().numpy(), k.cpu().numpy())
+    for i in range(2):
+        n = int(k[i])
+        np.testing.assert_array_equal(tight[0][i, :n].cpu().numpy(), roomy[0][i, :n].cpu().numpy())
+        np.testing.assert_array_equal(tight[1][i, :n].cpu().numpy(), roomy[1][i, :n].cpu().numpy())
+    n_plans = len(yolo._plans)
+    yolo.postprocess(heads, capacity=4096)
+    assert len(yolo._plans) == n_plans                  # served from the cache
