@@ -40,20 +40,56 @@ def timeit(fn, reps):
     return a.elapsed_time(b) / reps
 
 
+_c3_cache = {}
+
+
 def c3_lvis(reps, batch=8):
-    # LVIS-1203, 6 anchors / scale, 608: 219.8 MB per image -> batch 8 = 1.76 GB (C3 is quoted at b32)
-    heads = [torch.randn((batch, 6 * 1208, g, g), device="cuda") for g in (19, 38, 76)]
-    for h in heads:
-        h[:, 4::1208] = h[:, 4::1208] * 1.5 - 6.0
-    idf = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "idf_lvis_smooth.npy"))).cuda()
+    """LVIS-1203, 6 anchors / scale, 608: 219.8 MB per image (C3 is quoted at b32 = 7.0 GB).  Input: the survey's
+    CLUSTERED generator (8 distinct images, repeated to fill larger batches); the first two images are checked against
+    the CPU oracle (candidate counts, kept counts) before anything is timed."""
+    from oracle import cref, yolo_ref
+    if "heads" not in _c3_cache:
+        _c3_cache["np"] = syn.yolo_heads(3001, 8, 608, 1203, syn.LVIS_ANCHORS, "clustered")
+        _c3_cache["heads"] = [torch.from_numpy(h).cuda() for h in _c3_cache["np"]]
+    base = _c3_cache["heads"]
+    heads = [h if batch == 8 else torch.cat([h] * (batch // 8), 0).contiguous() for h in base] if batch >= 8 else [h[:batch].contiguous() for h in base]
+    idf_cpu = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "idf_lvis_smooth.npy")))
+    idf = idf_cpu.cuda()
     plan = ops.YoloPostprocess([19, 38, 76], batch, syn.LVIS_ANCHORS, 608, 1203, True, 0.1, 0.6, ops.NMS_MAJORITY,
-                               4096, 256, "cuda")
+                               4096, 512, "cuda")
+    plan(heads, idf)
+    plan.check_status()
+    cand = ops.yolo_decode_filter([h[:2].contiguous() for h in heads], syn.LVIS_ANCHORS, 608, 1203, idf, True, 0.1, capacity=4096)
+    for i in range(2):       # oracle check of the timed input (same images whatever the batch)
+        rec = yolo_ref.score_filter(yolo_ref.decode([torch.from_numpy(h[i:i + 1]) for h in _c3_cache["np"]], syn.LVIS_ANCHORS, 608,
+                                                    1203, idf_cpu, True), 0.1)[0]
+        n = rec["det6"].shape[0]
+        assert int(plan.cand_count[i]) == n, (int(plan.cand_count[i]), n)
+        g6 = torch.cat([cand["box"][i, :n], cand["score"][i, :n, None], cand["label"][i, :n, None].float()], 1).cpu().numpy()
+        ki, _ = cref.nms_majority(g6, 0.6, 1203)
+        assert int(plan.det_count[i]) == len(ki), (int(plan.det_count[i]), len(ki))
+    ms = timeit(lambda: plan(heads, idf), reps)
+    nbytes = sum(h.numel() * 4 for h in heads)
+    return {"config": "C3 YOLOv3-608 LVIS-1203 A=6 decode+filter+nms_majority (clustered generator, oracle-checked)",
+            "batch": batch, "ms": ms, "images_per_s": batch / ms * 1e3, "algorithmic_GBs": nbytes / ms / 1e6,
+            "hbm_frac": nbytes / ms / 1e6 / HBM_GBS, "candidates": int(plan.cand_count.sum()), "kept": int(plan.det_count.sum())}
+
+
+def c2_uniform(reps, batch=64):
+    """C2 on the UNIFORM ("stress") generator: ~10 % of the cells pass instead of ~3 % -- the same bytes, three times
+    the live cells and ~2300 candidates per image for the NMS.  Serial calls on one stream (no software pipeline)."""
+    base = [torch.from_numpy(h).cuda() for h in syn.yolo_heads(2001, 8, 608, 80, syn.COCO_ANCHORS, "uniform")]
+    heads = [torch.cat([h] * (batch // 8), 0).contiguous() for h in base]
+    idf = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "idf_coco_smooth.npy"))).cuda()
+    plan = ops.YoloPostprocess([19, 38, 76], batch, syn.COCO_ANCHORS, 608, 80, True, 0.1, 0.6, ops.NMS_MAJORITY, 4096, 4096, "cuda")
+    ms_dec = timeit(lambda: plan.decode(heads, idf), reps)
     ms = timeit(lambda: plan(heads, idf), reps)
     plan.check_status()
     nbytes = sum(h.numel() * 4 for h in heads)
-    return {"config": "C3 YOLOv3-608 LVIS-1203 A=6 decode+filter+nms_majority", "batch": batch, "ms": ms,
-            "images_per_s": batch / ms * 1e3, "algorithmic_GBs": nbytes / ms / 1e6, "hbm_frac": nbytes / ms / 1e6 / HBM_GBS,
-            "candidates": int(plan.cand_count.sum()), "kept": int(plan.det_count.sum())}
+    return {"config": "C2 YOLOv3-608 COCO b64, UNIFORM generator (stress: ~10 % live cells), serial decode+NMS", "batch": batch,
+            "ms": ms, "decode_ms": ms_dec, "images_per_s": batch / ms * 1e3, "decode_GBs": nbytes / ms_dec / 1e6,
+            "decode_hbm_frac": nbytes / ms_dec / 1e6 / HBM_GBS, "candidates": int(plan.cand_count.sum()),
+            "kept": int(plan.det_count.sum())}
 
 
 def c4_match(reps, batch=64, max_gt=100):
@@ -126,7 +162,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     args = ap.parse_args()
-    rows = [c3_lvis(max(args.reps // 4, 3)), c3_lvis(max(args.reps // 4, 3), batch=32)] + c4_match(args.reps) + c5_rpn(args.reps) + dense_decode(args.reps) + roi_heads(args.reps)
+    rows = [c3_lvis(max(args.reps // 4, 3)), c3_lvis(max(args.reps // 4, 3), batch=32), c2_uniform(args.reps)] + c4_match(args.reps) + c5_rpn(args.reps) + dense_decode(args.reps) + roi_heads(args.reps)
     for r in rows:
         print(json.dumps(r), flush=True)
 

@@ -83,6 +83,7 @@ def main():
     plan.nms()
     torch.cuda.synchronize()
     lib.b200_debug_set_resolve_prof(None)
+    lib.b200_debug_set_nms_path(-1)         # back to the library default
     pr = prof.cpu().numpy()
     pr = pr[pr[:, 0] > 0]
     t0 = pr[:, 0].min()

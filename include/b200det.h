@@ -175,8 +175,11 @@ int b200_debug_set_timeline(void* after_plan, void* after_pairs, void* after_res
 /* Profiling hook: device buffer int64[segments, 16] that the resolve kernel fills with clock64 stamps at its
  * phase boundaries (A stage, B fixed point, C vote, D order, E emit, end) + n and K; NULL to disable. */
 int b200_debug_set_resolve_prof(void* buf);
-/* Debug hook: 1 = run every NMS through the general three-launch path (plan / pairs / resolve), 0 (default) =
- * segments of <= 4096 boxes take the single-launch path (nms_fused.cu).  Both produce identical results. */
+/* NMS kernel path (process-wide): 1 = the general three-launch path (plan / pairs / resolve: spatially pruned tile
+ * pairs, small CTAs that co-reside with the streaming decode kernel), 0 = segments of <= 4096 boxes take the
+ * single-launch path (nms_fused.cu: no work queue, no cross-kernel dependencies), -1 (default) = by workload:
+ * candidate slabs of the YOLO post-process -> general, array inputs (nms / batched_nms, RPN, ROI heads) ->
+ * single-launch.  Both produce identical results (the tests run the NMS cases through both). */
 int b200_debug_set_nms_path(int general);
 /* Tuning hook: launch shape of the NMS resolve CTAs (threads: multiple of 32 in 64..1024, dynamic shared memory
  * in KB 16..200; out-of-range values keep the current setting).  Default 1024 threads, 112 KB. */
@@ -305,6 +308,15 @@ int b200_rpn_filter(const float* objectness, const float* deltas, const float* a
                     int32_t post_nms_top_n, double nms_thr, float score_thr, float min_size,
                     int32_t nms_mode, float* out_boxes, float* out_scores, int32_t* out_index, int32_t* out_count,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* RegionProposalNetwork._get_top_n_idx(objectness, num_anchors_per_level) (rpn.py:215-228): per image and level the
+ * indices of the min(pre_nms_top_n, n_l) largest raw objectness logits, in descending order (Tensor.topk order for
+ * tie-free input; equal logits: lower index first), offset by the level start and concatenated over the levels:
+ * out_index [B, sum_l min(pre_nms_top_n, n_l)] int64.  workspace: b200_rpn_top_n_idx_workspace_bytes, 256 B aligned. */
+size_t b200_rpn_top_n_idx_workspace_bytes(int32_t batch, int32_t total_anchors, int32_t num_levels, int32_t pre_nms_top_n);
+int b200_rpn_top_n_idx(const float* objectness, int32_t batch, int32_t total_anchors, const int32_t* level_sizes_host,
+                       int32_t num_levels, int32_t pre_nms_top_n, int64_t* out_index, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* Same filter on boxes that are already decoded: the exact signature-level replacement of
  * RegionProposalNetwork.filter_proposals(proposals, objectness, image_shapes, num_anchors_per_level)

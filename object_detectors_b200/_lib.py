@@ -65,6 +65,8 @@ SIGNATURES = {
     "b200_rpn_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "b200_rpn_filter": (C.c_int, [_p, _p, _p, _i32, _i32, C.POINTER(C.c_int32), _i32, _p, _i32, _i32, _f64,
                                   _f32, _f32, _i32, _p, _p, _p, _p, _p, _sz, _p]),
+    "b200_rpn_top_n_idx_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "b200_rpn_top_n_idx": (C.c_int, [_p, _i32, _i32, C.POINTER(C.c_int32), _i32, _i32, _p, _p, _sz, _p]),
     "b200_rpn_filter_proposals": (C.c_int, [_p, _p, _i32, _i32, C.POINTER(C.c_int32), _i32, _p, _i32, _i32, _f64,
                                             _f32, _f32, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "b200_abs_coord": (C.c_int, [_p, _i64, _p, _p]),

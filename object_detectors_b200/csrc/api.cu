@@ -32,6 +32,9 @@ int launch_rpn_filter(const float* objectness, const float* deltas, const float*
                       float* out_boxes, float* out_scores, int* out_index, int* out_count,
                       void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t rpn_workspace_bytes(int batch, int total, int num_levels, int pre_k);
+size_t rpn_topk_workspace_bytes(int batch, int total, int num_levels, int pre_k);
+int launch_rpn_topk(const float* objectness, int batch, int total, const int* level_sizes_host, int num_levels, int pre_k,
+                    long long* out_index, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 namespace {
 
@@ -165,7 +168,7 @@ int b200_debug_set_resolve(int threads, int smem_kb) {
     if (smem_kb >= 16 && smem_kb <= 200) b200::g_resolve_smem_kb = smem_kb;
     return B200_OK;
 }
-int b200_debug_set_nms_path(int general) { b200::g_nms_force_general = general ? 1 : 0; return B200_OK; }
+int b200_debug_set_nms_path(int general) { b200::g_nms_force_general = general < 0 ? -1 : (general ? 1 : 0); return B200_OK; }
 int b200_debug_set_resolve_prof(void* buf) { b200::g_resolve_prof = static_cast<long long*>(buf); return B200_OK; }
 static void* g_ev_decode_begin = nullptr;
 static void* g_ev_decode_end = nullptr;
@@ -512,6 +515,23 @@ int b200_rpn_filter(const float* objectness, const float* deltas, const float* a
                              image_hw, pre_nms_top_n, post_nms_top_n, nms_thr, score_thr, min_size, nms_mode,
                              out_boxes, out_scores, out_index, out_count, workspace, workspace_bytes,
                              static_cast<cudaStream_t>(stream));
+}
+
+size_t b200_rpn_top_n_idx_workspace_bytes(int32_t batch, int32_t total_anchors, int32_t num_levels, int32_t pre_nms_top_n) {
+    if (batch < 1 || total_anchors < 1 || num_levels < 1 || pre_nms_top_n < 1) return 0;
+    return rpn_topk_workspace_bytes(batch, total_anchors, num_levels, pre_nms_top_n);
+}
+
+int b200_rpn_top_n_idx(const float* objectness, int32_t batch, int32_t total_anchors, const int32_t* level_sizes_host,
+                       int32_t num_levels, int32_t pre_nms_top_n, int64_t* out_index, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+    if (!objectness || !level_sizes_host || !out_index || batch < 1 || total_anchors < 1 || num_levels < 1 ||
+        num_levels > 16 || pre_nms_top_n < 1)
+        return B200_ERR_INVALID;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return B200_ERR_WORKSPACE;
+    return launch_rpn_topk(objectness, batch, total_anchors, level_sizes_host, num_levels, pre_nms_top_n,
+                           reinterpret_cast<long long*>(out_index), workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int b200_rpn_filter_proposals(const float* objectness, const float* proposals, int32_t batch,

@@ -163,7 +163,13 @@ __device__ __forceinline__ float match_iou(const Box& p, float a1e, const Box& q
     return __fsub_rn(iou, __fdiv_rn(__fsub_rn(c_area, uni), c_area));
 }
 
-template <int KIND>
+// SKIP (IoU / GIoU with a positive ignore threshold): a pair whose boxes do not intersect has IoU == +0 and
+// GIoU <= 0, so it can neither clear the no-object flag (v < thr) nor beat a POSITIVE best value -- it is dropped
+// after the 6-instruction intersection test and only intersecting pairs (a few percent, coherent across a warp
+// because consecutive anchors are neighbouring cells) pay for the IEEE divisions.  A ground-truth box whose best
+// intersecting value is not positive (or that intersects no anchor) is redone exhaustively by k_iou_match_redo, so
+// the result is bit-identical to the exhaustive evaluation.
+template <int KIND, bool SKIP>
 __global__ void __launch_bounds__(kMatchThreads)
 k_iou_match(const float* __restrict__ gt, const int* __restrict__ gt_count, int max_gt,
             const float* __restrict__ anchors, int N, int kind, float ignore_thr,
@@ -206,12 +212,18 @@ k_iou_match(const float* __restrict__ gt, const int* __restrict__ gt_count, int 
 #pragma unroll
             for (int k = 0; k < kMatchItems; ++k) {
                 if (valid[k]) {
+                    if (SKIP) {
+                        const float w = __fsub_rn(fminf(g.x2, anc[k].x2), fmaxf(g.x1, anc[k].x1));
+                        const float h = __fsub_rn(fminf(g.y2, anc[k].y2), fmaxf(g.y1, anc[k].y1));
+                        if (w <= 0.f || h <= 0.f) continue;               // inter == 0 (NaN coordinates fall through)
+                    }
                     const float v = match_iou<KIND>(g, a1e, anc[k], a2[k], kind);
                     free_[k] = free_[k] && (v < ignore_thr);
                     const unsigned ok = orderable(v);
                     if (ok > bk) { bk = ok; bkk = k; }                    // ascending n: first max
                 }
             }
+            if (SKIP && !__any_sync(kFullMask, bkk >= 0)) continue;       // no lane of this warp met the box
             const unsigned bn = bkk >= 0 ? (unsigned)(n0 + bkk * kMatchThreads + tid) : 0xffffffffu;
             const unsigned wmax = __reduce_max_sync(kFullMask, bk);
             const unsigned wn = __reduce_min_sync(kFullMask, bk == wmax ? bn : 0xffffffffu);
@@ -226,6 +238,34 @@ k_iou_match(const float* __restrict__ gt, const int* __restrict__ gt_count, int 
     for (int k = 0; k < kMatchItems; ++k) {
         const int n = n0 + k * kMatchThreads + tid;
         if (valid[k]) noobj[(size_t)b * N + n] = free_[k] ? 1 : 0;
+    }
+}
+
+// Exhaustive redo of the ground-truth boxes the skipping kernel could not decide (best intersecting value <= +0, or
+// no intersecting anchor): one CTA per image walks its flagged boxes; normally there are none.
+__global__ void __launch_bounds__(256)
+k_iou_match_redo(const float* __restrict__ gt, const int* __restrict__ gt_count, int max_gt,
+                 const float* __restrict__ anchors, int N, int kind, unsigned long long* __restrict__ best_key) {
+    __shared__ unsigned long long s_best;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int M = min(gt_count[b], max_gt);
+    for (int m = 0; m < M; ++m) {
+        const unsigned long long cur = best_key[(size_t)b * max_gt + m];
+        if ((unsigned)(cur >> 32) > 0x80000000u) continue;              // a positive best value: decided
+        if (tid == 0) s_best = 0ull;
+        __syncthreads();
+        const Box g = load_box(gt + ((size_t)b * max_gt + m) * 4, 1);
+        unsigned bk = 0u, bn = 0xffffffffu;
+        for (int n = tid; n < N; n += 256) {
+            const unsigned ok = orderable(pair_iou(g, load_box(anchors + 4 * (size_t)n, 1), kind));
+            if (ok > bk) { bk = ok; bn = (unsigned)n; }
+        }
+        const unsigned wmax = __reduce_max_sync(kFullMask, bk);
+        const unsigned wn = __reduce_min_sync(kFullMask, bk == wmax ? bn : 0xffffffffu);
+        if (lane == 0 && wn != 0xffffffffu) atomicMax(&s_best, ((unsigned long long)wmax << 32) | (unsigned long long)(~wn));
+        __syncthreads();
+        if (tid == 0) best_key[(size_t)b * max_gt + m] = s_best;
+        __syncthreads();
     }
 }
 
@@ -266,12 +306,18 @@ int launch_iou_match(const float* gt, const int* gt_count, int batch, int max_gt
     if (cudaMemsetAsync(best_key, 0, sizeof(unsigned long long) * (size_t)batch * max_gt, stream) != cudaSuccess)
         return B200_ERR_CUDA;
     dim3 grid(cdiv(n, kMatchThreads * kMatchItems), batch);
-    if (kind == B200_IOU)
-        k_iou_match<0><<<grid, kMatchThreads, 0, stream>>>(gt, gt_count, max_gt, anchors, n, kind, ignore_thr, best_key, noobj);
+    const bool skip = ignore_thr > 0.f && (kind == B200_IOU || kind == B200_GIOU);
+    if (kind == B200_IOU && skip)
+        k_iou_match<0, true><<<grid, kMatchThreads, 0, stream>>>(gt, gt_count, max_gt, anchors, n, kind, ignore_thr, best_key, noobj);
+    else if (kind == B200_GIOU && skip)
+        k_iou_match<1, true><<<grid, kMatchThreads, 0, stream>>>(gt, gt_count, max_gt, anchors, n, kind, ignore_thr, best_key, noobj);
+    else if (kind == B200_IOU)
+        k_iou_match<0, false><<<grid, kMatchThreads, 0, stream>>>(gt, gt_count, max_gt, anchors, n, kind, ignore_thr, best_key, noobj);
     else if (kind == B200_GIOU)
-        k_iou_match<1><<<grid, kMatchThreads, 0, stream>>>(gt, gt_count, max_gt, anchors, n, kind, ignore_thr, best_key, noobj);
+        k_iou_match<1, false><<<grid, kMatchThreads, 0, stream>>>(gt, gt_count, max_gt, anchors, n, kind, ignore_thr, best_key, noobj);
     else
-        k_iou_match<-1><<<grid, kMatchThreads, 0, stream>>>(gt, gt_count, max_gt, anchors, n, kind, ignore_thr, best_key, noobj);
+        k_iou_match<-1, false><<<grid, kMatchThreads, 0, stream>>>(gt, gt_count, max_gt, anchors, n, kind, ignore_thr, best_key, noobj);
+    if (skip) k_iou_match_redo<<<batch, 256, 0, stream>>>(gt, gt_count, max_gt, anchors, n, kind, best_key);
     k_match_finish<<<batch, 128, 0, stream>>>(best_key, gt_count, max_gt, n, best_anchor, noobj);
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }

@@ -973,7 +973,7 @@ cudaEvent_t g_nms_timeline[3] = {nullptr, nullptr, nullptr};
 long long* g_resolve_prof = nullptr;
 
 long long g_batched_nms_auto_limit = 100000;
-int g_nms_force_general = 0;    // debug (b200_debug_set_nms_path): 1 = three-launch path even for small segments
+int g_nms_force_general = -1;   // b200_debug_set_nms_path: -1 (default) = by workload, 1 = three-launch path, 0 = single-launch path
 // launch shape of the resolve CTAs (b200_debug_set_resolve): 1024 threads at <= 32 registers and 112 KB leave room
 // for a decode CTA on the same SM; 112 KB stage every segment of up to ~1200 boxes in shared memory
 int g_resolve_threads = 1024;
@@ -993,7 +993,11 @@ int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
         k_nms_canon<<<num_segments, kCanonThreads, 0, stream>>>(P);
         return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
     }
-    P.force_general = g_nms_force_general;
+    // Default choice by workload: candidate slabs of the YOLO post-process run beside the streaming decode kernel of
+    // the next batch, where the three small-footprint kernels of the general path co-reside with it and its spatially
+    // pruned tile pairs do half the work; array inputs (torchvision nms / batched_nms, RPN levels, ROI heads) are
+    // stand-alone calls on boxes spread all over the image, where one launch without a work queue wins.
+    P.force_general = g_nms_force_general >= 0 ? g_nms_force_general : (P.from_slab ? 1 : 0);
     P.prof = g_resolve_prof;
     if (!P.force_general && nms_fused_eligible(P)) {
         const int rc = launch_nms_fused(P, num_segments, stream);

@@ -2,17 +2,27 @@
 // Replaces BoxCoder.decode_single + RegionProposalNetwork._get_top_n_idx / filter_proposals
 // (torchvision_models/tvision/_utils.py:186-223, rpn.py:215-280).
 //
-//  k_rpn_select : one CTA per (image, level).  8-bit MSB radix select over the level's raw
-//                 objectness logits (4 histogram passes, L2-resident after the first) finds the
-//                 k-th largest key; the selected <= k entries are sorted in shared memory
-//                 (score desc, index asc == Tensor.topk order for tie-free input) and only those
-//                 are decoded / clipped / filtered -- the reference decodes all 268 569 anchors
-//                 first (rpn.py:355).  Survivors are written in order at a fixed stride.
+//  k_rpn_select_cluster : a CLUSTER of 8 CTAs per (image, level).  Every CTA pulls its eighth of the level's raw
+//                 objectness logits into shared memory ONCE (<= 100 KB of order-preserving keys; level 0 of an
+//                 800 x 1344 image is 201 600 logits), so HBM is read exactly once; the 8-bit MSB radix select then
+//                 runs out of shared memory, the eight local histograms are summed into CTA 0's through distributed
+//                 shared memory and every CTA takes the same decision (3 cluster barriers per pass).  The selected
+//                 <= k entries are compacted into one global list, sorted by CTA 0 (score desc, index asc ==
+//                 Tensor.topk order for tie-free input) and only those are decoded / clipped / filtered -- the
+//                 reference decodes all 268 569 anchors first (rpn.py:355).  Survivors are written in order at a
+//                 fixed stride.  With `topk_out` the kernel stops after the sort and emits the index list of
+//                 RegionProposalNetwork._get_top_n_idx (rpn.py:215-228).
+//  k_rpn_select : fallback for levels that do not fit eight shared-memory slices (> 204 800 anchors): one CTA per
+//                 (image, level), four histogram passes over global memory.
 //  k_rpn_units  : (coordinate-trick strategy) the image's shift unit for its per-level segments (see below).
 //  NMS          : the shared per-segment kernel of nms.cu (segments = image x level for the
 //                 vanilla strategy, = image for the coordinate trick).
 //  k_rpn_finish : merges an image's kept lists by score and emits the first post_nms_top_n.
+#include <cooperative_groups.h>
+
 #include "nms.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace b200 {
 
@@ -41,101 +51,83 @@ struct RpnParams {
     int* keep_count;  // [B*L] or [B]
     int segs_per_img;
     float* out_boxes; float* out_scores; int* out_index; int* out_count;
+    long long* topk_out;   // [B, Ktot] or nullptr: emit the sorted top-k anchor indices and stop (_get_top_n_idx)
+    // sliced select
+    int level_slices[kMaxLevels], level_coff[kMaxLevels];   // slices per level, candidate offset of the level
+    int cand_stride;                  // candidates per image = sum_l slices_l * k_l (multi-slice levels only)
+    unsigned long long* cand;         // [B, cand_stride] (~key << 32 | index inside the level)
+    int* sel_counter;                 // [B * L] slice arrival counters (zeroed before the launch)
 };
 
+// ascending bitonic sort of key[0..P) in shared memory, P a power of two.  Steps with a partner distance below 64
+// stay inside aligned blocks of 64 keys and are done by one warp per block without CTA barriers.
 __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* key, int P) {
-    for (int k = 2; k <= P; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    if (P < 64) {
+        for (int k = 2; k <= P; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (P >> 1); t += blockDim.x) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int ixj = i | j;
+                    const unsigned long long a = key[i], b = key[ixj];
+                    if ((a > b) == ((i & k) == 0)) { key[i] = b; key[ixj] = a; }
+                }
+                __syncthreads();
+            }
+        return;
+    }
+    for (int base = warp * 64; base < P; base += nwarp * 64) {
+        unsigned long long* kk = key + base;
+        for (int k = 2; k <= 64; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const int i = ((lane & ~(j - 1)) << 1) | (lane & (j - 1));
+                const int ixj = i | j;
+                const unsigned long long a = kk[i], b = kk[ixj];
+                if ((a > b) == (((base + i) & k) == 0)) { kk[i] = b; kk[ixj] = a; }
+                __syncwarp();
+            }
+    }
+    __syncthreads();
+    for (int k = 128; k <= P; k <<= 1) {
+        for (int j = k >> 1; j >= 64; j >>= 1) {
+            for (int t = tid; t < (P >> 1); t += blockDim.x) {
                 const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const int ixj = i | j;
-                const bool asc = (i & k) == 0;
                 const unsigned long long a = key[i], b = key[ixj];
-                if ((a > b) == asc) { key[i] = b; key[ixj] = a; }
+                if ((a > b) == ((i & k) == 0)) { key[i] = b; key[ixj] = a; }
             }
             __syncthreads();
         }
+        for (int base = warp * 64; base < P; base += nwarp * 64) {
+            unsigned long long* kk = key + base;
+            const bool asc = (base & k) == 0;
+            for (int j = 32; j > 0; j >>= 1) {
+                const int i = ((lane & ~(j - 1)) << 1) | (lane & (j - 1));
+                const int ixj = i | j;
+                const unsigned long long a = kk[i], b = kk[ixj];
+                if ((a > b) == asc) { kk[i] = b; kk[ixj] = a; }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
 }
 
-__global__ void __launch_bounds__(kSelThreads, 1)
-k_rpn_select(const __grid_constant__ RpnParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem_raw);  // [pow2(k)]
-    __shared__ int hist[256];
-    __shared__ unsigned s_prefix, s_mask;
-    __shared__ int s_remaining, s_cnt, s_tie;
-    __shared__ int s_scan[kSelWarps];
-
-    const int l = blockIdx.x, b = blockIdx.y;
+// sorted selection -> (optional) index list, else decode / clip / filter in order.  `sel` holds `got` keys
+// (~orderable(score) << 32 | index inside the level) in shared memory, padded to Ppad.
+__device__ void rpn_finish_level(const RpnParams& P, int b, int l, unsigned long long* sel, int got, int Ppad, const float* src,
+                                 int* s_scan) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = P.level_n[l], k = P.level_k[l];
-    const float* src = P.obj + (size_t)b * P.total + P.level_off[l];
-    int Ppad = 1;
-    while (Ppad < k) Ppad <<= 1;
-
-    // ---- radix select: key of the k-th largest logit ------------------------------------------
-    if (tid == 0) { s_prefix = 0u; s_mask = 0u; s_remaining = k; s_cnt = 0; s_tie = 0; }
-    __syncthreads();
-    if (n > k) {
-        for (int pass = 3; pass >= 0; --pass) {
-            for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
-            __syncthreads();
-            const unsigned prefix = s_prefix, mask = s_mask;
-            const int shift = 8 * pass;
-            for (int i = tid; i < n; i += kSelThreads) {
-                const unsigned key = orderable(__ldg(src + i));
-                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
-            }
-            __syncthreads();
-            if (warp == 0) {
-                // bins 255 .. 0, 8 per lane (lane 0 owns the top bins); find the bin holding rank `remaining`
-                int local[8], sum = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { local[j] = hist[255 - (lane * 8 + j)]; sum += local[j]; }
-                int incl = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(kFullMask, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                int before = incl - sum;
-                const int rem = s_remaining;
-                if (before < rem && rem <= incl) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (before < rem && rem <= before + local[j]) {
-                            s_prefix = prefix | ((unsigned)(255 - (lane * 8 + j)) << shift);
-                            s_mask = mask | (255u << shift);
-                            s_remaining = rem - before;
-                        }
-                        before += local[j];
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    const unsigned T = s_prefix;           // key of the k-th largest (exact after 4 passes)
-    const int take_ties = s_remaining;     // how many entries equal to T are still needed
-    // ---- collect the selected entries --------------------------------------------------------
-    for (int i0 = 0; i0 < n; i0 += kSelThreads) {
-        const int i = i0 + tid;
-        if (i < n) {
-            const unsigned key = orderable(__ldg(src + i));
-            bool take = n <= k || key > T;
-            if (!take && key == T) take = atomicAdd(&s_tie, 1) < take_ties;
-            if (take) sel[atomicAdd(&s_cnt, 1)] = ((unsigned long long)(~key) << 32) | (unsigned)i;
-        }
-    }
-    __syncthreads();
-    const int got = s_cnt;  // == k
     for (int i = got + tid; i < Ppad; i += kSelThreads) sel[i] = ~0ull;
     __syncthreads();
     bitonic_sort_u64(sel, Ppad);
-
+    const size_t out0 = (size_t)b * P.Ktot + P.level_koff[l];
+    if (P.topk_out) {
+        for (int r = tid; r < got; r += kSelThreads) P.topk_out[out0 + r] = P.level_off[l] + (int)(unsigned)sel[r];
+        return;
+    }
     // ---- decode / clip / filter the selected anchors, keep order ------------------------------
     const float img_h = P.image_hw[2 * b], img_w = P.image_hw[2 * b + 1];
-    const size_t out0 = (size_t)b * P.Ktot + P.level_koff[l];
     int running = 0;
     for (int r0 = 0; r0 < got; r0 += kSelThreads) {
         const int r = r0 + tid;
@@ -191,44 +183,399 @@ k_rpn_select(const __grid_constant__ RpnParams P) {
     }
 }
 
-// merge the kept lists of an image by score, emit the first post_k (rpn.py:272-278)
+
+// ------------------------------------------------------------------------------------------ sliced select
+static constexpr int kSliceMax = 20480;       // logits one CTA holds in shared memory (80 KB of 32-bit keys)
+static constexpr int kNarrowMax = 3072;       // entries of the threshold bin refined out of a compact list (24 KB)
+
+struct SelShared {
+    int hist[256];
+    unsigned prefix, mask;
+    int remaining;
+    int c_out, c_mid, last;
+    int bin, above, in_bin;
+    int scan[kSelWarps];
+};
+
+// one histogram pass: entries of v[0..m) whose masked bits equal `prefix`, binned by byte `shift / 8`.
+// Float keys concentrate in a handful of exponent bins: lanes that hit the same bin are merged (match.any) into
+// ONE shared-memory atomic instead of up to 32 serialised ones.
+__device__ __forceinline__ void hist_pass(const unsigned* v, int m, unsigned prefix, unsigned mask, int shift, int* hist) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i - lane < m; i += kSelThreads) {
+        const unsigned key = i < m ? v[i] : 0u;
+        const bool in = i < m && (key & mask) == prefix;
+        const unsigned bin = in ? (key >> shift) & 255u : 256u;
+        const unsigned peers = __match_any_sync(kFullMask, bin);
+        if (in && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+    }
+}
+
+// warp 0: the bin (ascending) that holds rank `rem` (1-based) of the histogram; entries before it
+__device__ __forceinline__ void find_bin(const int* hist, int rem, int& bin, int& before_bin, int& in_bin) {
+    const int lane = threadIdx.x & 31;
+    int local[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { local[j] = hist[lane * 8 + j]; sum += local[j]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += u;
+    }
+    int before = incl - sum, fb = -1, fbefore = 0, fin = 0;
+    if (before < rem && rem <= incl) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (fb < 0 && rem <= before + local[j]) { fb = lane * 8 + j; fbefore = before; fin = local[j]; }
+            before += local[j];
+        }
+    }
+    const unsigned who = __ballot_sync(kFullMask, fb >= 0);
+    const int src = who ? __ffs(who) - 1 : 0;
+    bin = __shfl_sync(kFullMask, fb, src);
+    before_bin = __shfl_sync(kFullMask, fbefore, src);
+    in_bin = __shfl_sync(kFullMask, fin, src);
+}
+
+// Block-wide MSB radix select over v[0..m) in shared memory: the threshold T and the number of entries equal to T
+// that belong to the k SMALLEST values (smaller value = larger score: v = ~orderable(logit)).  m > k >= 1.
+// `prefix0` / `mask0` / `first_pass`: bytes already decided by the caller.
+__device__ void pick_smallest(const unsigned* v, int m, int k, SelShared& S, unsigned prefix0, unsigned mask0, int first_pass,
+                              unsigned& T, int& take_eq) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { S.prefix = prefix0; S.mask = mask0; S.remaining = k; }
+    __syncthreads();
+    for (int pass = first_pass; pass >= 0; --pass) {
+        if (tid < 256) S.hist[tid] = 0;
+        __syncthreads();
+        const unsigned prefix = S.prefix, mask = S.mask;
+        const int shift = 8 * pass;
+        hist_pass(v, m, prefix, mask, shift, S.hist);
+        __syncthreads();
+        if (warp == 0) {
+            int bin, before, in_bin;
+            find_bin(S.hist, S.remaining, bin, before, in_bin);
+            if (tid == 0) {
+                S.prefix = prefix | ((unsigned)bin << shift);
+                S.mask = mask | (255u << shift);
+                S.remaining -= before;
+            }
+        }
+        __syncthreads();
+    }
+    T = S.prefix;
+    take_eq = S.remaining;
+}
+
+// The min(k, cnt) smallest entries of vals[0..cnt) (shared memory) as (value << 32 | idx_of(i)) into out[] (any
+// order; equal values: lowest i first).  One histogram pass over everything finds the byte-3 bin of the k-th value;
+// one compaction pass sends the entries of better bins straight to out[] and the (few) entries of that bin to a
+// compact list, where the remaining three bytes are decided.  A bin too crowded for the list falls back to
+// histogram passes over the whole array.
+template <typename IdxOf>
+__device__ void select_block(const unsigned* vals, int cnt, int k, unsigned long long* out, IdxOf idx_of, SelShared& S,
+                             unsigned* nv, unsigned* ni) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (cnt <= k) {
+        for (int i = tid; i < cnt; i += kSelThreads) out[i] = ((unsigned long long)vals[i] << 32) | idx_of(i);
+        __syncthreads();
+        return;
+    }
+    if (tid < 256) S.hist[tid] = 0;
+    if (tid == 0) { S.c_out = 0; S.c_mid = 0; }
+    __syncthreads();
+    hist_pass(vals, cnt, 0u, 0u, 24, S.hist);
+    __syncthreads();
+    if (warp == 0) {
+        int bin, before, in_bin;
+        find_bin(S.hist, k, bin, before, in_bin);
+        if (tid == 0) { S.bin = bin; S.above = before; S.in_bin = in_bin; }
+    }
+    __syncthreads();
+    const unsigned b1 = (unsigned)S.bin;
+    const int above = S.above, in_bin = S.in_bin, need = k - above;      // 1 <= need <= in_bin
+    const bool narrow = in_bin <= kNarrowMax;
+    // warp-aggregated compaction: entries of better bins -> out[0..above), the threshold bin -> the compact list
+    for (int i = tid; i - lane < cnt; i += kSelThreads) {
+        const unsigned v = i < cnt ? vals[i] : ~0u;
+        const bool hi = i < cnt && (v >> 24) < b1, mid = narrow && i < cnt && (v >> 24) == b1;
+        const unsigned bh = __ballot_sync(kFullMask, hi), bm = __ballot_sync(kFullMask, mid);
+        int base_h = 0, base_m = 0;
+        if (lane == 0) {
+            if (bh) base_h = atomicAdd(&S.c_out, __popc(bh));
+            if (bm) base_m = atomicAdd(&S.c_mid, __popc(bm));
+        }
+        base_h = __shfl_sync(kFullMask, base_h, 0);
+        base_m = __shfl_sync(kFullMask, base_m, 0);
+        const unsigned lt = (1u << lane) - 1u;
+        if (hi) out[base_h + __popc(bh & lt)] = ((unsigned long long)v << 32) | idx_of(i);
+        if (mid) { const int p = base_m + __popc(bm & lt); nv[p] = v; ni[p] = (unsigned)i; }     // ascending i inside a warp
+    }
+    __syncthreads();
+    unsigned T;
+    int take_eq;
+    const unsigned* rv = narrow ? nv : vals;
+    const int rn = narrow ? in_bin : cnt;
+    if (narrow && in_bin == need) {
+        T = ~0u; take_eq = 0;                                   // the whole bin is selected
+        for (int p = tid; p < in_bin; p += kSelThreads) out[above + p] = ((unsigned long long)nv[p] << 32) | idx_of((int)ni[p]);
+        __syncthreads();
+        return;
+    }
+    pick_smallest(rv, rn, narrow ? need : k, S, narrow ? (b1 << 24) : 0u, narrow ? 0xff000000u : 0u, narrow ? 2 : 3, T, take_eq);
+    // entries below T inside the threshold bin, then the first take_eq entries equal to T in index order
+    if (tid == 0) S.c_mid = 0;
+    __syncthreads();
+    int lt_cnt = 0;
+    for (int p = tid; p < rn; p += kSelThreads) { const unsigned v = rv[p]; lt_cnt += (v >> 24) == b1 && v < T; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lt_cnt += __shfl_xor_sync(kFullMask, lt_cnt, o);
+    if (lane == 0 && lt_cnt) atomicAdd(&S.c_mid, lt_cnt);
+    __syncthreads();
+    const int lt_total = S.c_mid;                               // == need - take_eq
+    __syncthreads();
+    if (tid == 0) S.c_mid = 0;
+    __syncthreads();
+    for (int p = tid; p < rn; p += kSelThreads) {
+        const unsigned v = rv[p];
+        if ((v >> 24) == b1 && v < T)
+            out[above + atomicAdd(&S.c_mid, 1)] = ((unsigned long long)v << 32) | idx_of(narrow ? (int)ni[p] : p);
+    }
+    // ties at the threshold.  Usually every entry equal to T is taken (tie-free input: T itself): append them all.
+    if (tid == 0) S.c_out = 0;
+    __syncthreads();
+    int eq_cnt = 0;
+    for (int p = tid; p < rn; p += kSelThreads) eq_cnt += rv[p] == T;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) eq_cnt += __shfl_xor_sync(kFullMask, eq_cnt, o);
+    if (lane == 0 && eq_cnt) atomicAdd(&S.c_out, eq_cnt);
+    __syncthreads();
+    const int eq_total = S.c_out;
+    __syncthreads();
+    if (eq_total <= take_eq) {
+        if (tid == 0) S.c_out = 0;
+        __syncthreads();
+        for (int p = tid; p < rn; p += kSelThreads)
+            if (rv[p] == T)
+                out[above + lt_total + atomicAdd(&S.c_out, 1)] = ((unsigned long long)T << 32) | idx_of(narrow ? (int)ni[p] : p);
+    } else if (warp == 0) {
+        // more equal entries than places: the lowest indices win.  The compact list is ascending in i only inside
+        // each warp's chunk, so equal entries are ranked by index explicitly.
+        int taken = 0;
+        for (int base = 0; base < rn && taken < take_eq; base += 32) {
+            const int p = base + lane;
+            const bool is = p < rn && rv[p] == T;
+            const unsigned bal = __ballot_sync(kFullMask, is);
+            if (!narrow) {
+                const int pos = taken + __popc(bal & ((1u << lane) - 1u));
+                if (is && pos < take_eq) out[above + lt_total + pos] = ((unsigned long long)T << 32) | idx_of(p);
+            } else if (is) {
+                const unsigned mine = ni[p];
+                int rank = 0;
+                for (int q = 0; q < rn; ++q) rank += rv[q] == T && ni[q] < mine;
+                if (rank < take_eq) out[above + lt_total + rank] = ((unsigned long long)T << 32) | idx_of((int)mine);
+            }
+            taken += narrow ? 0 : __popc(bal);
+        }
+    }
+    __syncthreads();
+}
+
+// Level l of image b is cut into R_l = ceil(n_l / kSliceMax) slices, one CTA each.  A CTA reads its slice ONCE
+// (order-preserving keys into shared memory), selects its local top min(k, m) there -- a superset of its share of
+// the level's top k -- and appends them to the level's candidate list.  The CTA that arrives last at the level's
+// counter (nobody waits) selects the top k among the R_l * k candidates, sorts them and runs the level's decode /
+// clip / filter (or emits the index list).  Single-slice levels skip the candidate round trip.
+__global__ void __launch_bounds__(kSelThreads, 2)
+k_rpn_select_sliced(const __grid_constant__ RpnParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned* nv = reinterpret_cast<unsigned*>(smem_raw);                       // [kNarrowMax] compact list: values
+    unsigned* ni = nv + kNarrowMax;                                             // [kNarrowMax]               indices
+    unsigned* keys = ni + kNarrowMax;                                           // slice keys / candidate keys
+    unsigned char* after = reinterpret_cast<unsigned char*>(keys);
+    __shared__ SelShared S;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    int l = 0, r = blockIdx.x;
+    while (r >= P.level_slices[l]) { r -= P.level_slices[l]; ++l; }
+    const int R = P.level_slices[l];
+    const int n = P.level_n[l], k = P.level_k[l];
+    const float* src = P.obj + (size_t)b * P.total + P.level_off[l];
+    const int per = (((n + R - 1) / R) + 3) & ~3;
+    const int i0 = min(n, r * per), m = min(n, i0 + per) - i0;
+
+    // ---- the one read of the logits ---------------------------------------------------------------------------------
+    for (int i = tid; i < m; i += kSelThreads) keys[i] = ~orderable(ldg_stream_f32(src + i0 + i));
+    __syncthreads();
+
+    int got;
+    unsigned long long* sel;
+    if (R == 1) {
+        // the slice is the level: select straight into the sort buffer behind the keys
+        sel = reinterpret_cast<unsigned long long*>(after + (((size_t)m * 4 + 15) & ~(size_t)15));
+        select_block(keys, m, k, sel, [&](int i) { return (unsigned)(i0 + i); }, S, nv, ni);
+        got = min(k, m);
+    } else {
+        unsigned long long* cand = P.cand + ((size_t)b * P.cand_stride + P.level_coff[l]) + (size_t)r * k;
+        select_block(keys, m, k, cand, [&](int i) { return (unsigned)(i0 + i); }, S, nv, ni);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) S.last = atomicAdd(P.sel_counter + b * P.L + l, 1) == R - 1;
+        __syncthreads();
+        if (!S.last) return;
+        __threadfence();
+        // ---- last CTA of the level: top k of the R * k candidates (slice r' holds min(k, m_r') of them) ----------
+        const unsigned long long* all_cand = P.cand + ((size_t)b * P.cand_stride + P.level_coff[l]);
+        int total = 0;
+        for (int rr = 0; rr < R; ++rr) {
+            const int j0 = min(n, rr * per), mm = min(n, j0 + per) - j0;
+            const int c = min(k, mm);
+            for (int i = tid; i < c; i += kSelThreads) keys[total + i] = (unsigned)(__ldcg(all_cand + (size_t)rr * k + i) >> 32);
+            total += c;
+        }
+        __syncthreads();
+        sel = reinterpret_cast<unsigned long long*>(after + (((size_t)total * 4 + 15) & ~(size_t)15));
+        // candidate i of the concatenation lives in slice i / c_full; the slices are equally long except the last
+        const int c_full = min(k, per);
+        select_block(keys, total, k, sel, [&](int i) {
+            const int rr = min(i / c_full, R - 1);
+            return (unsigned)__ldcg(all_cand + (size_t)rr * k + (i - rr * c_full));
+        }, S, nv, ni);
+        got = min(k, total);
+    }
+    int Ppad = 1;
+    while (Ppad < got) Ppad <<= 1;
+    rpn_finish_level(P, b, l, sel, got, Ppad, src, S.scan);
+}
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+k_rpn_select(const __grid_constant__ RpnParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem_raw);  // [pow2(k)]
+    __shared__ int hist[256];
+    __shared__ unsigned s_prefix, s_mask;
+    __shared__ int s_remaining, s_cnt, s_tie;
+    __shared__ int s_scan[kSelWarps];
+
+    const int l = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = P.level_n[l], k = P.level_k[l];
+    const float* src = P.obj + (size_t)b * P.total + P.level_off[l];
+    int Ppad = 1;
+    while (Ppad < k) Ppad <<= 1;
+
+    // ---- radix select: key of the k-th largest logit ------------------------------------------
+    if (tid == 0) { s_prefix = 0u; s_mask = 0u; s_remaining = k; s_cnt = 0; s_tie = 0; }
+    __syncthreads();
+    if (n > k) {
+        for (int pass = 3; pass >= 0; --pass) {
+            for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
+            __syncthreads();
+            const unsigned prefix = s_prefix, mask = s_mask;
+            const int shift = 8 * pass;
+            for (int i = tid; i - lane < n; i += kSelThreads) {
+                const unsigned key = i < n ? orderable(__ldg(src + i)) : 0u;
+                const bool in = i < n && (key & mask) == prefix;
+                const unsigned bin = in ? (key >> shift) & 255u : 256u;
+                const unsigned peers = __match_any_sync(kFullMask, bin);          // one atomic per distinct bin and warp
+                if (in && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // bins 255 .. 0, 8 per lane (lane 0 owns the top bins); find the bin holding rank `remaining`
+                int local[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { local[j] = hist[255 - (lane * 8 + j)]; sum += local[j]; }
+                int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(kFullMask, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                int before = incl - sum;
+                const int rem = s_remaining;
+                if (before < rem && rem <= incl) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (before < rem && rem <= before + local[j]) {
+                            s_prefix = prefix | ((unsigned)(255 - (lane * 8 + j)) << shift);
+                            s_mask = mask | (255u << shift);
+                            s_remaining = rem - before;
+                        }
+                        before += local[j];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const unsigned T = s_prefix;           // key of the k-th largest (exact after 4 passes)
+    const int take_ties = s_remaining;     // how many entries equal to T are still needed
+    // ---- collect the selected entries --------------------------------------------------------
+    for (int i0 = 0; i0 < n; i0 += kSelThreads) {
+        const int i = i0 + tid;
+        if (i < n) {
+            const unsigned key = orderable(__ldg(src + i));
+            bool take = n <= k || key > T;
+            if (!take && key == T) take = atomicAdd(&s_tie, 1) < take_ties;
+            if (take) sel[atomicAdd(&s_cnt, 1)] = ((unsigned long long)(~key) << 32) | (unsigned)i;
+        }
+    }
+    __syncthreads();
+    const int got = s_cnt;  // == k
+    rpn_finish_level(P, b, l, sel, got, Ppad, src, s_scan);
+}
+
+// merge the kept lists of an image by score, emit the first post_k (rpn.py:272-278).  Every segment's kept list
+// already is in descending score (the NMS emits in that order), so an element's place in the merged order is its own
+// position plus, for every other segment, the number of that segment's elements in front of it (binary search):
+// no sort.
 __global__ void __launch_bounds__(1024, 1)
 k_rpn_finish(const __grid_constant__ RpnParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);
-    __shared__ int s_total;
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);     // [sum of kept] grouped by segment
+    __shared__ int s_at[kMaxLevels + 1];
     const int b = blockIdx.x, tid = threadIdx.x;
     const size_t base = (size_t)b * P.Ktot;
-    if (tid == 0) s_total = 0;
+    const int S = P.segs_per_img;
+    if (tid == 0) {
+        int at = 0;
+        for (int s = 0; s < S; ++s) { s_at[s] = at; at += P.keep_count[b * S + s]; }
+        s_at[S] = at;
+    }
     __syncthreads();
-    const int* starts = P.seg_start;
-    for (int s = 0; s < P.segs_per_img; ++s) {
-        const int seg = b * P.segs_per_img + s;
-        const int kc = P.keep_count[seg];
-        const int st = starts[seg];
-        const int at = s_total;
+    for (int s = 0; s < S; ++s) {
+        const int seg = b * S + s;
+        const int kc = s_at[s + 1] - s_at[s], st = P.seg_start[seg];
         for (int i = tid; i < kc; i += 1024) {
             const int pos = st + (int)P.keep[st + i];           // absolute row
-            key[at + i] = ((unsigned long long)(~orderable(P.score[pos])) << 32) | (unsigned)(pos - (int)base);
+            key[s_at[s] + i] = ((unsigned long long)(~orderable(P.score[pos])) << 32) | (unsigned)(pos - (int)base);
         }
-        __syncthreads();
-        if (tid == 0) s_total = at + kc;
-        __syncthreads();
     }
-    const int total = s_total;
-    {
-        int Ppad = 1;
-        while (Ppad < total) Ppad <<= 1;
-        for (int i = total + tid; i < Ppad; i += 1024) key[i] = ~0ull;
-        __syncthreads();
-        bitonic_sort_u64(key, Ppad);
-    }
+    __syncthreads();
+    const int total = s_at[S];
     const int nout = min(total, P.post_k);
-    for (int i = tid; i < nout; i += 1024) {
-        const size_t pos = base + (unsigned)key[i];
-        reinterpret_cast<float4*>(P.out_boxes)[(size_t)b * P.post_k + i] = P.box[pos];
-        P.out_scores[(size_t)b * P.post_k + i] = P.score[pos];
-        if (P.out_index) P.out_index[(size_t)b * P.post_k + i] = P.aidx[pos];
+    for (int e = tid; e < total; e += 1024) {
+        int s = 0;
+        while (e >= s_at[s + 1]) ++s;
+        const unsigned long long mine = key[e];
+        int rank = e - s_at[s];
+        for (int o = 0; o < S; ++o) {
+            if (o == s) continue;
+            int lo = s_at[o], hi = s_at[o + 1];               // first element of segment o that is not in front of mine
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (key[mid] < mine) lo = mid + 1; else hi = mid;
+            }
+            rank += lo - s_at[o];
+        }
+        if (rank < nout) {
+            const size_t pos = base + (unsigned)mine;
+            reinterpret_cast<float4*>(P.out_boxes)[(size_t)b * P.post_k + rank] = P.box[pos];
+            P.out_scores[(size_t)b * P.post_k + rank] = P.score[pos];
+            if (P.out_index) P.out_index[(size_t)b * P.post_k + rank] = P.aidx[pos];
+        }
     }
     if (tid == 0) P.out_count[b] = nout;
 }
@@ -261,19 +608,21 @@ k_rpn_units(const RpnParams P, float* __restrict__ units) {
 }
 
 // ------------------------------------------------------------------------------------------ host
+static size_t rpn_select_ws_bytes(int batch, int total, int num_levels, int pre_k);
 namespace {
 struct RpnWs {
     float4* box; float* score; int* label; int* aidx;
     int* seg_start; int* seg_count;
     long long* keep; int* keep_count; float* units;
     void* nms; size_t nms_bytes;
+    void* sel; size_t sel_bytes;
 };
 // NMS scratch: B*L segments of <= pre_k boxes for either batched_nms strategy
 size_t rpn_nms_bytes(int batch, int levels, int pre_k) {
     const size_t T = (size_t)batch * levels * pre_k;
     return nms_scratch_bytes(T, (size_t)batch * levels, (size_t)pre_k);
 }
-size_t rpn_carve(int batch, int levels, int pre_k, void* base, size_t bytes, RpnWs* w) {
+size_t rpn_carve(int batch, int total, int levels, int pre_k, void* base, size_t bytes, RpnWs* w) {
     const size_t T = (size_t)batch * levels * pre_k;   // worst case rows (>= B*Ktot)
     unsigned char* p = reinterpret_cast<unsigned char*>(base);
     size_t used = 0;
@@ -285,15 +634,66 @@ size_t rpn_carve(int batch, int levels, int pre_k, void* base, size_t bytes, Rpn
     t.units = (float*)take(4 * (size_t)batch * levels);
     t.nms_bytes = rpn_nms_bytes(batch, levels, pre_k);
     t.nms = take(t.nms_bytes);
+    t.sel_bytes = rpn_select_ws_bytes(batch, total, levels, pre_k);
+    t.sel = take(t.sel_bytes);
     if (base && used > bytes) return 0;
     if (w) *w = t;
     return used;
 }
 }  // namespace
 
+// per-level top-k (+ decode / filter unless P.topk_out): sliced kernel when the shared-memory plan fits
+static int launch_rpn_select(RpnParams& P, int kmax, void* sel_ws, size_t sel_ws_bytes, cudaStream_t stream) {
+    int pp = 1;
+    while (pp < kmax) pp <<= 1;
+    static SmemOptIn optin1, optin3;
+    // shared-memory plan of the sliced kernel: the slice keys, or (last CTA) the candidates' keys + the sort buffer
+    int slices = 0, coff = 0;
+    size_t smem = 0;
+    for (int l = 0; l < P.L; ++l) {
+        const int n = P.level_n[l], k = P.level_k[l];
+        const int R = (n + kSliceMax - 1) / kSliceMax;
+        const int per = (((n + R - 1) / R) + 3) & ~3;
+        int kp = 1;
+        while (kp < k) kp <<= 1;
+        P.level_slices[l] = R;
+        P.level_coff[l] = coff;
+        size_t need = (size_t)per * 4;
+        if (R == 1) need = (((size_t)n * 4 + 15) & ~(size_t)15) + (size_t)kp * 8;
+        else {
+            coff += R * k;
+            const size_t merge = (((size_t)R * (k < per ? k : per) * 4 + 15) & ~(size_t)15) + (size_t)kp * 8;
+            need = need > merge ? need : merge;
+        }
+        smem = smem > need ? smem : need;
+        slices += R;
+    }
+    smem += 2 * sizeof(unsigned) * (size_t)kNarrowMax;            // the compact refinement list
+    P.cand_stride = coff;
+    const size_t cand_bytes = align_up(sizeof(unsigned long long) * (size_t)P.B * (size_t)(coff > 0 ? coff : 1), 256);
+    const size_t cnt_bytes = align_up(sizeof(int) * (size_t)P.B * P.L, 256);
+    if (smem <= 200 * 1024 && slices <= 65535 && sel_ws && sel_ws_bytes >= cand_bytes + cnt_bytes) {
+        P.cand = reinterpret_cast<unsigned long long*>(sel_ws);
+        P.sel_counter = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(sel_ws) + cand_bytes);
+        if (cudaMemsetAsync(P.sel_counter, 0, sizeof(int) * (size_t)P.B * P.L, stream) != cudaSuccess) return B200_ERR_CUDA;
+        if (optin3.ensure(k_rpn_select_sliced, 200 * 1024) != cudaSuccess) return B200_ERR_CUDA;
+        k_rpn_select_sliced<<<dim3(slices, P.B), kSelThreads, smem, stream>>>(P);
+    } else {
+        if (optin1.ensure(k_rpn_select, 8192 * 8) != cudaSuccess) return B200_ERR_CUDA;
+        k_rpn_select<<<dim3(P.L, P.B), kSelThreads, sizeof(unsigned long long) * (size_t)pp, stream>>>(P);
+    }
+    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
+
+// scratch of the sliced select: candidate lists of the multi-slice levels (<= 8 bytes x pre_k per started slice) + counters
+static size_t rpn_select_ws_bytes(int batch, int total, int num_levels, int pre_k) {
+    const size_t slices = (size_t)(total + kSliceMax - 1) / kSliceMax + (size_t)num_levels;
+    return align_up(sizeof(unsigned long long) * (size_t)batch * slices * (size_t)pre_k, 256) +
+           align_up(sizeof(int) * (size_t)batch * num_levels, 256) + 256;
+}
+
 size_t rpn_workspace_bytes(int batch, int total, int num_levels, int pre_k) {
-    (void)total;
-    return rpn_carve(batch, num_levels, pre_k, nullptr, 0, nullptr) + 256;
+    return rpn_carve(batch, total, num_levels, pre_k, nullptr, 0, nullptr) + 256;
 }
 
 int launch_rpn_filter(const float* objectness, const float* deltas, const float* anchors, const float* proposals, int batch,
@@ -319,18 +719,14 @@ int launch_rpn_filter(const float* objectness, const float* deltas, const float*
     P.Ktot = koff;
     if (koff > 16384 || kmax > 8192) return B200_ERR_INVALID;   // shared-memory sort capacity
     RpnWs w;
-    if (!rpn_carve(batch, num_levels, pre_k, workspace, workspace_bytes, &w)) return B200_ERR_WORKSPACE;
+    if (!rpn_carve(batch, total, num_levels, pre_k, workspace, workspace_bytes, &w)) return B200_ERR_WORKSPACE;
     P.box = w.box; P.score = w.score; P.label = w.label; P.aidx = w.aidx;
     P.seg_start = w.seg_start; P.seg_count = w.seg_count;
     P.keep = w.keep; P.keep_count = w.keep_count;
     P.out_boxes = out_boxes; P.out_scores = out_scores; P.out_index = out_index; P.out_count = out_count;
 
-    int pp = 1;
-    while (pp < kmax) pp <<= 1;
-    const size_t sel_smem = sizeof(unsigned long long) * (size_t)pp;
-    static SmemOptIn optin1, optin2;
-    if (optin1.ensure(k_rpn_select, 8192 * 8) != cudaSuccess) return B200_ERR_CUDA;
-    k_rpn_select<<<dim3(num_levels, batch), kSelThreads, sel_smem, stream>>>(P);
+    const int rcs = launch_rpn_select(P, kmax, w.sel, w.sel_bytes, stream);
+    if (rcs != B200_OK) return rcs;
 
     NmsParams np{};
     const size_t T = (size_t)batch * P.Ktot;
@@ -355,11 +751,37 @@ int launch_rpn_filter(const float* objectness, const float* deltas, const float*
     }
     const int rc = launch_nms(np, nseg, stream);
     if (rc != B200_OK) return rc;
-    int fp = 1;
-    while (fp < P.Ktot) fp <<= 1;
+    static SmemOptIn optin2;
     if (optin2.ensure(k_rpn_finish, 16384 * 8) != cudaSuccess) return B200_ERR_CUDA;
-    k_rpn_finish<<<batch, 1024, sizeof(unsigned long long) * (size_t)fp, stream>>>(P);
+    k_rpn_finish<<<batch, 1024, sizeof(unsigned long long) * (size_t)(P.Ktot > 0 ? P.Ktot : 1), stream>>>(P);
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
+
+// RegionProposalNetwork._get_top_n_idx (rpn.py:215-228): per level the indices of the top min(pre_k, n_l) raw objectness
+// logits in descending order, offset by the level start; out [B, sum_l min(pre_k, n_l)] int64
+int launch_rpn_topk(const float* objectness, int batch, int total, const int* level_sizes_host, int num_levels, int pre_k,
+                    long long* out_index, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    RpnParams P{};
+    P.obj = objectness; P.B = batch; P.total = total; P.L = num_levels; P.pre_k = pre_k;
+    int off = 0, koff = 0, kmax = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        const int n = level_sizes_host[l];
+        if (n < 1) return B200_ERR_INVALID;
+        P.level_off[l] = off; P.level_n[l] = n;
+        P.level_k[l] = n < pre_k ? n : pre_k;
+        P.level_koff[l] = koff;
+        off += n; koff += P.level_k[l];
+        kmax = kmax > P.level_k[l] ? kmax : P.level_k[l];
+    }
+    if (off != total || kmax > 8192) return B200_ERR_INVALID;
+    P.Ktot = koff;
+    if (!workspace || workspace_bytes < rpn_select_ws_bytes(batch, total, num_levels, pre_k)) return B200_ERR_WORKSPACE;
+    P.topk_out = out_index;
+    return launch_rpn_select(P, kmax, workspace, workspace_bytes, stream);
+}
+
+size_t rpn_topk_workspace_bytes(int batch, int total, int num_levels, int pre_k) {
+    return rpn_select_ws_bytes(batch, total, num_levels, pre_k);
 }
 
 }  // namespace b200

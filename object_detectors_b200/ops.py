@@ -432,6 +432,22 @@ def rpn_filter(objectness: Tensor, deltas: Tensor, anchors: Tensor, level_sizes:
 
 
 @_device_guard
+def rpn_top_n_idx(objectness: Tensor, level_sizes: Sequence[int], pre_nms_top_n: int) -> Tensor:
+    """RegionProposalNetwork._get_top_n_idx: objectness [B, total] raw logits -> int64 [B, sum_l min(k, n_l)]."""
+    lib = _lib.load()
+    objectness = _need_cuda(objectness, "objectness", torch.float32)
+    b, total = objectness.shape
+    lv = (C.c_int32 * len(level_sizes))(*[int(v) for v in level_sizes])
+    ktot = sum(min(int(pre_nms_top_n), int(v)) for v in level_sizes)
+    out = torch.empty((b, ktot), dtype=torch.int64, device=objectness.device)
+    ws = workspace(lib.b200_rpn_top_n_idx_workspace_bytes(b, total, len(level_sizes), int(pre_nms_top_n)), objectness.device,
+                   "rpn_topk")
+    _lib.check(lib.b200_rpn_top_n_idx(_ptr(objectness), b, total, lv, len(level_sizes), int(pre_nms_top_n), _ptr(out),
+                                      _ptr(ws), ws.numel(), _stream()), "b200_rpn_top_n_idx")
+    return out
+
+
+@_device_guard
 def rpn_filter_proposals(objectness: Tensor, proposals: Tensor, level_sizes: Sequence[int], image_hw: Tensor,
                          pre_nms_top_n: int, post_nms_top_n: int, nms_thr: float = 0.7, score_thr: float = 0.0,
                          min_size: float = 1e-3, nms_mode: int = NMS_TV_CLASS):

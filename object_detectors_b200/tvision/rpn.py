@@ -8,6 +8,7 @@ reference's signature (rpn.py:230) and is written to be bound onto the reference
     from object_detectors_b200.tvision import rpn as b200_rpn
     RegionProposalNetwork.filter_proposals = b200_rpn.filter_proposals
 
+``_get_top_n_idx(self, objectness, num_anchors_per_level)`` (rpn.py:215) is the per-level top-k index list alone.
 ``filter_from_deltas`` is the fused variant that also replaces ``box_coder.decode`` (rpn.py:355) by
 decoding only the per-level top-k anchors.
 """
@@ -44,6 +45,14 @@ def filter_proposals(self, proposals: Tensor, objectness: Tensor, image_shapes: 
         objectness, proposals.detach().float(), list(num_anchors_per_level), hw, pre, post, self.nms_thresh,
         self.score_thresh, self.min_size, _strategy_mode(kept_per_image, strategy))
     return _split(boxes, scores, count)
+
+
+def _get_top_n_idx(self, objectness: Tensor, num_anchors_per_level: Sequence[int]) -> Tensor:
+    """``RegionProposalNetwork._get_top_n_idx(objectness, num_anchors_per_level)`` (rpn.py:215-228): per level the
+    indices of the ``min(pre_nms_top_n, n_l)`` largest logits in descending order, offset by the level start,
+    concatenated over the levels -> int64 ``[B, sum_l k_l]``.  One cluster-select kernel instead of a ``split`` /
+    ``topk`` / ``cat`` per level; bind it like ``filter_proposals``."""
+    return ops.rpn_top_n_idx(objectness.detach().float(), list(num_anchors_per_level), self.pre_nms_top_n())
 
 
 def filter_from_deltas(objectness: Tensor, pred_bbox_deltas: Tensor, anchors: Tensor,

@@ -54,7 +54,7 @@ def test_helper_get_abs_coord_and_bbox_iou():
     np.testing.assert_allclose(out.detach().cpu().numpy(), yolo_ref.bbox_iou(gt, cx[:20], 1).numpy(), rtol=1e-6, atol=1e-7)
 
 
-def test_helper_nms_majority_matches_reference_golden():
+def test_helper_nms_majority_matches_reference_golden(nms_path):
     from object_detectors_b200.yolo.utilities import helper
     gold = np.load(os.path.join(G, "nms_majority_boxes.npz"))
     for i in range(4):
@@ -261,7 +261,7 @@ def test_legacy_yololoss_get_target():
 # --------------------------------------------------------------------------------- roi_heads.py
 @pytest.mark.parametrize("tag,loss_name", [("ce", "ce"), ("gombit", "gombit_x"), ("sigmoid", "bce")])
 @pytest.mark.parametrize("strategy", ["vanilla", "coordinate_trick", "torchvision"])
-def test_roi_postprocess_detections_bound_like_the_reference(tag, loss_name, strategy):
+def test_roi_postprocess_detections_bound_like_the_reference(tag, loss_name, strategy, nms_path):
     """postprocess_detections bound onto a RoIHeads-like object; expected values: the oracle (pinned to the
     reference by tests/test_oracle_golden.py) with the same batched_nms strategy, and for the installed
     torchvision's own switch (4000 coordinates on CPU) the reference's golden output itself."""
@@ -438,3 +438,46 @@ def test_yoloforw_postprocess_retries_with_the_true_candidate_count():
     n_plans = len(yolo._plans)
     yolo.postprocess(heads, capacity=4096)
     assert len(yolo._plans) == n_plans                  # served from the cache
+
+
+@pytest.mark.parametrize("shape,bsz,pre", [((224, 320), 3, 300), ((800, 1344), 2, 2000), ((800, 1344), 2, 1000)])
+def test_rpn_get_top_n_idx(shape, bsz, pre):
+    """RegionProposalNetwork._get_top_n_idx (rpn.py:215-228) bound like the reference: the index list of split /
+    topk / cat per level, bit-exact (tie-free logits)."""
+    from object_detectors_b200.tvision import rpn as b200_rpn
+    ih, iw = shape
+    obj, _, _, per_level = syn.rpn_inputs(43, bsz, ih, iw)
+    fake_self = types.SimpleNamespace(pre_nms_top_n=lambda: pre)
+    got = b200_rpn._get_top_n_idx(fake_self, torch.from_numpy(obj).cuda(), per_level).cpu()
+    want, off = [], 0
+    for ob in torch.from_numpy(obj).split(per_level, 1):                      # the reference's loop, on the CPU
+        k = min(pre, ob.shape[1])
+        want.append(ob.topk(k, dim=1)[1] + off)
+        off += ob.shape[1]
+    want = torch.cat(want, 1)
+    assert got.dtype == torch.int64 and got.shape == want.shape
+    np.testing.assert_array_equal(got.numpy(), want.numpy())
+
+
+def test_rpn_top_n_idx_with_ties():
+    """Equal logits around the k-th value: the selection is a valid top-k (multiset of values equal to topk's) and,
+    among equal logits, the lower index comes first."""
+    from object_detectors_b200 import ops
+    g = np.random.default_rng(3)
+    per_level = [5000, 700]
+    obj = np.round(g.standard_normal((2, 5700)) * 4).astype(np.float32) / 4 + np.float32(0.0)     # heavy ties, no -0.0
+    got = ops.rpn_top_n_idx(torch.from_numpy(obj).cuda(), per_level, 600).cpu().numpy()
+    off = 0
+    col = 0
+    for n in per_level:
+        k = min(600, n)
+        for b in range(2):
+            idx = got[b, col:col + k] - off
+            vals = obj[b, off:off + n][idx]
+            want_vals = np.sort(obj[b, off:off + n])[::-1][:k]
+            np.testing.assert_array_equal(vals, want_vals)
+            assert len(set(idx.tolist())) == k
+            same = vals[1:] == vals[:-1]
+            assert np.all(idx[1:][same] > idx[:-1][same])
+        off += n
+        col += k

@@ -104,7 +104,7 @@ def test_decode_dense(name):
 
 @pytest.mark.parametrize("name", list(CASES))
 @pytest.mark.parametrize("mode", ["majority", "tv", "tv_class"])
-def test_postprocess_two_stage(name, mode):
+def test_postprocess_two_stage(name, mode, nms_path):
     """decode+filter+NMS in one call.  Stage 2 is checked bit-exactly by running the C oracle on
     the GPU's own candidate list (identical inputs -> identical keep / labels)."""
     ops = _ops()
@@ -180,7 +180,7 @@ def _segments(sizes, seed, clusters, num_classes):
 
 
 @pytest.mark.parametrize("sizes", [[300, 0, 1, 64, 65, 1000, 2, 129], [4096], [5000]])
-def test_nms_modes_bit_exact(sizes):
+def test_nms_modes_bit_exact(sizes, nms_path):
     ops = _ops()
     boxes, scores, labels, off, bs, ss, ls = _segments(sizes, 50, 12, 7)
     tb, ts = torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda()
@@ -205,7 +205,7 @@ def test_nms_modes_bit_exact(sizes):
             np.testing.assert_array_equal(got, want, err_msg=f"mode {mode} segment {s} (n={n})")
 
 
-def test_nms_threshold_semantics():
+def test_nms_threshold_semantics(nms_path):
     """IoU == fp32(0.6) exactly: torchvision suppresses ((double)0.6f > 0.6), nms_majority removes it
     without a vote; zero-area pairs: NaN IoU never suppresses in torchvision, is removed in majority."""
     ops = _ops()
@@ -270,7 +270,7 @@ def test_iou_match(kind, img, batch, max_gt):
 @pytest.mark.parametrize("shape,bsz,pre,post", [((224, 320), 2, 300, 300), ((416, 608), 2, 1000, 1000),
                                                 ((800, 1344), 2, 2000, 2000)])
 @pytest.mark.parametrize("strategy", ["vanilla", "trick"])
-def test_rpn_filter(shape, bsz, pre, post, strategy):
+def test_rpn_filter(shape, bsz, pre, post, strategy, nms_path):
     ops = _ops()
     ih, iw = shape
     obj, deltas, anchors, per_level = syn.rpn_inputs(41, bsz, ih, iw)
@@ -349,7 +349,7 @@ def test_decode_variants_agree(name):
             _close_score(o["score"][i, :n].cpu().numpy(), ref["score"][i, :n].cpu().numpy())
 
 
-def test_c2_full_size_end_to_end():
+def test_c2_full_size_end_to_end(nms_path):
     """The bench.py workload itself (BASELINE configs[1]: 608 / COCO-80 / batch 64, seed 1000) through the fused
     call, against the oracle run end to end on the CPU: per-image candidate anchor sets, kept anchor lists (in
     score order) and labels after the majority vote bit-exact, 40 762 candidates and 8 365 detections in total.
