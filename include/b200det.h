@@ -353,6 +353,22 @@ int b200_matcher(const float* quality, int32_t m, int32_t n, float high_thr, flo
                  int32_t allow_low_quality, int64_t* matches, void* workspace, size_t workspace_bytes,
                  void* stream);
 
+/* box_iou + Matcher fused (rpn.py:192-193, roi_heads.py:633-634, retinanet.py:409-410, ssd.py:371-372):
+ *   matches = Matcher(high, low, allow_low_quality)(box_iou(gt_boxes, boxes))        (_utils.py:271-344)
+ * without ever writing the [M, N] quality matrix; bit-identical to that composition (torchvision's IoU arithmetic,
+ * first maximum on ties, BELOW_LOW = -1 / BETWEEN = -2, low-quality restore incl. ties).  ssd != 0 adds SSDMatcher's
+ * override matches[argmax_n q[m, :]] = m (:347-361; later m wins a shared box).  matched_vals [N] (nullable) receives
+ * q.max(dim=0).  gt_boxes [M,4], boxes [N,4] xyxy fp32, 16 B aligned; matches [N] int64. */
+size_t b200_match_boxes_workspace_bytes(int32_t m, int32_t n);
+int b200_match_boxes(const float* gt_boxes, int32_t m, const float* boxes, int32_t n, float high_thr, float low_thr,
+                     int32_t allow_low_quality, int32_t ssd, int64_t* matches, float* matched_vals, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* SSDMatcher.__call__(match_quality_matrix) on a materialised matrix = b200_matcher(high = low = threshold, no
+ * low-quality restore) followed by this override (_utils.py:355-359).  workspace: 8 bytes per ground truth. */
+int b200_matcher_ssd_override(const float* quality, int32_t m, int32_t n, int64_t* matches, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * result emission (the step right after the path)
  * ---------------------------------------------------------------------------------------- */

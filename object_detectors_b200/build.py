@@ -17,7 +17,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libb200det.so")
-SOURCES = ("api.cu", "decode.cu", "decode_ring.cu", "nms.cu", "nms_fused.cu", "iou.cu", "rpn.cu", "misc.cu", "roi.cu", "exchange.cu", "emit.cu")
+SOURCES = ("api.cu", "decode.cu", "decode_ring.cu", "nms.cu", "nms_fused.cu", "iou.cu", "rpn.cu", "misc.cu", "roi.cu", "exchange.cu", "emit.cu", "match.cu")
 HEADERS = ("common.cuh", "decode.cuh", "decode_ring.cuh", "nms.cuh", "nms_dev.cuh", os.path.join("..", "..", "include", "b200det.h"))
 
 NVCC_FLAGS = [

@@ -541,6 +541,45 @@ def matcher(quality: Tensor, high: float, low: float, allow_low_quality: bool = 
 
 
 @_device_guard
+def match_boxes(gt_boxes: Tensor, boxes: Tensor, high: float, low: float, allow_low_quality: bool = False,
+                ssd: bool = False, return_vals: bool = False):
+    """``Matcher(high, low, allow_low_quality)(box_iou(gt_boxes, boxes))`` (or SSDMatcher with ``ssd=True``) in one
+    fused pass over the pairs: the [M, N] matrix is never materialised.  -> int64 [N] (and matched_vals fp32 [N])."""
+    lib = _lib.load()
+    gt_boxes = _need_cuda(gt_boxes, "gt_boxes").to(torch.float32).contiguous()
+    boxes = _need_cuda(boxes, "boxes").to(torch.float32).contiguous()
+    m, n = gt_boxes.shape[0], boxes.shape[0]
+    if m == 0:
+        raise ValueError("No ground-truth boxes available for one of the images during training")
+    if n == 0:
+        raise ValueError("No proposal boxes available for one of the images during training")
+    if gt_boxes.data_ptr() % 16:
+        gt_boxes = gt_boxes.clone()
+    if boxes.data_ptr() % 16:
+        boxes = boxes.clone()
+    matches = torch.empty((n,), dtype=torch.int64, device=boxes.device)
+    vals = torch.empty((n,), dtype=torch.float32, device=boxes.device) if return_vals else None
+    ws = workspace(lib.b200_match_boxes_workspace_bytes(m, n), boxes.device, "match_boxes")
+    _lib.check(lib.b200_match_boxes(_ptr(gt_boxes), m, _ptr(boxes), n, float(np.float32(high)), float(np.float32(low)),
+                                    int(bool(allow_low_quality)), int(bool(ssd)), _ptr(matches), _ptr(vals), _ptr(ws),
+                                    ws.numel(), _stream()), "b200_match_boxes")
+    return (matches, vals) if return_vals else matches
+
+
+@_device_guard
+def matcher_ssd(quality: Tensor, threshold: float) -> Tensor:
+    """SSDMatcher.__call__ on a materialised [M,N] matrix (_utils.py:347-361)."""
+    lib = _lib.load()
+    quality = _need_cuda(quality, "match_quality_matrix", torch.float32)
+    m, n = quality.shape
+    matches = matcher(quality, threshold, threshold, False)
+    ws = workspace(8 * m, quality.device, "matcher_ssd")
+    _lib.check(lib.b200_matcher_ssd_override(_ptr(quality), m, n, _ptr(matches), _ptr(ws), ws.numel(), _stream()),
+               "b200_matcher_ssd_override")
+    return matches
+
+
+@_device_guard
 def yolo_legacy_decode(head: Tensor, anchors_px, num_classes: int, img_size) -> Tensor:
     """One head of the legacy YOLOLoss layer (yolo/nets/yolo_loss.py:34-105, inference branch):
     [B, A*(5+C), H, W] -> [B, A*H*W, 5+C], rows ordered (a, h, w)."""

@@ -59,3 +59,24 @@ class Matcher:
             raise ValueError("No proposal boxes available for one of the images during training")
         return ops.matcher(match_quality_matrix.float(), self.high_threshold, self.low_threshold,
                            self.allow_low_quality_matches)
+
+    def match_boxes(self, gt_boxes: Tensor, boxes: Tensor) -> Tensor:
+        """``self(box_ops.box_iou(gt_boxes, boxes))`` without the [M, N] matrix (rpn.py:192-193, roi_heads.py:633-634,
+        retinanet.py:409-410): IoU, column max, thresholds and the low-quality restore in two fused kernels."""
+        return ops.match_boxes(gt_boxes, boxes, self.high_threshold, self.low_threshold, self.allow_low_quality_matches)
+
+
+class SSDMatcher(Matcher):
+    """``_utils.py:347-361``: threshold matching plus "every ground truth keeps its best prior"."""
+
+    def __init__(self, threshold: float):
+        super().__init__(threshold, threshold, allow_low_quality_matches=False)
+
+    def __call__(self, match_quality_matrix: Tensor) -> Tensor:
+        if match_quality_matrix.numel() == 0:
+            return super().__call__(match_quality_matrix)       # raises like the reference
+        return ops.matcher_ssd(match_quality_matrix.float(), self.high_threshold)
+
+    def match_boxes(self, gt_boxes: Tensor, boxes: Tensor) -> Tensor:
+        """``self(box_ops.box_iou(gt_boxes, boxes))`` (ssd.py:371-372) without the matrix."""
+        return ops.match_boxes(gt_boxes, boxes, self.high_threshold, self.low_threshold, False, ssd=True)

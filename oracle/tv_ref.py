@@ -238,3 +238,11 @@ def roi_postprocess(class_logits: Tensor, box_regression: Tensor, proposals: Seq
         k = k[:detections_per_img]                                                                 # :774
         out.append((boxes[k], sc[k], labels[k], k))
     return out
+
+
+def ssd_matcher(quality: Tensor, threshold: float) -> Tensor:
+    """SSDMatcher.__call__ (_utils.py:347-361): threshold matching, then every ground truth keeps its best prior."""
+    matches = matcher(quality, threshold, threshold, False)
+    best_pred = quality.max(dim=1)[1]
+    matches[best_pred] = torch.arange(best_pred.size(0), dtype=torch.int64)
+    return matches

@@ -481,3 +481,35 @@ def test_rpn_top_n_idx_with_ties():
             assert np.all(idx[1:][same] > idx[:-1][same])
         off += n
         col += k
+
+
+@pytest.mark.parametrize("m,n,seed", [(12, 700, 3), (1, 257, 5), (50, 268569, 7), (300, 5000, 9)])
+def test_fused_box_iou_matcher(m, n, seed):
+    """b200_match_boxes == Matcher(...)(box_iou(gt, boxes)) of the reference (torchvision's CPU box_iou + the oracle's
+    restatement of _utils.py:271-361), bit for bit, without the [M, N] matrix: both threshold settings, the
+    low-quality restore incl. exact ties (duplicated boxes), a ground truth that meets no box, and SSDMatcher."""
+    from object_detectors_b200.tvision._utils import Matcher, SSDMatcher
+    if n > 100000:
+        _, _, anchors, _ = syn.rpn_inputs(41, 1, 800, 1344)
+        pr = anchors
+        gt, _, _ = syn.random_boxes(seed, m, extent=1300.0, clusters=6)
+    else:
+        gt, _, _ = syn.random_boxes(seed, m, clusters=3)
+        pr, _, _ = syn.random_boxes(seed + 1, n, clusters=3)
+        pr[100:110] = pr[0:10]                                     # exact ties
+    gt = gt.copy()
+    gt[-1] = [5000.0, 5000.0, 5040.0, 5030.0] if m > 1 else gt[-1]  # intersects nothing: an all-zero row
+    tg, tp = torch.from_numpy(gt), torch.from_numpy(pr)
+    q = tv_ref.box_iou(tg, tp)
+    for allow in (False, True):
+        for hi, lo in ((0.7, 0.3), (0.5, 0.5)):
+            want = tv_ref.matcher(q.clone(), hi, lo, allow).numpy()
+            got = Matcher(hi, lo, allow).match_boxes(tg.cuda(), tp.cuda()).cpu().numpy()
+            np.testing.assert_array_equal(got, want, err_msg=f"allow={allow} thr=({hi},{lo})")
+    want = tv_ref.ssd_matcher(q.clone(), 0.5).numpy()
+    np.testing.assert_array_equal(SSDMatcher(0.5).match_boxes(tg.cuda(), tp.cuda()).cpu().numpy(), want)
+    if n <= 5000:
+        np.testing.assert_array_equal(SSDMatcher(0.5)(q.cuda()).cpu().numpy(), want)
+    from object_detectors_b200 import ops
+    _, vals = ops.match_boxes(tg.cuda(), tp.cuda(), 0.7, 0.3, return_vals=True)
+    np.testing.assert_array_equal(vals.cpu().numpy(), q.max(dim=0)[0].numpy())
