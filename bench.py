@@ -375,6 +375,52 @@ def run_b200(args):
             pl.check_status()
         return float(t[0]), float(t[1]), float(t[2])
 
+    def graph_loop(steps, warm, sample_clocks=False):
+        """The same `steps` steps captured ONCE into a CUDA graph (all streams fork from / join the capturing stream
+        exactly like fence_in / fence_out) and timed as one replay: the host enqueues one launch for the whole loop.
+        Untimed before the measurement: `warm` eager steps, the capture, and one replay (graph upload)."""
+        fence_in()
+        for i in range(warm):
+            step(i)
+        fence_out()
+        torch.cuda.synchronize()
+        for pl in plans:
+            pl.check_status()
+        cap = torch.cuda.Stream(device=dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(cap):
+            graph.capture_begin(capture_error_mode="thread_local")
+            fence_in()
+            for i in range(steps):
+                step(i)
+            fence_out()
+            graph.capture_end()
+            graph.replay()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sample_clocks:
+            window[0] = time.perf_counter()
+        t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(cap):
+            t_begin.record()
+            h0 = time.perf_counter()
+            graph.replay()
+            host_us[0] = (time.perf_counter() - h0) / steps * 1e6
+            t_end.record()
+        torch.cuda.synchronize()
+        if sample_clocks:
+            window[1] = time.perf_counter()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([t_begin.elapsed_time(t_end)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for pl in plans:
+            pl.check_status()
+        return float(t[0]), graph
+
     host_us = [0.0]
     window = [None, None]
     sampler = ClockSampler(local)
@@ -382,7 +428,17 @@ def run_b200(args):
         sampler.start()
         time.sleep(0.25)          # let nvidia-smi deliver its first sample before the (sub-second) timed region
     warm = max(args.warmup, 3)
-    ms_total, k_ms, k_busy = timed_loop(args.steps, warm, sample_clocks=True)
+    used_graph = False
+    graph = None
+    if args.graph and mode != "nccl":
+        try:
+            ms_total, graph = graph_loop(args.steps, warm, sample_clocks=True)
+            used_graph = True
+        except Exception as e:          # capture is an optimisation of the host side only: fall back, loudly
+            print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing the eager loop", file=sys.stderr, flush=True)
+            torch.cuda.synchronize()
+    if not used_graph:
+        ms_total, k_ms, k_busy = timed_loop(args.steps, warm, sample_clocks=True)
     clocks = sampler.stop(window[0], window[1]) if rank == 0 else None
     host_enqueue_us = host_us[0]
     last_plan = plans[(args.steps - 1) % n_p]
@@ -394,7 +450,7 @@ def run_b200(args):
     #      independent witness) -------------------------------------------------------------------------------------
     exchange_verified = None
     if mode == "p2p":
-        got = exchange.read(steps_done[0] - 1).reshape(world, batch, -1)
+        got = exchange.read(exchange.steps()[0] - 1).reshape(world, batch, -1)     # the device's own step counter
         msg = ops.pack_detections(last_plan.det, last_plan.det_count)
         truth = torch.empty((world, message_len(batch, MAX_DET)), dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(truth.view(-1), msg)
@@ -407,6 +463,14 @@ def run_b200(args):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         exchange_verified = bool(int(flag[0]))
         assert exchange_verified, "one-sided exchange delivered bytes that differ from the ranks' own detections"
+
+    # ---- diagnostic: the same loop enqueued eagerly, with CUDA events around every decode kernel ----------------------
+    eager_ms = None
+    if used_graph:
+        eager_ms, k_ms, k_busy = timed_loop(args.steps, 3)
+        eager_host_us = host_us[0]
+    else:
+        eager_host_us = host_enqueue_us
 
     # ---- for the record: the decode kernel alone (one stream, nothing overlapping it, no exchange) -----------------
     serial[0] = True
@@ -487,6 +551,10 @@ def run_b200(args):
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "kept": e2e_kept},
             "gpu_launches": args.steps * launches_per_step,
             "host_enqueue_us_per_step": host_enqueue_us,
+            "launch": ("one CUDA graph replay for the whole timed loop (captured after the warm-up; every stream forks from and "
+                       "joins the capturing stream)" if used_graph else "eager: every launch enqueued from Python"),
+            "eager_loop": ({"ms_per_step": eager_ms / args.steps, "host_enqueue_us_per_step": eager_host_us,
+                            "value": world * batch * args.steps / (eager_ms * 1e-3)} if eager_ms is not None else None),
             "clocks": clocks,
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -516,6 +584,7 @@ def main():
     ap.add_argument("--slots", type=int, default=32, help="p2p exchange: receive slots per rank (steps a rank may run ahead)")
     ap.add_argument("--exchange-every", type=int, default=4,
                     help="nccl exchange: steps per all-gather bucket (1 = gather after every step)")
+    ap.add_argument("--graph", type=int, default=1, help="1: time one CUDA-graph replay of the loop (default); 0: eager launches")
     ap.add_argument("--ring", default="4,1,101", help="RING decode: warps per CTA, stages per warp, CTAs per SM (+100: 32-cell tiles)")
     args = ap.parse_args()
     if args.impl == "reference":

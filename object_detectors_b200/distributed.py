@@ -228,6 +228,12 @@ class PeerExchange:
                                                     self.C.c_void_p(st.cuda_stream)), "b200_exchange_read")
         return out
 
+    def steps(self):
+        """(steps pushed, steps waited for) as the device counts them (host-synchronous)."""
+        a, b = self.C.c_int64(0), self.C.c_int64(0)
+        self._lib.check(self.lib.b200_exchange_steps(self.ctx, self.C.byref(a), self.C.byref(b)), "b200_exchange_steps")
+        return int(a.value), int(b.value)
+
     def close(self):
         if self.ctx:
             self.lib.b200_exchange_destroy(self.ctx)
