@@ -353,6 +353,23 @@ int b200_matcher(const float* quality, int32_t m, int32_t n, float high_thr, flo
                  int32_t allow_low_quality, int64_t* matches, void* workspace, size_t workspace_bytes,
                  void* stream);
 
+/* RetinaNet.postprocess_detections (retinanet.py:414-472) for a whole batch: per image and level the
+ * min(topk_candidates, .) best of sigmoid(tfidf[c] * logit) > score_thr over the flattened [anchors_l, C] scores (one
+ * sliced select per level, only the survivors are decoded with BoxCoder(1,1,1,1) and clipped), then ONE class-aware
+ * batched_nms per image and the first detections_per_img by score.
+ *   cls_logits [B, sumA, C], bbox_regression [B, sumA, 4], anchors [sumA, 4] (shared by the images),
+ *   level_anchors_host [L] anchors per level, tfidf [C] or NULL, image_hw [B,2];
+ *   out_boxes [B, D, 4], out_scores [B, D], out_labels [B, D] int32 (class index, 0-based as the reference), out_count [B].
+ * nms_mode: B200_NMS_TV_CLASS / _TV_TRICK / _TV_AUTO (torchvision's batched_nms strategies). */
+size_t b200_retinanet_workspace_bytes(int32_t batch, int32_t total_anchors, int32_t num_classes, int32_t num_levels,
+                                      int32_t topk_candidates);
+int b200_retinanet_postprocess(const float* cls_logits, const float* bbox_regression, const float* anchors, int32_t batch,
+                               int32_t total_anchors, int32_t num_classes, const int32_t* level_anchors_host,
+                               int32_t num_levels, const float* tfidf, const float* image_hw, int32_t topk_candidates,
+                               float score_thr, double nms_thr, int32_t nms_mode, int32_t detections_per_img,
+                               float* out_boxes, float* out_scores, int32_t* out_labels, int32_t* out_count,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* box_iou + Matcher fused (rpn.py:192-193, roi_heads.py:633-634, retinanet.py:409-410, ssd.py:371-372):
  *   matches = Matcher(high, low, allow_low_quality)(box_iou(gt_boxes, boxes))        (_utils.py:271-344)
  * without ever writing the [M, N] quality matrix; bit-identical to that composition (torchvision's IoU arithmetic,

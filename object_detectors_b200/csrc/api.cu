@@ -32,6 +32,12 @@ int launch_rpn_filter(const float* objectness, const float* deltas, const float*
                       float* out_boxes, float* out_scores, int* out_index, int* out_count,
                       void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t rpn_workspace_bytes(int batch, int total, int num_levels, int pre_k);
+int launch_rpn_filter_ex(const float* objectness, const float* deltas, const float* anchors, const float* proposals, int batch,
+                         int total, const int* level_sizes_host, int num_levels, const float* image_hw,
+                         int pre_k, int post_k, double nms_thr, float score_thr, float min_size, int nms_mode,
+                         float* out_boxes, float* out_scores, int* out_index, int* out_count,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream, int classes,
+                         const float* class_scale, int* out_labels);
 size_t rpn_topk_workspace_bytes(int batch, int total, int num_levels, int pre_k);
 int launch_rpn_topk(const float* objectness, int batch, int total, const int* level_sizes_host, int num_levels, int pre_k,
                     long long* out_index, void* workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -553,6 +559,38 @@ int b200_rpn_filter_proposals(const float* objectness, const float* proposals, i
                              num_levels, image_hw, pre_nms_top_n, post_nms_top_n, nms_thr, score_thr, min_size,
                              nms_mode, out_boxes, out_scores, out_index, out_count, workspace, workspace_bytes,
                              static_cast<cudaStream_t>(stream));
+}
+
+// RetinaNet.postprocess_detections (retinanet.py:414-472)
+size_t b200_retinanet_workspace_bytes(int32_t batch, int32_t total_anchors, int32_t num_classes, int32_t num_levels,
+                                      int32_t topk_candidates) {
+    if (batch < 1 || total_anchors < 1 || num_classes < 1 || num_levels < 1 || topk_candidates < 1) return 0;
+    return rpn_workspace_bytes(batch, total_anchors * num_classes, num_levels, topk_candidates);
+}
+
+int b200_retinanet_postprocess(const float* cls_logits, const float* bbox_regression, const float* anchors, int32_t batch,
+                               int32_t total_anchors, int32_t num_classes, const int32_t* level_anchors_host,
+                               int32_t num_levels, const float* tfidf, const float* image_hw, int32_t topk_candidates,
+                               float score_thr, double nms_thr, int32_t nms_mode, int32_t detections_per_img,
+                               float* out_boxes, float* out_scores, int32_t* out_labels, int32_t* out_count,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    if (!cls_logits || !bbox_regression || !anchors || !level_anchors_host || !image_hw || !out_boxes || !out_scores ||
+        !out_labels || !out_count || batch < 1 || total_anchors < 1 || num_classes < 1 || num_levels < 1 || num_levels > 16 ||
+        topk_candidates < 1 || detections_per_img < 1)
+        return B200_ERR_INVALID;
+    if (nms_mode != B200_NMS_TV_CLASS && nms_mode != B200_NMS_TV_TRICK && nms_mode != B200_NMS_TV_AUTO) return B200_ERR_INVALID;
+    if (!aligned16(bbox_regression) || !aligned16(anchors) || !aligned16(out_boxes)) return B200_ERR_INVALID;
+    if ((long long)total_anchors * num_classes > 0x7fffffffll) return B200_ERR_INVALID;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u) ||
+        workspace_bytes < b200_retinanet_workspace_bytes(batch, total_anchors, num_classes, num_levels, topk_candidates))
+        return B200_ERR_WORKSPACE;
+    int32_t level_sizes[16];
+    for (int l = 0; l < num_levels; ++l) level_sizes[l] = level_anchors_host[l] * num_classes;
+    // no small-box filter in RetinaNet: min_size = -inf
+    return launch_rpn_filter_ex(cls_logits, bbox_regression, anchors, nullptr, batch, total_anchors * num_classes, level_sizes,
+                                num_levels, image_hw, topk_candidates, detections_per_img, nms_thr, score_thr, -INFINITY,
+                                nms_mode, out_boxes, out_scores, nullptr, out_count, workspace, workspace_bytes,
+                                static_cast<cudaStream_t>(stream), num_classes, tfidf, out_labels);
 }
 
 // ------------------------------------------------------------------------- element-wise drop-ins

@@ -57,7 +57,23 @@ struct RpnParams {
     int cand_stride;                  // candidates per image = sum_l slices_l * k_l (multi-slice levels only)
     unsigned long long* cand;         // [B, cand_stride] (~key << 32 | index inside the level)
     int* sel_counter;                 // [B * L] slice arrival counters (zeroed before the launch)
+    // many-class heads (RetinaNet): a level is [anchors_l, C] logits, flattened; C == 1 for the RPN
+    int C;                            // classes per anchor
+    const float* class_scale;         // [C] or nullptr: logits are multiplied by it before the sigmoid (tfidf_post)
+    int strict_thr;                   // 1: score >  score_thr (retinanet.py:437), 0: score >= score_thr (rpn.py:268)
+    int label_class;                  // 1: NMS label = class (index % C), 0: NMS label = level
+    int level_aoff[kMaxLevels];       // first anchor of the level (= level_off / C)
+    int atotal;                       // anchors per image (= total / C): row count of deltas / proposals
+    int* out_labels;                  // [B, post_k] or nullptr
+    int* img_start; int* img_count;   // [B] image-wide segments (k_rpn_compact)
 };
+
+// the logit the selection orders by: raw objectness, or tfidf_post[c] * logit for many-class heads
+__device__ __forceinline__ float level_logit(const RpnParams& P, const float* src, int j) {
+    const float x = ldg_stream_f32(src + j);
+    if (!P.class_scale) return x;
+    return __fmul_rn(__ldg(P.class_scale + (j - (j / P.C) * P.C)), x);
+}
 
 // ascending bitonic sort of key[0..P) in shared memory, P a power of two.  Steps with a partner distance below 64
 // stay inside aligned blocks of 64 keys and are done by one warp per block without CTA barriers.
@@ -134,18 +150,20 @@ __device__ void rpn_finish_level(const RpnParams& P, int b, int l, unsigned long
         bool ok = false;
         float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
         float prob = 0.f;
-        int a = 0;
+        int a = 0, cls = 0;
         if (r < got) {
             const int i = (int)(unsigned)sel[r];
-            a = P.level_off[l] + i;
-            prob = sigmoid_ref(src[i]);                                            // rpn.py:255
+            const int an = i / P.C;
+            cls = i - an * P.C;
+            a = P.level_aoff[l] + an;
+            prob = sigmoid_ref(level_logit(P, src, i));                            // rpn.py:255 / retinanet.py:436
             float x1, y1, x2, y2;
             if (P.proposals) {
-                const float4 pb = *reinterpret_cast<const float4*>(P.proposals + ((size_t)b * P.total + a) * 4);
+                const float4 pb = *reinterpret_cast<const float4*>(P.proposals + ((size_t)b * P.atotal + a) * 4);
                 x1 = pb.x; y1 = pb.y; x2 = pb.z; y2 = pb.w;
             } else {
                 const float4 an = *reinterpret_cast<const float4*>(P.anchors + 4 * (size_t)a);
-                const float4 d = *reinterpret_cast<const float4*>(P.deltas + ((size_t)b * P.total + a) * 4);
+                const float4 d = *reinterpret_cast<const float4*>(P.deltas + ((size_t)b * P.atotal + a) * 4);
                 // BoxCoder.decode_single, weights (1,1,1,1)                           _utils.py:199-221
                 const float w = __fsub_rn(an.z, an.x), h = __fsub_rn(an.w, an.y);
                 const float cx = __fadd_rn(an.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(an.y, __fmul_rn(0.5f, h));
@@ -160,7 +178,8 @@ __device__ void rpn_finish_level(const RpnParams& P, int b, int l, unsigned long
             y1 = fminf(fmaxf(y1, 0.f), img_h); y2 = fminf(fmaxf(y2, 0.f), img_h);
             box = make_float4(x1, y1, x2, y2);
             // remove_small_boxes + score threshold (rpn.py:263-269)
-            ok = (__fsub_rn(x2, x1) >= P.min_size) && (__fsub_rn(y2, y1) >= P.min_size) && (prob >= P.score_thr);
+            ok = (__fsub_rn(x2, x1) >= P.min_size) && (__fsub_rn(y2, y1) >= P.min_size) &&
+                 (P.strict_thr ? prob > P.score_thr : prob >= P.score_thr);
         }
         const unsigned bal = __ballot_sync(kFullMask, ok);
         if (lane == 0) s_scan[warp] = __popc(bal);
@@ -171,7 +190,7 @@ __device__ void rpn_finish_level(const RpnParams& P, int b, int l, unsigned long
             const size_t o = out0 + running + before + __popc(bal & ((1u << lane) - 1u));
             P.box[o] = box;
             P.score[o] = prob;
-            P.label[o] = l;
+            P.label[o] = P.label_class ? cls : l;
             P.aidx[o] = a;
         }
         running += total;
@@ -406,7 +425,7 @@ k_rpn_select_sliced(const __grid_constant__ RpnParams P) {
     const int i0 = min(n, r * per), m = min(n, i0 + per) - i0;
 
     // ---- the one read of the logits ---------------------------------------------------------------------------------
-    for (int i = tid; i < m; i += kSelThreads) keys[i] = ~orderable(ldg_stream_f32(src + i0 + i));
+    for (int i = tid; i < m; i += kSelThreads) keys[i] = ~orderable(level_logit(P, src, i0 + i));
     __syncthreads();
 
     int got;
@@ -475,7 +494,7 @@ k_rpn_select(const __grid_constant__ RpnParams P) {
             const unsigned prefix = s_prefix, mask = s_mask;
             const int shift = 8 * pass;
             for (int i = tid; i - lane < n; i += kSelThreads) {
-                const unsigned key = i < n ? orderable(__ldg(src + i)) : 0u;
+                const unsigned key = i < n ? orderable(level_logit(P, src, i)) : 0u;
                 const bool in = i < n && (key & mask) == prefix;
                 const unsigned bin = in ? (key >> shift) & 255u : 256u;
                 const unsigned peers = __match_any_sync(kFullMask, bin);          // one atomic per distinct bin and warp
@@ -516,7 +535,7 @@ k_rpn_select(const __grid_constant__ RpnParams P) {
     for (int i0 = 0; i0 < n; i0 += kSelThreads) {
         const int i = i0 + tid;
         if (i < n) {
-            const unsigned key = orderable(__ldg(src + i));
+            const unsigned key = orderable(level_logit(P, src, i));
             bool take = n <= k || key > T;
             if (!take && key == T) take = atomicAdd(&s_tie, 1) < take_ties;
             if (take) sel[atomicAdd(&s_cnt, 1)] = ((unsigned long long)(~key) << 32) | (unsigned)i;
@@ -575,9 +594,36 @@ k_rpn_finish(const __grid_constant__ RpnParams P) {
             reinterpret_cast<float4*>(P.out_boxes)[(size_t)b * P.post_k + rank] = P.box[pos];
             P.out_scores[(size_t)b * P.post_k + rank] = P.score[pos];
             if (P.out_index) P.out_index[(size_t)b * P.post_k + rank] = P.aidx[pos];
+            if (P.out_labels) P.out_labels[(size_t)b * P.post_k + rank] = P.label[pos];
         }
     }
     if (tid == 0) P.out_count[b] = nout;
+}
+
+// image-wide segments (class-aware NMS across the levels): the per-level survivor lists of an image, written at a
+// fixed stride, are moved together so that the image is one contiguous segment
+__global__ void __launch_bounds__(1024, 1)
+k_rpn_compact(const __grid_constant__ RpnParams P) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const size_t base = (size_t)b * P.Ktot;
+    int at = P.seg_count[b * P.L];
+    for (int l = 1; l < P.L; ++l) {
+        const int n = P.seg_count[b * P.L + l];
+        const size_t from = base + P.level_koff[l];
+        if ((size_t)at != (size_t)P.level_koff[l]) {
+            // destination precedes the source; chunks of 1024 rows are read completely before they are written
+            for (int i0 = 0; i0 < n; i0 += 1024) {
+                const int i = i0 + tid;
+                float4 bx; float sc = 0.f; int lb = 0, ai = 0;
+                if (i < n) { bx = P.box[from + i]; sc = P.score[from + i]; lb = P.label[from + i]; ai = P.aidx[from + i]; }
+                __syncthreads();
+                if (i < n) { P.box[base + at + i] = bx; P.score[base + at + i] = sc; P.label[base + at + i] = lb; P.aidx[base + at + i] = ai; }
+                __syncthreads();
+            }
+        }
+        at += n;
+    }
+    if (tid == 0) { P.img_start[b] = (int)base; P.img_count[b] = at; }
 }
 
 // Coordinate-trick arithmetic on per-level segments: torchvision shifts level l by l * (max coordinate of the
@@ -616,11 +662,16 @@ struct RpnWs {
     long long* keep; int* keep_count; float* units;
     void* nms; size_t nms_bytes;
     void* sel; size_t sel_bytes;
+    int* img_start; int* img_count;
 };
 // NMS scratch: B*L segments of <= pre_k boxes for either batched_nms strategy
 size_t rpn_nms_bytes(int batch, int levels, int pre_k) {
     const size_t T = (size_t)batch * levels * pre_k;
-    return nms_scratch_bytes(T, (size_t)batch * levels, (size_t)pre_k);
+    const size_t per_level = nms_scratch_bytes(T, (size_t)batch * levels, (size_t)pre_k);
+    // many-class heads run ONE segment of up to levels * pre_k boxes per image (bounded by the 16384-row sort capacity)
+    const size_t ktot = (size_t)levels * pre_k < 16384 ? (size_t)levels * pre_k : 16384;
+    const size_t per_image = nms_scratch_bytes(T, (size_t)batch, ktot);
+    return per_level > per_image ? per_level : per_image;
 }
 size_t rpn_carve(int batch, int total, int levels, int pre_k, void* base, size_t bytes, RpnWs* w) {
     const size_t T = (size_t)batch * levels * pre_k;   // worst case rows (>= B*Ktot)
@@ -632,6 +683,7 @@ size_t rpn_carve(int batch, int total, int levels, int pre_k, void* base, size_t
     t.seg_start = (int*)take(4 * (size_t)batch * levels); t.seg_count = (int*)take(4 * (size_t)batch * levels);
     t.keep = (long long*)take(8 * T); t.keep_count = (int*)take(4 * (size_t)batch * levels);
     t.units = (float*)take(4 * (size_t)batch * levels);
+    t.img_start = (int*)take(4 * (size_t)batch); t.img_count = (int*)take(4 * (size_t)batch);
     t.nms_bytes = rpn_nms_bytes(batch, levels, pre_k);
     t.nms = take(t.nms_bytes);
     t.sel_bytes = rpn_select_ws_bytes(batch, total, levels, pre_k);
@@ -696,12 +748,18 @@ size_t rpn_workspace_bytes(int batch, int total, int num_levels, int pre_k) {
     return rpn_carve(batch, total, num_levels, pre_k, nullptr, 0, nullptr) + 256;
 }
 
-int launch_rpn_filter(const float* objectness, const float* deltas, const float* anchors, const float* proposals, int batch,
-                      int total, const int* level_sizes_host, int num_levels, const float* image_hw,
-                      int pre_k, int post_k, double nms_thr, float score_thr, float min_size, int nms_mode,
-                      float* out_boxes, float* out_scores, int* out_index, int* out_count,
-                      void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+// `classes` == 1: the RPN filter (labels = level, one NMS segment per image and level).  `classes` > 1: the many-class
+// head of RetinaNet (retinanet.py:414-472): levels are [anchors_l, classes] logits scaled by `class_scale`, strict
+// score threshold, label = class, ONE class-aware NMS segment per image, labels returned.
+int launch_rpn_filter_ex(const float* objectness, const float* deltas, const float* anchors, const float* proposals, int batch,
+                         int total, const int* level_sizes_host, int num_levels, const float* image_hw,
+                         int pre_k, int post_k, double nms_thr, float score_thr, float min_size, int nms_mode,
+                         float* out_boxes, float* out_scores, int* out_index, int* out_count,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream, int classes,
+                         const float* class_scale, int* out_labels) {
     RpnParams P{};
+    P.C = classes; P.atotal = total / classes; P.class_scale = class_scale; P.strict_thr = classes > 1; P.label_class = classes > 1;
+    P.out_labels = out_labels;
     P.obj = objectness; P.deltas = deltas; P.anchors = anchors; P.proposals = proposals; P.image_hw = image_hw;
     P.B = batch; P.total = total; P.L = num_levels; P.pre_k = pre_k; P.post_k = post_k;
     P.score_thr = score_thr; P.min_size = min_size;
@@ -709,7 +767,9 @@ int launch_rpn_filter(const float* objectness, const float* deltas, const float*
     for (int l = 0; l < num_levels; ++l) {
         const int n = level_sizes_host[l];
         if (n < 1) return B200_ERR_INVALID;
+        if (n % classes) return B200_ERR_INVALID;
         P.level_off[l] = off; P.level_n[l] = n;
+        P.level_aoff[l] = off / classes;
         P.level_k[l] = n < pre_k ? n : pre_k;
         P.level_koff[l] = koff;
         off += n; koff += P.level_k[l];
@@ -723,6 +783,7 @@ int launch_rpn_filter(const float* objectness, const float* deltas, const float*
     P.box = w.box; P.score = w.score; P.label = w.label; P.aidx = w.aidx;
     P.seg_start = w.seg_start; P.seg_count = w.seg_count;
     P.keep = w.keep; P.keep_count = w.keep_count;
+    P.img_start = w.img_start; P.img_count = w.img_count;
     P.out_boxes = out_boxes; P.out_scores = out_scores; P.out_index = out_index; P.out_count = out_count;
 
     const int rcs = launch_rpn_select(P, kmax, w.sel, w.sel_bytes, stream);
@@ -730,6 +791,26 @@ int launch_rpn_filter(const float* objectness, const float* deltas, const float*
 
     NmsParams np{};
     const size_t T = (size_t)batch * P.Ktot;
+    if (classes > 1) {
+        // class-aware NMS over the whole image (batched_nms(image_boxes, image_scores, image_labels), retinanet.py:463)
+        k_rpn_compact<<<batch, 1024, 0, stream>>>(P);
+        if (!nms_carve_scratch(&np, T, (size_t)batch, (size_t)P.Ktot, w.nms, w.nms_bytes)) return B200_ERR_WORKSPACE;
+        np.boxes = reinterpret_cast<const float*>(w.box); np.scores = w.score; np.labels = w.label;
+        np.keep = w.keep; np.labels_out = nullptr; np.keep_count = w.keep_count;
+        np.thr_f = (float)nms_thr; np.thr_d = nms_thr;
+        np.from_slab = 0;
+        np.max_seg = P.Ktot;
+        np.seg_offsets = w.img_start; np.seg_counts = w.img_count;
+        np.mode = nms_mode;
+        P.segs_per_img = 1;
+        P.seg_start = w.img_start;
+        const int rc1 = launch_nms(np, batch, stream);
+        if (rc1 != B200_OK) return rc1;
+        static SmemOptIn optin4;
+        if (optin4.ensure(k_rpn_finish, 16384 * 8) != cudaSuccess) return B200_ERR_CUDA;
+        k_rpn_finish<<<batch, 1024, sizeof(unsigned long long) * (size_t)(P.Ktot > 0 ? P.Ktot : 1), stream>>>(P);
+        return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+    }
     const bool trick = nms_mode == B200_NMS_TV_TRICK;
     const int nseg = batch * num_levels;             // one segment per (image, level) for either strategy
     const int max_seg = kmax;
@@ -757,11 +838,22 @@ int launch_rpn_filter(const float* objectness, const float* deltas, const float*
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }
 
+int launch_rpn_filter(const float* objectness, const float* deltas, const float* anchors, const float* proposals, int batch,
+                      int total, const int* level_sizes_host, int num_levels, const float* image_hw,
+                      int pre_k, int post_k, double nms_thr, float score_thr, float min_size, int nms_mode,
+                      float* out_boxes, float* out_scores, int* out_index, int* out_count,
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    return launch_rpn_filter_ex(objectness, deltas, anchors, proposals, batch, total, level_sizes_host, num_levels, image_hw, pre_k,
+                                post_k, nms_thr, score_thr, min_size, nms_mode, out_boxes, out_scores, out_index, out_count,
+                                workspace, workspace_bytes, stream, 1, nullptr, nullptr);
+}
+
 // RegionProposalNetwork._get_top_n_idx (rpn.py:215-228): per level the indices of the top min(pre_k, n_l) raw objectness
 // logits in descending order, offset by the level start; out [B, sum_l min(pre_k, n_l)] int64
 int launch_rpn_topk(const float* objectness, int batch, int total, const int* level_sizes_host, int num_levels, int pre_k,
                     long long* out_index, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     RpnParams P{};
+    P.C = 1; P.atotal = total;
     P.obj = objectness; P.B = batch; P.total = total; P.L = num_levels; P.pre_k = pre_k;
     int off = 0, koff = 0, kmax = 0;
     for (int l = 0; l < num_levels; ++l) {

@@ -647,6 +647,39 @@ def roi_postprocess(class_logits: Tensor, box_regression: Tensor, proposals: Seq
 
 
 @_device_guard
+def retinanet_postprocess(cls_logits: Tensor, bbox_regression: Tensor, anchors: Tensor, level_anchors: Sequence[int],
+                          image_shapes, tfidf: Optional[Tensor] = None, score_thresh: float = 0.05,
+                          topk_candidates: int = 1000, nms_thresh: float = 0.5, detections_per_img: int = 300,
+                          nms_mode: int = NMS_TV_AUTO):
+    """RetinaNet.postprocess_detections (retinanet.py:414-472) for the whole batch.  cls_logits [B, sumA, C],
+    bbox_regression [B, sumA, 4], anchors [sumA, 4].  -> boxes [B,D,4], scores [B,D], labels [B,D] i32, count [B] i32."""
+    lib = _lib.load()
+    cls_logits = _need_cuda(cls_logits, "cls_logits", torch.float32)
+    bbox_regression = _need_cuda(bbox_regression, "bbox_regression", torch.float32)
+    anchors = _need_cuda(anchors, "anchors", torch.float32)
+    b, total, c = cls_logits.shape
+    dev = cls_logits.device
+    if bbox_regression.shape != (b, total, 4) or anchors.shape != (total, 4) or sum(level_anchors) != total:
+        raise RuntimeError("cls_logits / bbox_regression / anchors / level sizes disagree")
+    hw = torch.tensor([[float(h), float(w)] for h, w in image_shapes], dtype=torch.float32, device=dev)
+    if tfidf is not None:
+        tfidf = torch.as_tensor(tfidf, dtype=torch.float32, device=dev).expand(c).contiguous()
+    lv = (C.c_int32 * len(level_anchors))(*[int(v) for v in level_anchors])
+    d = int(detections_per_img)
+    boxes = torch.zeros((b, d, 4), dtype=torch.float32, device=dev)
+    scores = torch.zeros((b, d), dtype=torch.float32, device=dev)
+    labels = torch.zeros((b, d), dtype=torch.int32, device=dev)
+    count = torch.zeros((b,), dtype=torch.int32, device=dev)
+    ws = workspace(lib.b200_retinanet_workspace_bytes(b, total, c, len(level_anchors), int(topk_candidates)), dev, "retina")
+    _lib.check(lib.b200_retinanet_postprocess(_ptr(cls_logits), _ptr(bbox_regression), _ptr(anchors), b, total, c, lv,
+                                              len(level_anchors), _ptr(tfidf), _ptr(hw), int(topk_candidates),
+                                              float(np.float32(score_thresh)), float(nms_thresh), int(nms_mode), d,
+                                              _ptr(boxes), _ptr(scores), _ptr(labels), _ptr(count), _ptr(ws), ws.numel(),
+                                              _stream()), "b200_retinanet_postprocess")
+    return boxes, scores, labels, count
+
+
+@_device_guard
 def emit_results(det: Tensor, det_count: Tensor, img_hw: Tensor, image_id: Tensor, inp_dim: float,
                  class_map: Optional[Tensor] = None, strict_reference: bool = True):
     """b200_emit_results: packed evaluation records of a whole batch.  -> (records [B*max_det, 6] fp32,

@@ -204,6 +204,25 @@ def rpn_inputs(seed: int, batch: int, img_h: int = 800, img_w: int = 1344):
     return obj, deltas, anchors, per_level
 
 
+def retina_inputs(seed: int, batch: int, img_h: int, img_w: int, num_classes: int):
+    """Head outputs of a RetinaNet-style many-class head on the FPN anchor layout of ``rpn_anchors``:
+    ``cls_logits [B, sumA, C]`` ~ N(-5, 1.2^2) (a few percent pass sigmoid > 0.05: the large levels overflow the
+    1000-candidate top-k, the small ones do not) with clustered boosts so that the class-aware NMS has duplicates to
+    suppress, ``bbox_regression [B, sumA, 4]`` ~ N(0, 0.3^2), ``anchors [sumA, 4]``, anchors per level."""
+    g = _rng(seed)
+    anchors, per_level = rpn_anchors(img_h, img_w)
+    n = anchors.shape[0]
+    logits = g.standard_normal((batch, n, num_classes), dtype=np.float32) * np.float32(1.2) - np.float32(5.0)
+    regs = g.standard_normal((batch, n, 4), dtype=np.float32) * np.float32(0.3)
+    cx, cy = (anchors[:, 0] + anchors[:, 2]) * 0.5, (anchors[:, 1] + anchors[:, 3]) * 0.5
+    for b in range(batch):
+        for _ in range(int(g.integers(3, 8))):
+            ox, oy = g.uniform(0.2, 0.8) * img_w, g.uniform(0.2, 0.8) * img_h
+            near = np.nonzero((np.abs(cx - ox) < 24) & (np.abs(cy - oy) < 24))[0]
+            logits[b, near, int(g.integers(0, num_classes))] += np.float32(6.0) + g.standard_normal(near.shape[0]).astype(np.float32)
+    return logits, regs, anchors, per_level
+
+
 def roi_inputs(seed: int, rows_per_image: Sequence[int], num_classes: int, img_h: int = 800, img_w: int = 1216):
     """Box-head outputs of a Faster R-CNN ROI head: ``class_logits [R, C]`` (background column 0 dominant except for
     a few foreground rows per cluster), ``box_regression [R, 4C]`` ~ N(0, 0.5^2), ``proposals`` list of ``[r_i, 4]``

@@ -246,3 +246,39 @@ def ssd_matcher(quality: Tensor, threshold: float) -> Tensor:
     best_pred = quality.max(dim=1)[1]
     matches[best_pred] = torch.arange(best_pred.size(0), dtype=torch.int64)
     return matches
+
+
+def retinanet_postprocess(cls_logits: Tensor, bbox_regression: Tensor, anchors: Tensor, level_anchors: Sequence[int],
+                          image_shapes, tfidf, score_thresh: float = 0.05, topk_candidates: int = 1000,
+                          nms_thresh: float = 0.5, detections_per_img: int = 300, strategy: str = "torchvision"):
+    """RetinaNet.postprocess_detections (retinanet.py:414-472), same torch CPU ops in the same order.
+    cls_logits [B, sumA, C]; returns per image (boxes, scores, labels)."""
+    out = []
+    scale = tfidf if tfidf is not None else 1.0
+    for b in range(cls_logits.shape[0]):
+        ib, isc, il = [], [], []
+        for lg, rg, an in zip((cls_logits[b] * scale).split(list(level_anchors), 0), bbox_regression[b].split(list(level_anchors), 0),
+                              anchors.split(list(level_anchors), 0)):
+            c = lg.shape[-1]
+            s = torch.sigmoid(lg).flatten()
+            keep = s > score_thresh
+            s = s[keep]
+            idx = torch.where(keep)[0]
+            k = min(topk_candidates, idx.size(0))
+            s, order = s.topk(k)
+            idx = idx[order]
+            a_idx, lab = idx // c, idx % c
+            bx = decode_single(rg[a_idx], an[a_idx])
+            h, w = image_shapes[b]
+            bx = torch.stack((bx[:, 0].clamp(0, w), bx[:, 1].clamp(0, h), bx[:, 2].clamp(0, w), bx[:, 3].clamp(0, h)), 1)
+            ib.append(bx); isc.append(s); il.append(lab)
+        ib, isc, il = torch.cat(ib), torch.cat(isc), torch.cat(il)
+        if strategy == "vanilla":
+            keep = batched_nms_vanilla(ib, isc, il, nms_thresh)
+        elif strategy == "coordinate_trick":
+            keep = batched_nms_coordinate_trick(ib, isc, il, nms_thresh)
+        else:
+            keep = batched_nms_vanilla(ib, isc, il, nms_thresh) if ib.numel() > 4000 else batched_nms_coordinate_trick(ib, isc, il, nms_thresh)
+        keep = keep[:detections_per_img]
+        out.append((ib[keep], isc[keep], il[keep]))
+    return out

@@ -5,6 +5,7 @@ outputs are committed).
 
   legacy_yolo_loss.npz : YOLOLoss.forward(input) of yolo/nets/yolo_loss.py (inference branch), two heads
   legacy_get_target.npz: YOLOLoss.get_target of yolo/nets/yolo_loss.py:107-161 (mask, noobj_mask, tx, ty, tw, th, tconf, tcls)
+  retinanet_postprocess.npz : RetinaNet.postprocess_detections of torchvision_models/tvision/retinanet.py:414-472
   roi_postprocess.npz  : RoIHeads.postprocess_detections of torchvision_models/tvision/roi_heads.py for the three
                          activations (ce / gombit / sigmoid), tfidf on, COCO-91 shaped head
 
@@ -97,9 +98,33 @@ def roi():
     np.savez_compressed(os.path.join(HERE, "roi_postprocess.npz"), **pack)
 
 
+def retinanet():
+    """The reference's RetinaNet post-process on seeded head outputs (two images, five levels, tfidf on)."""
+    sys.path.insert(0, os.path.join(REF, "torchvision_models"))
+    from tvision import retinanet as ref_retina
+    from torchvision.models.detection import _utils as det_utils
+    C = 91
+    r = ref_retina.RetinaNet.__new__(ref_retina.RetinaNet)
+    torch.nn.Module.__init__(r)
+    r.tfidf_post = torch.from_numpy(np.linspace(0.6, 1.8, C).astype(np.float32))
+    r.score_thresh, r.topk_candidates, r.nms_thresh, r.detections_per_img = 0.05, 1000, 0.5, 300
+    r.box_coder = det_utils.BoxCoder(weights=(1.0, 1.0, 1.0, 1.0))
+    logits, regs, anchors, per_level = syn.retina_inputs(61, 2, 256, 320, C)
+    tl, tr, ta = torch.from_numpy(logits), torch.from_numpy(regs), torch.from_numpy(anchors)
+    head = {"cls_logits": list(tl.split(per_level, 1)), "bbox_regression": list(tr.split(per_level, 1))}
+    out = r.postprocess_detections(head, [list(ta.split(per_level, 0)) for _ in range(2)], [(256, 320)] * 2)
+    pack = {"args": np.array([61, 2, 256, 320, C]), "idf": r.tfidf_post.numpy()}
+    for i, o in enumerate(out):
+        pack[f"boxes_{i}"] = o["boxes"].numpy()
+        pack[f"scores_{i}"] = o["scores"].numpy()
+        pack[f"labels_{i}"] = o["labels"].numpy()
+    np.savez_compressed(os.path.join(HERE, "retinanet_postprocess.npz"), **pack)
+
+
 if __name__ == "__main__":
     legacy()
+    retinanet()
     legacy_get_target()
     roi()
-    for f in ("legacy_yolo_loss.npz", "legacy_get_target.npz", "roi_postprocess.npz"):
+    for f in ("legacy_yolo_loss.npz", "legacy_get_target.npz", "retinanet_postprocess.npz", "roi_postprocess.npz"):
         print(f"  {f:32s} {os.path.getsize(os.path.join(HERE, f)):>9d} B")

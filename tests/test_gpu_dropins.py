@@ -513,3 +513,39 @@ def test_fused_box_iou_matcher(m, n, seed):
     from object_detectors_b200 import ops
     _, vals = ops.match_boxes(tg.cuda(), tp.cuda(), 0.7, 0.3, return_vals=True)
     np.testing.assert_array_equal(vals.cpu().numpy(), q.max(dim=0)[0].numpy())
+
+
+@pytest.mark.parametrize("strategy", ["vanilla", "coordinate_trick", "torchvision"])
+def test_retinanet_postprocess_detections_bound_like_the_reference(strategy, nms_path):
+    """RetinaNet.postprocess_detections (retinanet.py:414-472) bound onto a RetinaNet-like object, against the oracle
+    (pinned bit-exactly to the reference by tests/test_oracle_golden.py) and -- for the installed torchvision's own
+    strategy switch -- against the reference's golden output itself: labels and counts exact, boxes
+    |d| <= 1e-5 * max(|ref|, img), scores 1e-5 relative."""
+    from object_detectors_b200 import _lib
+    from object_detectors_b200.tvision import retinanet as b200_retina
+    gold = np.load(os.path.join(G, "retinanet_postprocess.npz"))
+    seed, bsz, ih, iw, c = [int(v) for v in gold["args"]]
+    logits, regs, anchors, per_level = syn.retina_inputs(seed, bsz, ih, iw, c)
+    idf = torch.from_numpy(gold["idf"])
+    tl, tr, ta = torch.from_numpy(logits), torch.from_numpy(regs), torch.from_numpy(anchors)
+    head = {"cls_logits": [t.cuda() for t in tl.split(per_level, 1)], "bbox_regression": [t.cuda() for t in tr.split(per_level, 1)]}
+    fake_self = types.SimpleNamespace(tfidf_post=idf.cuda(), score_thresh=0.05, topk_candidates=1000, nms_thresh=0.5,
+                                      detections_per_img=300)
+    lib = _lib.load()
+    if strategy == "torchvision":
+        lib.b200_set_batched_nms_auto_limit(4000)        # the CPU oracle's switch point
+    try:
+        got = b200_retina.postprocess_detections(fake_self, head, [[a.cuda() for a in ta.split(per_level, 0)]] * bsz,
+                                                 [(ih, iw)] * bsz, strategy=strategy)
+    finally:
+        lib.b200_set_batched_nms_auto_limit(100000)
+    ref = tv_ref.retinanet_postprocess(tl, tr, ta, per_level, [(ih, iw)] * bsz, idf, strategy=strategy)
+    for i, (rb, rs, rl) in enumerate(ref):
+        assert got[i]["boxes"].shape[0] == rb.shape[0] > 0
+        np.testing.assert_array_equal(got[i]["labels"].cpu().numpy(), rl.numpy())
+        s, b = got[i]["scores"].cpu().numpy(), got[i]["boxes"].cpu().numpy()
+        assert np.all(np.abs(s - rs.numpy()) <= 1e-5 * np.abs(rs.numpy()) + 1e-12)
+        assert np.all(np.abs(b - rb.numpy()) <= 1e-5 * np.maximum(np.abs(rb.numpy()), max(ih, iw)))
+        if strategy == "torchvision":
+            np.testing.assert_array_equal(got[i]["labels"].cpu().numpy(), gold[f"labels_{i}"])
+            assert np.all(np.abs(b - gold[f"boxes_{i}"]) <= 1e-5 * np.maximum(np.abs(gold[f"boxes_{i}"]), max(ih, iw)))

@@ -172,3 +172,22 @@ def test_roi_postprocess(tag, activation):
         np.testing.assert_array_equal(l.numpy(), gold[f"{tag}_labels_{i}"])
         np.testing.assert_array_equal(s.numpy(), gold[f"{tag}_scores_{i}"])
         np.testing.assert_array_equal(b.numpy(), gold[f"{tag}_boxes_{i}"])
+
+
+def test_retinanet_postprocess_oracle_matches_reference_golden():
+    """oracle/tv_ref.retinanet_postprocess == the UNMODIFIED reference's RetinaNet.postprocess_detections
+    (tests/golden/retinanet_postprocess.npz, written by make_golden_extra.py), bit for bit."""
+    import os
+    import numpy as np
+    import torch
+    from object_detectors_b200 import synthetic as syn
+    from oracle import tv_ref
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "retinanet_postprocess.npz"))
+    seed, bsz, ih, iw, c = [int(v) for v in g["args"]]
+    logits, regs, anchors, per_level = syn.retina_inputs(seed, bsz, ih, iw, c)
+    out = tv_ref.retinanet_postprocess(torch.from_numpy(logits), torch.from_numpy(regs), torch.from_numpy(anchors), per_level,
+                                       [(ih, iw)] * bsz, torch.from_numpy(g["idf"]))
+    for i, (b, s, l) in enumerate(out):
+        np.testing.assert_array_equal(b.numpy(), g[f"boxes_{i}"])
+        np.testing.assert_array_equal(s.numpy(), g[f"scores_{i}"])
+        np.testing.assert_array_equal(l.numpy(), g[f"labels_{i}"])
