@@ -36,12 +36,16 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--long", type=int, default=1000)
     ap.add_argument("--gen", default="clustered")
+    ap.add_argument("--resolve", default="", help="general NMS path: resolve CTA shape 'threads,smem_kb' (b200_debug_set_resolve)")
+    ap.add_argument("--timeline", action="store_true", help="print decode start/end and NMS end of every timed step (split mode)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     lib = _lib.load()
     lib.b200_set_decode_variant(3)
     lib.b200_debug_set_ring(*[int(x) for x in args.ring.split(",")])
     lib.b200_debug_set_nms_path(1 if args.nms == "general" else 0)
+    if args.resolve:
+        lib.b200_debug_set_resolve(*[int(x) for x in args.resolve.split(",")])
     heads = [torch.from_numpy(h).to(dev) for h in syn.yolo_heads(1000, BATCH, IMG, NC, syn.COCO_ANCHORS, args.gen)]
     idf = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "idf_coco_smooth.npy"))).to(dev)
     grids = [h.shape[2] for h in heads]
@@ -105,11 +109,34 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b)
 
+    if args.timeline and args.split:
+        import ctypes as C
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        for row in evs:
+            for e in row:
+                e.record()
+        torch.cuda.synchronize()
+        base_step = step
+
+        def step(i, _b=base_step):      # noqa: F811
+            lib.b200_debug_set_decode_events(C.c_void_p(evs[i][0].cuda_event), C.c_void_p(evs[i][1].cuda_event))
+            _b(i)
+            evs[i][2].record(ns[i % n_n])
+        run(args.steps, args.warmup)
+        t0 = torch.cuda.Event(enable_timing=True)
+        ms0 = run.__globals__ if False else None
     ms = [run(args.steps, args.warmup) for _ in range(args.reps)]
+    if args.timeline and args.split:
+        lib.b200_debug_set_decode_events(None, None)
+        ref = evs[0][0]
+        print("step | decode start .. end (dur) | nms end (after decode end)")
+        for i, (a, b, c) in enumerate(evs):
+            ta, tb, tc = ref.elapsed_time(a) * 1e3, ref.elapsed_time(b) * 1e3, ref.elapsed_time(c) * 1e3
+            print(f"{i:4d} | {ta:8.1f} .. {tb:8.1f} ({tb - ta:6.1f}) | {tc:8.1f} (+{tc - tb:6.1f})")
     for pl in plans:
         pl.check_status()
     long_ms = run(args.long, 10) if args.long else 0.0
-    print(json.dumps({"ring": args.ring, "chains": args.chains, "split": args.split, "nms": args.nms, "steps": args.steps,
+    print(json.dumps({"ring": args.ring, "chains": args.chains, "split": args.split, "nms": args.nms, "steps": args.steps, "resolve": args.resolve,
                       "ms": [round(m, 4) for m in ms], "img_per_s_best": BATCH * args.steps / (min(ms) * 1e-3),
                       "img_per_s_first": BATCH * args.steps / (ms[0] * 1e-3),
                       "us_per_step_20": 1e3 * float(np.median(ms)) / args.steps,

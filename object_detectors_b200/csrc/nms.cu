@@ -296,16 +296,28 @@ __device__ __forceinline__ void pair_tile(const NmsParams& P, int seg, int rt, i
     const int tid = threadIdx.x;
     const int r = tid >> 2, cg = tid & 3;
     unsigned long long* dom = P.dom + (size_t)seg * (size_t)P.max_seg * (size_t)P.max_words;
+    // degenerate boxes (zero / negative / non-finite area, NaN coordinates) can yield NaN IoU, which the majority rule
+    // treats as "removed": a tile that holds one never uses the cheap reject below
+    int bad = 0;
     if (tid < 64) {
         const int i = rt * 64 + tid;
-        if (i < n) { const Item it = load_item<SLAB>(P, off, i, unit); S.rb[tid] = it.b; S.ra[tid] = it.area; S.rk[tid] = it.key; S.rl[tid] = it.label; }
+        if (i < n) {
+            const Item it = load_item<SLAB>(P, off, i, unit);
+            S.rb[tid] = it.b; S.ra[tid] = it.area; S.rk[tid] = it.key; S.rl[tid] = it.label;
+            bad = !(it.area > 0.f) || !(it.area < 3.0e38f) || !(it.b.x == it.b.x) || !(it.b.y == it.b.y) || !(it.b.z == it.b.z) || !(it.b.w == it.b.w);
+        }
     } else if (tid < 128) {
         const int j = ct * 64 + tid - 64;
-        if (j < n) { const Item it = load_item<SLAB>(P, off, j, unit); S.cb[tid - 64] = it.b; S.ca[tid - 64] = it.area; S.ck[tid - 64] = it.key; S.cl[tid - 64] = it.label; }
+        if (j < n) {
+            const Item it = load_item<SLAB>(P, off, j, unit);
+            S.cb[tid - 64] = it.b; S.ca[tid - 64] = it.area; S.ck[tid - 64] = it.key; S.cl[tid - 64] = it.label;
+            bad = !(it.area > 0.f) || !(it.area < 3.0e38f) || !(it.b.x == it.b.x) || !(it.b.y == it.b.y) || !(it.b.z == it.b.z) || !(it.b.w == it.b.w);
+        }
     } else {
         S.trans[tid - 128] = 0u;
     }
-    __syncthreads();
+    const bool filter = __syncthreads_or(bad) == 0 && P.thr_f > 0.f;
+    const float fthr = 0.999f * P.thr_f;
     const int i = rt * 64 + r;
     unsigned long long bits = 0ull;
     if (i < n) {
@@ -313,13 +325,24 @@ __device__ __forceinline__ void pair_tile(const NmsParams& P, int seg, int rt, i
         const float ai = S.ra[r];
         const unsigned long long ki = S.rk[r];
         const int li = S.rl[r];
+        const float tai = fthr * ai;
 #pragma unroll 4
         for (int c = 0; c < 16; ++c) {
             const int cc = c * 4 + cg;            // the 4 threads of a row read adjacent columns
             const int j = ct * 64 + cc;
             if (j < n && (rt != ct || cc > r)) {
+                const float4 bj = S.cb[cc];
+                const float aj = S.ca[cc];
+                if (filter) {
+                    // IoU <= inter / max(area): a pair whose intersection is clearly below thr * max(area) cannot
+                    // suppress (margin 1e-3, far above any fp32 rounding).  One clamp is enough: with w >= 0 a
+                    // negative h makes the product <= 0, below the positive bound.
+                    const float w = fmaxf(fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x), 0.f);
+                    const float h = fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y);
+                    if (w * h < fmaxf(tai, fthr * aj)) continue;
+                }
                 const bool i_first = ki < S.ck[cc];
-                if (pair_hit<MODE>(P, bi, ai, li, S.cb[cc], S.ca[cc], S.cl[cc], i_first)) {
+                if (pair_hit<MODE>(P, bi, ai, li, bj, aj, S.cl[cc], i_first)) {
                     if (i_first) atomicOr(&S.trans[2 * cc + (r >> 5)], 1u << (r & 31));   // i dominates j
                     else bits |= 1ull << cc;                                              // j dominates i
                 }
