@@ -370,6 +370,19 @@ int b200_retinanet_postprocess(const float* cls_logits, const float* bbox_regres
                                float* out_boxes, float* out_scores, int32_t* out_labels, int32_t* out_count,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* SSD.postprocess_detections (ssd.py:386-430) for a whole batch: scores = softmax(tfidf * cls_logits) over all classes,
+ * ONE box per anchor (BoxCoder.decode_single with `weights_host`, clipped to the image), per foreground class the
+ * candidates with score > score_thr capped at topk_per_class by score (ssd.py:404-409), class-aware batched_nms, the
+ * first max_det by score.  cls_logits [R, C], bbox_regression [R, 4], anchors [R, 4] (rows of image b =
+ * [row_offsets[b], row_offsets[b+1])); det [B, max_det, 6] = x1,y1,x2,y2,score,label; workspace / capacity / status as
+ * b200_roi_postprocess (overflow of the candidate slab is reported in status bit 0, cand_count holds the true counts). */
+int b200_ssd_postprocess(const float* cls_logits, const float* bbox_regression, const float* anchors,
+                         const int32_t* row_offsets, int32_t batch, int32_t total_rows, int32_t num_classes,
+                         const float* image_hw, const float* tfidf, const float* weights_host, float xform_clip,
+                         float score_thr, int32_t topk_per_class, double nms_thr, int32_t nms_mode, int32_t capacity,
+                         int32_t max_det, float* det, int32_t* det_count, int32_t* cand_count, int32_t* status,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* box_iou + Matcher fused (rpn.py:192-193, roi_heads.py:633-634, retinanet.py:409-410, ssd.py:371-372):
  *   matches = Matcher(high, low, allow_low_quality)(box_iou(gt_boxes, boxes))        (_utils.py:271-344)
  * without ever writing the [M, N] quality matrix; bit-identical to that composition (torchvision's IoU arithmetic,

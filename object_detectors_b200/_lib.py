@@ -76,6 +76,8 @@ SIGNATURES = {
     "b200_retinanet_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "b200_retinanet_postprocess": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, C.POINTER(C.c_int32), _i32, _p, _p, _i32, _f32, _f64, _i32,
                                              _i32, _p, _p, _p, _p, _p, _sz, _p]),
+    "b200_ssd_postprocess": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, C.POINTER(C.c_float), _f32, _f32, _i32, _f64, _i32,
+                                       _i32, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "b200_match_boxes_workspace_bytes": (_sz, [_i32, _i32]),
     "b200_match_boxes": (C.c_int, [_p, _i32, _p, _i32, _f32, _f32, _i32, _i32, _p, _p, _p, _sz, _p]),
     "b200_matcher_ssd_override": (C.c_int, [_p, _i32, _i32, _p, _p, _sz, _p]),

@@ -78,6 +78,8 @@ struct RoiParams {
     int cap;
     int* count;
     int* status;
+    int shared_deltas;        // 1: deltas [R, 4], one box per row for every class (SSD); 0: [R, 4C] (ROI heads)
+    int class_major;          // canonical candidate order: 1 = (class, row) (SSD's per-class loop), 0 = (row, class)
 };
 
 __device__ __forceinline__ int image_of_row(const int* off, int B, int r) {
@@ -133,7 +135,7 @@ k_roi_candidates(const __grid_constant__ RoiParams p) {
                 score = __fdiv_rn(1.0f, expf(expf(z)));
             }
             if (score > p.score_thr) {                                                    // :763
-                const float4 d = reinterpret_cast<const float4*>(p.deltas)[(size_t)r * C + c];
+                const float4 d = reinterpret_cast<const float4*>(p.deltas)[p.shared_deltas ? (size_t)r : (size_t)r * C + c];
                 const float dx = __fdiv_rn(d.x, p.wx), dy = __fdiv_rn(d.y, p.wy);          // _utils.py:205-208
                 const float dw = fminf(__fdiv_rn(d.z, p.ww), p.clip), dh = fminf(__fdiv_rn(d.w, p.wh), p.clip);
                 const float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, h), cy);
@@ -158,9 +160,69 @@ k_roi_candidates(const __grid_constant__ RoiParams p) {
         float4* d4 = reinterpret_cast<float4*>(p.slab + (size_t)b * (size_t)p.cap + (size_t)slot);
         d4[0] = make_float4(q.x1, q.y1, q.x2, q.y2);
         // canonical order inside the image = the reference's flattened (row, class) order
-        const int flat = (r - p.row_offsets[b]) * (C - 1) + (c - 1);
+        const int rows_b = p.row_offsets[b + 1] - p.row_offsets[b];
+        const int flat = p.class_major ? (c - 1) * rows_b + (r - p.row_offsets[b]) : (r - p.row_offsets[b]) * (C - 1) + (c - 1);
         d4[1] = make_float4(score, __int_as_float(c), __int_as_float(flat), 0.f);
     }
+}
+
+// SSD keeps at most `topk` candidates PER CLASS (score.topk(min(topk_candidates, n)), ssd.py:407-409) before the
+// NMS.  One CTA per image: class histogram of the slab; classes above the limit (rare) rank their members by
+// (score desc, canonical index asc) and drop the tail; the slab is compacted in place.
+__global__ void __launch_bounds__(1024, 1)
+k_class_topk(Cand* __restrict__ slab_all, int* __restrict__ count, int cap, int C, int topk, int* __restrict__ status) {
+    extern __shared__ int cls_cnt[];                  // [C]
+    __shared__ int s_over, s_scan[32], s_total;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Cand* slab = slab_all + (size_t)b * cap;
+    const int n = min(count[b], cap);
+    for (int c = tid; c < C; c += 1024) cls_cnt[c] = 0;
+    if (tid == 0) s_over = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) atomicAdd(&cls_cnt[slab[i].label], 1);
+    __syncthreads();
+    for (int c = tid; c < C; c += 1024) if (cls_cnt[c] > topk) s_over = 1;
+    __syncthreads();
+    if (!s_over) return;
+    // rank inside the class, one warp per member of an over-full class
+    for (int i = warp; i < n; i += 32) {
+        const Cand ci = slab[i];
+        int keep = 1;
+        if (cls_cnt[ci.label] > topk) {
+            int better = 0;
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int j = j0 + lane;
+                bool bt = false;
+                if (j < n) {
+                    const Cand cj = slab[j];
+                    bt = cj.label == ci.label && (cj.score > ci.score || (cj.score == ci.score && cj.anchor < ci.anchor));
+                }
+                better += __popc(__ballot_sync(kFullMask, bt));
+            }
+            keep = better < topk;
+        }
+        if (lane == 0) slab[i].pad = keep;
+    }
+    __syncthreads();
+    // in-place compaction: chunks of 1024 rows are read completely before they are written (destination <= source)
+    int at = 0;
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + tid;
+        Cand c{};
+        bool keep = false;
+        if (i < n) { c = slab[i]; keep = c.pad != 0; }
+        const unsigned bal = __ballot_sync(kFullMask, keep);
+        if (lane == 0) s_scan[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 32; ++w) { const int v = s_scan[w]; if (w < warp) before += v; total += v; }
+        if (keep) { c.pad = 0; slab[at + before + __popc(bal & ((1u << lane) - 1u))] = c; }
+        at += total;
+        __syncthreads();
+    }
+    // an overflowed slab keeps its TRUE count (status bit 0 is set): the caller sizes the retry from it
+    if (tid == 0 && count[b] <= cap) count[b] = at;
+    (void)status; (void)s_total;
 }
 
 int launch_roi_candidates(const RoiParams& p, cudaStream_t st) {
@@ -235,6 +297,53 @@ int b200_roi_postprocess(const float* class_logits, const float* box_regression,
     np.max_det = max_det;
     np.slab = slab; np.count = count; np.cap = capacity; np.from_slab = 1;
     np.anchor_space = 0;                 // flat (row, class) indices: rank by counting
+    np.max_seg = capacity;
+    return launch_nms(np, batch, st);
+}
+
+// SSD.postprocess_detections (ssd.py:386-430)
+int b200_ssd_postprocess(const float* cls_logits, const float* bbox_regression, const float* anchors,
+                         const int32_t* row_offsets, int32_t batch, int32_t total_rows, int32_t num_classes,
+                         const float* image_hw, const float* tfidf, const float* weights_host, float xform_clip,
+                         float score_thr, int32_t topk_per_class, double nms_thr, int32_t nms_mode, int32_t capacity,
+                         int32_t max_det, float* det, int32_t* det_count, int32_t* cand_count, int32_t* status,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    if (!cls_logits || !bbox_regression || !anchors || !row_offsets || !image_hw || !weights_host || !det || !det_count ||
+        !status || batch < 1 || total_rows < 0 || num_classes < 2 || num_classes > 8192 || capacity < 1 || max_det < 1 ||
+        topk_per_class < 1)
+        return B200_ERR_INVALID;
+    if (nms_mode != B200_NMS_TV_CLASS && nms_mode != B200_NMS_TV_TRICK && nms_mode != B200_NMS_TV_AUTO) return B200_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(anchors) & 15u) || (reinterpret_cast<uintptr_t>(bbox_regression) & 15u)) return B200_ERR_INVALID;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u) || workspace_bytes < b200_roi_workspace_bytes(batch, capacity))
+        return B200_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t T = (size_t)batch * (size_t)capacity;
+    unsigned char* q = reinterpret_cast<unsigned char*>(workspace);
+    int* count = reinterpret_cast<int*>(q);                q += align_up(sizeof(int) * (size_t)batch, 256);
+    Cand* slab = reinterpret_cast<Cand*>(q);               q += align_up(sizeof(Cand) * T, 256);
+    const size_t nms_bytes = nms_scratch_bytes(T, (size_t)batch, (size_t)capacity);
+    B200_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)batch, st));
+    RoiParams p{};
+    p.logits = cls_logits; p.deltas = bbox_regression; p.proposals = anchors; p.row_offsets = row_offsets;
+    p.image_hw = image_hw; p.tfidf = tfidf; p.R = total_rows; p.C = num_classes; p.B = batch; p.activation = 0;
+    p.wx = weights_host[0]; p.wy = weights_host[1]; p.ww = weights_host[2]; p.wh = weights_host[3];
+    p.clip = xform_clip; p.score_thr = score_thr; p.min_size = -INFINITY;       // SSD has no small-box filter
+    p.slab = slab; p.cap = capacity; p.count = count; p.status = status;
+    p.shared_deltas = 1; p.class_major = 1;
+    const int rc = launch_roi_candidates(p, st);
+    if (rc != B200_OK) return rc;
+    k_class_topk<<<batch, 1024, sizeof(int) * (size_t)num_classes, st>>>(slab, count, capacity, num_classes, topk_per_class, status);
+    NmsParams np{};
+    if (!nms_carve_scratch(&np, T, (size_t)batch, (size_t)capacity, q, nms_bytes)) return B200_ERR_WORKSPACE;
+    np.mode = nms_mode;
+    np.thr_f = (float)nms_thr;
+    np.thr_d = nms_thr;
+    np.status = status;
+    np.det = det; np.det_keep = nullptr; np.det_anchor = nullptr; np.det_count = det_count;
+    np.cand_count_out = cand_count;
+    np.max_det = max_det;
+    np.slab = slab; np.count = count; np.cap = capacity; np.from_slab = 1;
+    np.anchor_space = 0;
     np.max_seg = capacity;
     return launch_nms(np, batch, st);
 }

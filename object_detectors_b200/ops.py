@@ -647,6 +647,41 @@ def roi_postprocess(class_logits: Tensor, box_regression: Tensor, proposals: Seq
 
 
 @_device_guard
+def ssd_postprocess(cls_logits: Tensor, bbox_regression: Tensor, image_anchors: Sequence[Tensor], image_shapes,
+                    tfidf: Optional[Tensor] = None, weights=(10.0, 10.0, 5.0, 5.0), xform_clip: float = 4.135166556742356,
+                    score_thresh: float = 0.01, topk_candidates: int = 400, nms_thresh: float = 0.45,
+                    detections_per_img: int = 200, nms_mode: int = NMS_TV_AUTO, capacity: Optional[int] = None):
+    """SSD.postprocess_detections (ssd.py:386-430) for the whole batch.  cls_logits [B, A, C], bbox_regression
+    [B, A, 4], image_anchors list of [A, 4].  -> det [B, D, 6], det_count [B], cand_count [B], status [1]."""
+    lib = _lib.load()
+    cls_logits = _need_cuda(cls_logits, "cls_logits", torch.float32)
+    bbox_regression = _need_cuda(bbox_regression, "bbox_regression", torch.float32)
+    b, a, c = cls_logits.shape
+    dev = cls_logits.device
+    anc = torch.cat([t.to(torch.float32) for t in image_anchors], 0).contiguous()
+    if bbox_regression.shape != (b, a, 4) or anc.shape != (b * a, 4):
+        raise RuntimeError("cls_logits / bbox_regression / anchors disagree")
+    off = torch.arange(0, (b + 1) * a, a, dtype=torch.int32, device=dev)
+    hw = torch.tensor([[float(h), float(w)] for h, w in image_shapes], dtype=torch.float32, device=dev)
+    if tfidf is not None:
+        tfidf = torch.as_tensor(tfidf, dtype=torch.float32, device=dev).expand(c).contiguous()
+    cap = int(capacity or max(1, min(a * (c - 1), ROI_DEFAULT_CAPACITY)))
+    d = int(detections_per_img)
+    det = torch.empty((b, d, 6), dtype=torch.float32, device=dev)
+    dcnt = torch.zeros((b,), dtype=torch.int32, device=dev)
+    ccnt = torch.zeros((b,), dtype=torch.int32, device=dev)
+    status = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ws = workspace(lib.b200_roi_workspace_bytes(b, cap), dev, "roi")
+    w4 = (C.c_float * 4)(*[float(v) for v in weights])
+    _lib.check(lib.b200_ssd_postprocess(
+        _ptr(cls_logits.reshape(b * a, c)), _ptr(bbox_regression.reshape(b * a, 4)), _ptr(anc), _ptr(off), b, b * a, c, _ptr(hw),
+        _ptr(tfidf), w4, float(np.float32(xform_clip)), float(np.float32(score_thresh)), int(topk_candidates), float(nms_thresh),
+        int(nms_mode), cap, d, _ptr(det), _ptr(dcnt), _ptr(ccnt), _ptr(status), _ptr(ws), ws.numel(), _stream()),
+        "b200_ssd_postprocess")
+    return det, dcnt, ccnt, status
+
+
+@_device_guard
 def retinanet_postprocess(cls_logits: Tensor, bbox_regression: Tensor, anchors: Tensor, level_anchors: Sequence[int],
                           image_shapes, tfidf: Optional[Tensor] = None, score_thresh: float = 0.05,
                           topk_candidates: int = 1000, nms_thresh: float = 0.5, detections_per_img: int = 300,

@@ -223,6 +223,30 @@ def retina_inputs(seed: int, batch: int, img_h: int, img_w: int, num_classes: in
     return logits, regs, anchors, per_level
 
 
+def ssd_inputs(seed: int, batch: int, num_anchors: int, num_classes: int, img: int = 300):
+    """Head outputs of an SSD300-style head: ``cls_logits [B, A, C]`` (background column 0 dominant; a few object
+    clusters whose class passes 0.01 on many anchors -- one of them on more than 400, so the per-class top-k bites),
+    ``bbox_regression [B, A, 4]`` ~ N(0, 0.5^2), default boxes ``[A, 4]`` clustered around the objects."""
+    g = _rng(seed)
+    logits = g.standard_normal((batch, num_anchors, num_classes), dtype=np.float32)
+    logits[:, :, 0] += np.float32(10.0)
+    regs = g.standard_normal((batch, num_anchors, 4), dtype=np.float32) * np.float32(0.5)
+    k = 6
+    centres = g.uniform(0.15, 0.85, size=(k, 2)) * img
+    sizes = np.exp(g.uniform(np.log(20), np.log(0.5 * img), size=(k, 2)))
+    which = g.integers(0, k, size=num_anchors)
+    c = centres[which] + g.standard_normal((num_anchors, 2)) * sizes[which] * 0.1
+    s = sizes[which] * np.exp(g.standard_normal((num_anchors, 2)) * 0.15)
+    anchors = np.concatenate([c - s / 2, c + s / 2], 1).astype(np.float32)
+    for b in range(batch):
+        cls = g.integers(1, num_classes, size=k)
+        for j in range(k):
+            rows = np.nonzero(which == j)[0]
+            take = rows if j == 0 else rows[: max(8, len(rows) // 6)]           # cluster 0: every anchor fires (> 400)
+            logits[b, take, cls[j]] += np.float32(6.5) + g.standard_normal(len(take)).astype(np.float32)
+    return logits, regs, anchors
+
+
 def roi_inputs(seed: int, rows_per_image: Sequence[int], num_classes: int, img_h: int = 800, img_w: int = 1216):
     """Box-head outputs of a Faster R-CNN ROI head: ``class_logits [R, C]`` (background column 0 dominant except for
     a few foreground rows per cluster), ``box_regression [R, 4C]`` ~ N(0, 0.5^2), ``proposals`` list of ``[r_i, 4]``

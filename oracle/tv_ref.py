@@ -282,3 +282,35 @@ def retinanet_postprocess(cls_logits: Tensor, bbox_regression: Tensor, anchors: 
         keep = keep[:detections_per_img]
         out.append((ib[keep], isc[keep], il[keep]))
     return out
+
+
+def ssd_postprocess(cls_logits: Tensor, bbox_regression: Tensor, image_anchors: Sequence[Tensor], image_shapes, tfidf,
+                    weights=(10.0, 10.0, 5.0, 5.0), score_thresh: float = 0.01, topk_candidates: int = 400,
+                    nms_thresh: float = 0.45, detections_per_img: int = 200, strategy: str = "torchvision"):
+    """SSD.postprocess_detections (ssd.py:386-430), same torch CPU ops in the same order.  cls_logits [B, A, C];
+    returns per image (boxes, scores, labels)."""
+    scale = tfidf.unsqueeze(0) if tfidf is not None else 1.0
+    pred_scores = torch.softmax(scale * cls_logits, dim=-1)
+    num_classes = pred_scores.size(-1)
+    out = []
+    for boxes, scores, anchors, (h, w) in zip(bbox_regression, pred_scores, image_anchors, image_shapes):
+        boxes = decode_single(boxes, anchors, weights)
+        boxes = torch.stack((boxes[:, 0].clamp(0, w), boxes[:, 1].clamp(0, h), boxes[:, 2].clamp(0, w), boxes[:, 3].clamp(0, h)), 1)
+        ib, isc, il = [], [], []
+        for label in range(1, num_classes):
+            score = scores[:, label]
+            keep = score > score_thresh
+            score, box = score[keep], boxes[keep]
+            k = min(topk_candidates, score.size(0))
+            score, idx = score.topk(k)
+            ib.append(box[idx]); isc.append(score); il.append(torch.full_like(score, fill_value=label, dtype=torch.int64))
+        ib, isc, il = torch.cat(ib), torch.cat(isc), torch.cat(il)
+        if strategy == "vanilla":
+            keep = batched_nms_vanilla(ib, isc, il, nms_thresh)
+        elif strategy == "coordinate_trick":
+            keep = batched_nms_coordinate_trick(ib, isc, il, nms_thresh)
+        else:
+            keep = batched_nms_vanilla(ib, isc, il, nms_thresh) if ib.numel() > 4000 else batched_nms_coordinate_trick(ib, isc, il, nms_thresh)
+        keep = keep[:detections_per_img]
+        out.append((ib[keep], isc[keep], il[keep]))
+    return out

@@ -6,6 +6,7 @@ outputs are committed).
   legacy_yolo_loss.npz : YOLOLoss.forward(input) of yolo/nets/yolo_loss.py (inference branch), two heads
   legacy_get_target.npz: YOLOLoss.get_target of yolo/nets/yolo_loss.py:107-161 (mask, noobj_mask, tx, ty, tw, th, tconf, tcls)
   retinanet_postprocess.npz : RetinaNet.postprocess_detections of torchvision_models/tvision/retinanet.py:414-472
+  ssd_postprocess.npz  : SSD.postprocess_detections of torchvision_models/tvision/ssd.py:386-430
   roi_postprocess.npz  : RoIHeads.postprocess_detections of torchvision_models/tvision/roi_heads.py for the three
                          activations (ce / gombit / sigmoid), tfidf on, COCO-91 shaped head
 
@@ -121,10 +122,34 @@ def retinanet():
     np.savez_compressed(os.path.join(HERE, "retinanet_postprocess.npz"), **pack)
 
 
+def ssd():
+    """The reference's SSD post-process on seeded head outputs (two images, 91 classes, tfidf on, one class over the
+    400-candidate limit)."""
+    sys.path.insert(0, os.path.join(REF, "torchvision_models"))
+    from tvision import ssd as ref_ssd
+    from torchvision.models.detection import _utils as det_utils
+    C, A = 91, 3000
+    r = ref_ssd.SSD.__new__(ref_ssd.SSD)
+    torch.nn.Module.__init__(r)
+    r.tfidf_post = torch.from_numpy(np.linspace(0.6, 1.8, C).astype(np.float32))
+    r.score_thresh, r.topk_candidates, r.nms_thresh, r.detections_per_img = 0.01, 400, 0.45, 200
+    r.box_coder = det_utils.BoxCoder(weights=(10.0, 10.0, 5.0, 5.0))
+    logits, regs, anchors = syn.ssd_inputs(71, 2, A, C)
+    head = {"cls_logits": torch.from_numpy(logits), "bbox_regression": torch.from_numpy(regs)}
+    out = r.postprocess_detections(head, [torch.from_numpy(anchors)] * 2, [(300, 300)] * 2)
+    pack = {"args": np.array([71, 2, A, C, 300]), "idf": r.tfidf_post.numpy()}
+    for i, o in enumerate(out):
+        pack[f"boxes_{i}"] = o["boxes"].numpy()
+        pack[f"scores_{i}"] = o["scores"].numpy()
+        pack[f"labels_{i}"] = o["labels"].numpy()
+    np.savez_compressed(os.path.join(HERE, "ssd_postprocess.npz"), **pack)
+
+
 if __name__ == "__main__":
     legacy()
+    ssd()
     retinanet()
     legacy_get_target()
     roi()
-    for f in ("legacy_yolo_loss.npz", "legacy_get_target.npz", "retinanet_postprocess.npz", "roi_postprocess.npz"):
+    for f in ("legacy_yolo_loss.npz", "legacy_get_target.npz", "retinanet_postprocess.npz", "ssd_postprocess.npz", "roi_postprocess.npz"):
         print(f"  {f:32s} {os.path.getsize(os.path.join(HERE, f)):>9d} B")

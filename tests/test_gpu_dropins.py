@@ -549,3 +549,39 @@ def test_retinanet_postprocess_detections_bound_like_the_reference(strategy, nms
         if strategy == "torchvision":
             np.testing.assert_array_equal(got[i]["labels"].cpu().numpy(), gold[f"labels_{i}"])
             assert np.all(np.abs(b - gold[f"boxes_{i}"]) <= 1e-5 * np.maximum(np.abs(gold[f"boxes_{i}"]), max(ih, iw)))
+
+
+@pytest.mark.parametrize("strategy", ["vanilla", "torchvision"])
+def test_ssd_postprocess_detections_bound_like_the_reference(strategy):
+    """SSD.postprocess_detections (ssd.py:386-430) bound onto an SSD-like object: softmax of tfidf * logits, one decoded box
+    per anchor, per-class threshold + top-400 (one class has 571 candidates), class-aware NMS, top 200 -- against the
+    oracle (pinned bit-exactly to the reference) and the reference's golden output; the first image's 17 563 candidates
+    overflow the default slab and exercise the exact-capacity retry.  Labels and counts exact, values in tolerance."""
+    from object_detectors_b200 import _lib
+    from object_detectors_b200.tvision import ssd as b200_ssd
+    from object_detectors_b200.tvision._utils import BoxCoder
+    gold = np.load(os.path.join(G, "ssd_postprocess.npz"))
+    seed, bsz, a, c, img = [int(v) for v in gold["args"]]
+    logits, regs, anchors = syn.ssd_inputs(seed, bsz, a, c, img)
+    idf = torch.from_numpy(gold["idf"])
+    fake_self = types.SimpleNamespace(tfidf_post=idf.cuda(), box_coder=BoxCoder((10.0, 10.0, 5.0, 5.0)), score_thresh=0.01,
+                                      topk_candidates=400, nms_thresh=0.45, detections_per_img=200)
+    head = {"cls_logits": torch.from_numpy(logits).cuda(), "bbox_regression": torch.from_numpy(regs).cuda()}
+    lib = _lib.load()
+    if strategy == "torchvision":
+        lib.b200_set_batched_nms_auto_limit(4000)        # the CPU oracle's switch point
+    try:
+        got = b200_ssd.postprocess_detections(fake_self, head, [torch.from_numpy(anchors).cuda()] * bsz, [(img, img)] * bsz,
+                                              strategy=strategy)
+    finally:
+        lib.b200_set_batched_nms_auto_limit(100000)
+    ref = tv_ref.ssd_postprocess(torch.from_numpy(logits), torch.from_numpy(regs), [torch.from_numpy(anchors)] * bsz,
+                                 [(img, img)] * bsz, idf, strategy=strategy)
+    for i, (rb, rs, rl) in enumerate(ref):
+        assert got[i]["boxes"].shape[0] == rb.shape[0] > 0
+        np.testing.assert_array_equal(got[i]["labels"].cpu().numpy(), rl.numpy())
+        s, b = got[i]["scores"].cpu().numpy(), got[i]["boxes"].cpu().numpy()
+        assert np.all(np.abs(s - rs.numpy()) <= 1e-5 * np.abs(rs.numpy()) + 1e-12)
+        assert np.all(np.abs(b - rb.numpy()) <= 1e-5 * np.maximum(np.abs(rb.numpy()), img))
+        if strategy == "torchvision":
+            np.testing.assert_array_equal(got[i]["labels"].cpu().numpy(), gold[f"labels_{i}"])

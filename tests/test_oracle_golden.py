@@ -191,3 +191,22 @@ def test_retinanet_postprocess_oracle_matches_reference_golden():
         np.testing.assert_array_equal(b.numpy(), g[f"boxes_{i}"])
         np.testing.assert_array_equal(s.numpy(), g[f"scores_{i}"])
         np.testing.assert_array_equal(l.numpy(), g[f"labels_{i}"])
+
+
+def test_ssd_postprocess_oracle_matches_reference_golden():
+    """oracle/tv_ref.ssd_postprocess == the UNMODIFIED reference's SSD.postprocess_detections
+    (tests/golden/ssd_postprocess.npz, written by make_golden_extra.py), bit for bit."""
+    import os
+    import numpy as np
+    import torch
+    from object_detectors_b200 import synthetic as syn
+    from oracle import tv_ref
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ssd_postprocess.npz"))
+    seed, bsz, a, c, img = [int(v) for v in g["args"]]
+    logits, regs, anchors = syn.ssd_inputs(seed, bsz, a, c, img)
+    out = tv_ref.ssd_postprocess(torch.from_numpy(logits), torch.from_numpy(regs), [torch.from_numpy(anchors)] * bsz,
+                                 [(img, img)] * bsz, torch.from_numpy(g["idf"]))
+    for i, (b, s, l) in enumerate(out):
+        np.testing.assert_array_equal(b.numpy(), g[f"boxes_{i}"])
+        np.testing.assert_array_equal(s.numpy(), g[f"scores_{i}"])
+        np.testing.assert_array_equal(l.numpy(), g[f"labels_{i}"])
