@@ -225,7 +225,7 @@ def run_b200(args):
     lib = _lib.load()
     VARIANTS = {"gated": 0, "stream": 1, "bulk": 2, "ring": 3}
     lib.b200_set_decode_variant(VARIANTS[args.variant])
-    lib.b200_debug_set_nms_path(1 if args.nms_path == "general" else 0)
+    lib.b200_debug_set_nms_path({"auto": -1, "general": 1, "fused": 0}[args.nms_path])
 
     # weak scaling (default, the reference's DistributedSampler data parallelism): every rank owns its own batch of
     # 64; strong scaling: the SAME 64 images split into contiguous blocks of 64 / world
@@ -516,7 +516,7 @@ def run_b200(args):
         step_ms = ms_total / args.steps
         achieved = algo_bytes / (step_ms * 1e-3) / 1e9
         cpu_v, cores, cpu_ts = time_cpu(sample_batch=BATCH, reps=12) if world == 1 else (None, os.cpu_count() or 1, [])
-        nms_kernels = 3 if args.nms_path == "general" else 1
+        nms_kernels = {"auto": 4, "general": 3, "fused": 1}[args.nms_path]
         launches_per_step = 1 + nms_kernels + (2 if mode == "p2p" else 1 if mode == "nccl" else 0)
         exch = {"none": "none (1 GPU)" if world == 1 else "disabled (diagnostic)",
                 "p2p": f"one-sided: push kernel stores the kept lists into every peer's receive buffer over NVLink (CUDA IPC "
@@ -574,8 +574,9 @@ def main():
                     help="weak: 64 images per GPU; strong: the same 64 images split over the GPUs (SURVEY 8e)")
     ap.add_argument("--variant", default="ring", choices=["ring", "gated", "stream", "bulk"],
                     help="fused decode kernel variant (include/b200det.h: B200_DECODE_*)")
-    ap.add_argument("--nms-path", default="general", choices=["general", "fused"],
-                    help="NMS kernels: three-launch general path or the single-launch path (nms_fused.cu)")
+    ap.add_argument("--nms-path", default="auto", choices=["auto", "general", "fused"],
+                    help="NMS kernels: auto = the library default (general path for segments of <= 1500 boxes + the "
+                         "single-launch path for larger ones), general / fused = one path only")
     ap.add_argument("--dstreams", type=int, default=3, help="decode streams = decode kernels in flight")
     ap.add_argument("--nstreams", type=int, default=3, help="streams for the NMS chains")
     ap.add_argument("--plans", type=int, default=6, help="rotating workspaces")

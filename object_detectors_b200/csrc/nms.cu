@@ -45,6 +45,7 @@ static constexpr int kKeptSmem = 2048;          // slow path: kept boxes sorted 
 static constexpr int kRankSortMax = 1024;       // kept boxes ordered by counting below this, bitonic network above
 static constexpr int kVoteFlag = 1 << 30;
 static constexpr int kVoteListCap = 128;
+static constexpr int kSplitBoxes = 1500;        // largest segment the shared-memory resolve holds at its default 112 KB
 
 
 
@@ -151,7 +152,7 @@ k_nms_plan(const __grid_constant__ NmsParams P) {
     long long off;
     int n, n_true;
     segment_range(P, seg, off, n, n_true);
-    if (n == 0) return;
+    if (n == 0 || n > P.split_hi) return;         // larger segments belong to the single-launch path
 
     // ---- coordinate-trick unit, y range of the box centres ------------------------------------
     float unit = 0.f;
@@ -919,6 +920,7 @@ k_nms_resolve(const __grid_constant__ NmsParams P, const unsigned smem_bytes) {
         }
         return;
     }
+    if (n > P.split_hi) return;                   // resolved by the single-launch path
     const int nw = cdiv(n, 64);
     const size_t fixed = fast_fixed_bytes(n, nw);
     const size_t sort_bytes = 12 * (size_t)next_pow2(n);
@@ -1020,13 +1022,22 @@ int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
     // the next batch, where the three small-footprint kernels of the general path co-reside with it and its spatially
     // pruned tile pairs do half the work; array inputs (torchvision nms / batched_nms, RPN levels, ROI heads) are
     // stand-alone calls on boxes spread all over the image, where one launch without a work queue wins.
-    P.force_general = g_nms_force_general >= 0 ? g_nms_force_general : (P.from_slab ? 1 : 0);
+    P.force_general = g_nms_force_general;
     P.prof = g_resolve_prof;
-    if (!P.force_general && nms_fused_eligible(P)) {
+    P.split_lo = 0;
+    P.split_hi = 0x7fffffff;
+    const bool fused_ok = nms_fused_eligible(P);
+    if (fused_ok && (P.force_general == 0 || (P.force_general < 0 && !P.from_slab))) {
         const int rc = launch_nms_fused(P, num_segments, stream);
         if (g_nms_timeline[2]) cudaEventRecord(g_nms_timeline[2], stream);
         return rc;
     }
+    // Candidate slabs (default): both paths, split by segment size.  The three kernels below take the segments their
+    // shared-memory resolve holds (<= kSplitBoxes boxes: the usual case, small CTAs that co-reside with the streaming
+    // decode kernel of the next batch); the single-launch kernel takes the larger ones, which would otherwise fall
+    // back to the global-memory resolve (20x slower).  Each kernel returns at once from segments that are not its own.
+    const bool split = fused_ok && P.force_general < 0 && P.from_slab;
+    if (split) P.split_hi = kSplitBoxes;
     const int sms = current_sm_count();
     if (cudaMemsetAsync(P.work_count, 0, 2 * sizeof(int), stream) != cudaSuccess) return B200_ERR_CUDA;
     if (P.from_slab) k_nms_plan<true><<<num_segments, kPlanThreads, 0, stream>>>(P);
@@ -1051,7 +1062,13 @@ int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
     if (P.from_slab) k_nms_resolve<true><<<num_segments, resolve_threads, smem, stream>>>(P, (unsigned)smem);
     else             k_nms_resolve<false><<<num_segments, resolve_threads, smem, stream>>>(P, (unsigned)smem);
     if (g_nms_timeline[2]) cudaEventRecord(g_nms_timeline[2], stream);
-    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+    if (cudaGetLastError() != cudaSuccess) return B200_ERR_CUDA;
+    if (split) {
+        P.split_lo = kSplitBoxes;
+        P.split_hi = 0x7fffffff;
+        return launch_nms_fused(P, num_segments, stream);
+    }
+    return B200_OK;
 }
 
 }  // namespace b200

@@ -67,6 +67,7 @@ struct NmsParams {
     int* f_rlabel;
     unsigned long long* f_rkey; // (~orderable(score) << 32) | tie << 12 | index inside the segment
     int force_general;          // debug: 1 = always take the three-launch path
+    int split_lo, split_hi;     // this launch only handles segments with split_lo < n <= split_hi (others are left alone)
 };
 
 // scratch bytes needed for T boxes in S segments of at most max_seg boxes each

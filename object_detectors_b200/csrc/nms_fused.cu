@@ -26,10 +26,11 @@
 
 namespace b200 {
 
-static constexpr int kFT = 1024;                // threads per CTA
-static constexpr int kFW = kFT / 32;
-static constexpr int kParts = kFT / 64;         // threads that share one row of a row tile (16)
-static constexpr int kBatchTiles = kParts;      // column tiles staged per batch: one column per thread
+// Threads per CTA is a template parameter NT: 1024 for stand-alone calls (array inputs), 256 when the kernel only takes
+// the large segments of a candidate slab next to the general path (it then has to start beside the streaming decode
+// kernel of the next batch: 256 threads x 64 registers and 41 KB co-reside with it, 1024 threads need the whole SM).
+// NT / 64 threads share one row of a row tile; the same number of column tiles is staged per batch.
+static constexpr int kMaxParts = 16;
 static constexpr int kHeavyCap = 256;           // kept boxes with many voters, relabelled by a whole warp
 static constexpr int kHeavyVoters = 12;
 static constexpr int kPoolInts = 9216;          // resolve scratch in shared memory (36 KB)
@@ -44,7 +45,9 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 
 // in-place exclusive scan of a[0..n) by the whole CTA (a may live in shared or global memory)
+template <int NT>
 __device__ __forceinline__ void f_exclusive_scan(int* a, int n, int* scratch) {
+    constexpr int kFT = NT, kFW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int carry = 0;
     for (int base = 0; base < n; base += kFT) {
@@ -66,7 +69,9 @@ __device__ __forceinline__ void f_exclusive_scan(int* a, int n, int* scratch) {
 
 // ascending bitonic sort of key[0..P2) in shared memory, P2 a power of two >= 64.  Steps with a partner distance
 // below 64 stay inside aligned blocks of 64 keys and are done by one warp per block without CTA barriers.
+template <int NT>
 __device__ __forceinline__ void f_bitonic(unsigned long long* key, int P2) {
+    constexpr int kFT = NT, kFW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int base = warp * 64; base < P2; base += kFW * 64) {
         unsigned long long* kk = key + base;
@@ -118,9 +123,10 @@ struct RankArrays {
 // ---------------------------------------------------------------------------------------------- RANK
 // returns true when the segment holds a degenerate box (zero / negative / non-finite area, NaN coordinates): such
 // boxes can yield NaN IoU, which the majority rule treats as "removed", so the segment never uses the prefilter
-template <bool SLAB>
+template <bool SLAB, int NT>
 __device__ bool fused_rank(const NmsParams& P, int seg, long long off, int n, int n_true, const RankArrays& R,
                            unsigned char* smem, float* red, bool first_member) {
+    constexpr int kFT = NT;
     const int tid = threadIdx.x;
     // ---- coordinate-trick unit (torchvision.ops.batched_nms: boxes + idxs * (boxes.max() + 1)) ------------------
     float unit = 0.f;
@@ -153,7 +159,7 @@ __device__ bool fused_rank(const NmsParams& P, int seg, long long off, int n, in
         key[i] = k;
     }
     __syncthreads();
-    f_bitonic(key, P2);
+    f_bitonic<NT>(key, P2);
     int bad = 0;
     for (int r = tid; r < n; r += kFT) {
         const unsigned long long k = key[r];
@@ -170,18 +176,19 @@ __device__ bool fused_rank(const NmsParams& P, int seg, long long off, int n, in
 
 // ---------------------------------------------------------------------------------------------- STRIPS
 struct StripSmem {
-    float4 cb[kBatchTiles * 64];
-    float ca[kBatchTiles * 64];
-    float cta[kBatchTiles * 64];                 // 0.999 * thr * area (prefilter)
-    int clab[kBatchTiles * 64];
-    unsigned wbuf[64 * kBatchTiles * 2];         // [64 rows][16 tiles] 64-bit words as 32-bit halves
+    float4 cb[kMaxParts * 64];
+    float ca[kMaxParts * 64];
+    float cta[kMaxParts * 64];                   // 0.999 * thr * area (prefilter)
+    int clab[kMaxParts * 64];
+    unsigned wbuf[64 * kMaxParts * 2];           // [64 rows][NT / 64 tiles] 64-bit words as 32-bit halves
 };
 static_assert(sizeof(StripSmem) <= kSmemBytes, "strip staging must fit");
 
 // row tile rt against column tiles [c0, c1), c1 <= rt + 1
-template <int MODE>
+template <int MODE, int NT>
 __device__ void fused_strip(const NmsParams& P, int seg, int n, int rt, int c0, int c1, const RankArrays& R,
                             unsigned char* smem, bool nofilter) {
+    constexpr int kParts = NT / 64, kBatchTiles = kParts;
     StripSmem& S = *reinterpret_cast<StripSmem*>(smem);
     const int tid = threadIdx.x;
     unsigned long long* dom = P.dom + (size_t)seg * (size_t)P.max_seg * (size_t)P.max_words;
@@ -266,11 +273,12 @@ struct ResolveSmem {
 };
 static_assert(sizeof(ResolveSmem) <= kSmemBytes, "resolve scratch must fit");
 
-// blocks of 64 rows in rank order.  Thread (row = tid / 16, g = tid % 16) holds words g + 16k (k < NK) of its row;
+// blocks of 64 rows in rank order.  Thread (row = tid / P, g = tid % P), P = NT / 64, holds words g + P*k (k < NK) of its row;
 // three register sets rotate so that the words of block b + 2 are in flight while block b is decided.
-template <int NK, bool MAJ>
+template <int NK, bool MAJ, int NT>
 __device__ __noinline__ void resolve_blocks(const unsigned long long* __restrict__ dom, size_t W, int n, int nw,
                                             ResolveSmem& M, int* sup) {
+    constexpr int kParts = NT / 64;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = tid / kParts, g = tid % kParts;
     struct Set { unsigned long long v[NK]; };
@@ -330,6 +338,16 @@ __device__ __noinline__ void resolve_blocks(const unsigned long long* __restrict
         }
         __syncthreads();
     };
+    if (NK > 4) {
+        // many words per thread (long rows handled by few threads): no register rotation, the words of a block are
+        // loaded when the block is decided
+        for (int blk = 0; blk < nw; ++blk) {
+            Set A;
+            load(blk, A);
+            decide(blk, A);
+        }
+        return;
+    }
     Set A, B, C;
     load(0, A);
     load(1, B);
@@ -341,9 +359,10 @@ __device__ __noinline__ void resolve_blocks(const unsigned long long* __restrict
     }
 }
 
-template <int MODE, bool SLAB>
+template <int MODE, bool SLAB, int NT>
 __device__ void fused_resolve(const NmsParams& P, int seg, long long off, int n, const RankArrays& R,
                               unsigned char* smem, int* scan, unsigned long long* prof) {
+    constexpr int kFT = NT, kFW = NT / 32, kParts = NT / 64;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nw = cdiv(n, 64);
     const size_t W = (size_t)P.max_words;
@@ -353,9 +372,10 @@ __device__ void fused_resolve(const NmsParams& P, int seg, long long off, int n,
     int* sup = pool;                                                                  // [n] (MAJORITY)
     constexpr bool MAJ = MODE == B200_NMS_MAJORITY;
     if (tid == 0) M.heavy_n = 0;
-    if (nw <= kParts)          resolve_blocks<1, MAJ>(dom, W, n, nw, M, sup);
-    else if (nw <= 2 * kParts) resolve_blocks<2, MAJ>(dom, W, n, nw, M, sup);
-    else                       resolve_blocks<4, MAJ>(dom, W, n, nw, M, sup);
+    if (nw <= kParts)          resolve_blocks<1, MAJ, NT>(dom, W, n, nw, M, sup);
+    else if (nw <= 2 * kParts) resolve_blocks<2, MAJ, NT>(dom, W, n, nw, M, sup);
+    else if (nw <= 4 * kParts) resolve_blocks<4, MAJ, NT>(dom, W, n, nw, M, sup);
+    else                       resolve_blocks<64 / kParts, MAJ, NT>(dom, W, n, nw, M, sup);
     if (prof && tid == 0) prof[5] = gtime();
 
     // ---- output slot of a kept rank = number of kept ranks below it ------------------------------------------------
@@ -413,7 +433,7 @@ __device__ void fused_resolve(const NmsParams& P, int seg, long long off, int n,
             }
         }
         __syncthreads();
-        f_exclusive_scan(voff, n + 1, scan);
+        f_exclusive_scan<NT>(voff, n + 1, scan);
         for (int p = tid; p < n; p += kFT) fill[p] = voff[p];
         __syncthreads();
         for (int j = tid; j < n; j += kFT) {
@@ -490,7 +510,7 @@ __device__ void fused_resolve(const NmsParams& P, int seg, long long off, int n,
             __syncthreads();
             for (int w = tid; w < awords; w += kFT) pre[w] = __popc(bm[w]);
             __syncthreads();
-            f_exclusive_scan(pre, awords, scan);
+            f_exclusive_scan<NT>(pre, awords, scan);
             for (int r = tid; r < n; r += kFT) {
                 if (!is_kept(r)) continue;
                 const int t = slot_of(r);
@@ -524,13 +544,14 @@ __device__ void fused_resolve(const NmsParams& P, int seg, long long off, int n,
 }
 
 // ---------------------------------------------------------------------------------------------- one segment
-template <bool SLAB>
+template <bool SLAB, int NT>
 __device__ void fused_segment(const NmsParams& P, int seg, int member, int team, const RankArrays& R,
                               unsigned char* smem, float* red, int* scan, int* cmd) {
     const int tid = threadIdx.x;
     long long off;
     int n, n_true;
     segment_range(P, seg, off, n, n_true);
+    if (n <= P.split_lo && (n > 0 || P.split_lo > 0)) return;          // the general path's segment (it also writes n == 0)
     if (tid == 0 && member == 0 && SLAB && P.cand_count_out) P.cand_count_out[seg] = n_true;
     if (n == 0) {
         if (tid == 0 && member == 0) {
@@ -541,7 +562,7 @@ __device__ void fused_segment(const NmsParams& P, int seg, int member, int team,
     }
     unsigned long long* prof = P.prof ? reinterpret_cast<unsigned long long*>(P.prof) + (size_t)blockIdx.x * 8 : nullptr;
     if (prof && tid == 0) { prof[0] = gtime(); prof[1] = ((unsigned long long)seg << 40) | ((unsigned long long)team << 32) | (unsigned)n; }
-    const bool nofilter = fused_rank<SLAB>(P, seg, off, n, n_true, R, smem, red, member == 0) || !(P.thr_f > 0.f);
+    const bool nofilter = fused_rank<SLAB, NT>(P, seg, off, n, n_true, R, smem, red, member == 0) || !(P.thr_f > 0.f);
     if (prof && tid == 0) prof[2] = gtime();
 
     // the nt*(nt+1)/2 tiles in row-major order (row tile rt holds column tiles 0..rt): this member's contiguous share
@@ -555,10 +576,10 @@ __device__ void fused_segment(const NmsParams& P, int seg, int member, int team,
         const int c0 = t - rt * (rt + 1) / 2;
         const int c1 = min(rt + 1, c0 + (t_end - t));
         switch (P.mode) {
-            case B200_NMS_MAJORITY: fused_strip<B200_NMS_MAJORITY>(P, seg, n, rt, c0, c1, R, smem, nofilter); break;
+            case B200_NMS_MAJORITY: fused_strip<B200_NMS_MAJORITY, NT>(P, seg, n, rt, c0, c1, R, smem, nofilter); break;
             case B200_NMS_TV_AUTO:   // shifted boxes of different labels never intersect: the label test is exact for both
-            case B200_NMS_TV_CLASS: fused_strip<B200_NMS_TV_CLASS>(P, seg, n, rt, c0, c1, R, smem, nofilter); break;
-            default:                fused_strip<B200_NMS_TV>(P, seg, n, rt, c0, c1, R, smem, nofilter); break;      // TV, TV_TRICK
+            case B200_NMS_TV_CLASS: fused_strip<B200_NMS_TV_CLASS, NT>(P, seg, n, rt, c0, c1, R, smem, nofilter); break;
+            default:                fused_strip<B200_NMS_TV, NT>(P, seg, n, rt, c0, c1, R, smem, nofilter); break;      // TV, TV_TRICK
         }
         t += c1 - c0;
     }
@@ -575,18 +596,19 @@ __device__ void fused_segment(const NmsParams& P, int seg, int member, int team,
     __syncthreads();
     if (prof && tid == 0) prof[4] = gtime();
     if (last) {
-        if (P.mode == B200_NMS_MAJORITY) fused_resolve<B200_NMS_MAJORITY, SLAB>(P, seg, off, n, R, smem, scan, prof);
-        else                             fused_resolve<B200_NMS_TV, SLAB>(P, seg, off, n, R, smem, scan, prof);
+        if (P.mode == B200_NMS_MAJORITY) fused_resolve<B200_NMS_MAJORITY, SLAB, NT>(P, seg, off, n, R, smem, scan, prof);
+        else                             fused_resolve<B200_NMS_TV, SLAB, NT>(P, seg, off, n, R, smem, scan, prof);
     }
     __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <bool SLAB>
-__global__ void __launch_bounds__(kFT, 1)
+template <bool SLAB, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT)
 k_nms_fused(const __grid_constant__ NmsParams P) {
+    constexpr int kFT = NT, kFW = NT / 32;
     __shared__ __align__(16) unsigned char smem[kSmemBytes];
-    __shared__ float red[kFW];
+    __shared__ float red[32];
     __shared__ int scan[32];
     __shared__ int cmd[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -595,7 +617,7 @@ k_nms_fused(const __grid_constant__ NmsParams P) {
     const RankArrays R{P.f_rbox + slot, P.f_rarea + slot, P.f_rlabel + slot, P.f_rkey + slot};
 
     if (S >= G) {
-        for (int seg = blockIdx.x; seg < S; seg += G) fused_segment<SLAB>(P, seg, 0, 1, R, smem, red, scan, cmd);
+        for (int seg = blockIdx.x; seg < S; seg += G) fused_segment<SLAB, NT>(P, seg, 0, 1, R, smem, red, scan, cmd);
         return;
     }
     // ---- fewer segments than CTAs: teams.  Every CTA derives the same assignment from the segment sizes (same
@@ -609,7 +631,7 @@ k_nms_fused(const __grid_constant__ NmsParams P) {
         long long off;
         int n, n_true;
         segment_range(P, tid, off, n, n_true);
-        cost = (float)n * (float)(n + 256);
+        cost = n > P.split_lo ? (float)n * (float)(n + 256) : 0.f;       // segments of the other path cost nothing
     }
     float tot = cost;
 #pragma unroll
@@ -646,7 +668,7 @@ k_nms_fused(const __grid_constant__ NmsParams P) {
     if (tid < S) first[tid] = team_of[tid];
     if (tid == S) first[tid] = 0;
     __syncthreads();
-    f_exclusive_scan(first, S + 1, scan);                          // first[s] = first CTA of segment s, first[S] <= G
+    f_exclusive_scan<NT>(first, S + 1, scan);                          // first[s] = first CTA of segment s, first[S] <= G
     __syncthreads();
     // binary search: the segment whose CTA range holds blockIdx.x
     const int me = blockIdx.x;
@@ -662,11 +684,11 @@ k_nms_fused(const __grid_constant__ NmsParams P) {
         team = first[lo + 1] - first[lo];
     }
     __syncthreads();
-    if (seg >= 0) fused_segment<SLAB>(P, seg, member, team, R, smem, red, scan, cmd);
+    if (seg >= 0) fused_segment<SLAB, NT>(P, seg, member, team, R, smem, red, scan, cmd);
 }
 
 // ---------------------------------------------------------------------------------------------- host
-static constexpr int kFusedGridMax = 160;       // private rank-array slots carved per launch (>= SMs of a B200)
+static constexpr int kFusedGridMax = 320;       // private rank-array slots carved per launch (>= 2 x SMs of a B200)
 int nms_fused_slots() { return kFusedGridMax; }
 
 bool nms_fused_eligible(const NmsParams& P) {
@@ -677,13 +699,24 @@ bool nms_fused_eligible(const NmsParams& P) {
 
 int launch_nms_fused(NmsParams& P, int num_segments, cudaStream_t stream) {
     if (cudaMemsetAsync(P.f_ctl, 0, sizeof(int) * (size_t)num_segments, stream) != cudaSuccess) return B200_ERR_CUDA;
-    int grid = current_sm_count();
-    if (grid > kFusedGridMax) grid = kFusedGridMax;
     // a lone small segment does not need the whole chip: at most one CTA per row tile
     const long long useful = (long long)num_segments * (P.max_words > 0 ? P.max_words : 1);
-    if (useful < grid) grid = (int)useful;
-    if (P.from_slab) k_nms_fused<true><<<grid, kFT, 0, stream>>>(P);
-    else             k_nms_fused<false><<<grid, kFT, 0, stream>>>(P);
+    const int sms = current_sm_count();
+    if (P.split_lo > 0) {
+        // beside the general path (large segments of a candidate slab only): small CTAs, two per SM, that start next
+        // to the streaming decode kernel and leave at once when the batch has no large segment
+        int grid = 2 * sms;
+        if (grid > kFusedGridMax) grid = kFusedGridMax;
+        if (useful < grid) grid = (int)useful;
+        if (P.from_slab) k_nms_fused<true, 256><<<grid, 256, 0, stream>>>(P);
+        else             k_nms_fused<false, 256><<<grid, 256, 0, stream>>>(P);
+    } else {
+        int grid = sms;
+        if (grid > kFusedGridMax) grid = kFusedGridMax;
+        if (useful < grid) grid = (int)useful;
+        if (P.from_slab) k_nms_fused<true, 1024><<<grid, 1024, 0, stream>>>(P);
+        else             k_nms_fused<false, 1024><<<grid, 1024, 0, stream>>>(P);
+    }
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }
 

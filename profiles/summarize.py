@@ -53,8 +53,31 @@ def launches(path):
         print(f"{k:48s} {len(v):8d} {sum(v) / len(v) / 1e3:10.2f} {100 * sum(v) / total:6.1f}%")
 
 
+def traffic(path, kernel, out_json):
+    """dram bytes of one launch of `kernel` from a `--set full` capture -> the JSON bench.py reads for roofline.traffic"""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    head, units = rows[0], rows[1]
+    ki = head.index("Kernel Name")
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        if kernel in r[ki]:
+            rd, wr = head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum")
+            d = {"kernel": r[ki], "dram_bytes_read": int(float(r[rd].replace(",", "")) * scale[units[rd]]),
+                 "dram_bytes_write": int(float(r[wr].replace(",", "")) * scale[units[wr]]),
+                 "duration_us": float(r[head.index("gpu__time_duration.sum")].replace(",", "")), "source": path.split("/")[-1],
+                 "note": "one launch, `ncu --set full --clock-control none` (replayed, cold cache)"}
+            json.dump(d, open(out_json, "w"), indent=1)
+            print(d)
+            return
+    raise SystemExit(f"kernel {kernel} not in {path}")
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "--launches":
+    if sys.argv[1] == "--traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    elif sys.argv[1] == "--launches":
         launches(sys.argv[2])
     else:
         kernels(sys.argv[1])
