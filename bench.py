@@ -1,24 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- images/sec of decode + conf filter + NMS on synthetic YOLOv3-608 COCO head tensors.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scaling weak|strong]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path (b200_yolo_postprocess_decode: fused decode+filter kernel, then
-b200_yolo_postprocess_nms: plan / pairs / resolve kernels) over one batch of 64 images per GPU (weak scaling:
-every rank owns its own 64-image batch, as the reference's DistributedSampler does); at N > 1 each step ends
-with the one exchange the path has, a pack kernel + ncclAllGather of the fixed-capacity kept-detection
-messages.  Steps are software pipelined: decode kernels rotate over 3 decode streams (so the HBM stream never
-drains), NMS chains over 3 other streams, the exchange has its own; 6 workspaces rotate.
+b200_yolo_postprocess_nms: the NMS kernels) over one batch of 64 images per GPU (weak scaling: every rank owns its own
+64-image batch, as the reference's DistributedSampler does; --scaling strong splits the same 64 images over the ranks);
+at N > 1 each step ends with the one exchange the path has: b200_exchange_push stores the kept-detection lists straight
+into every peer's receive buffer over NVLink, b200_exchange_wait completes when all ranks' lists of the step are there.
+Steps are software pipelined: decode kernels rotate over 3 decode streams (so the HBM stream never drains), NMS chains
+over 3 other streams, pushes and waits have a stream each; 6 workspaces rotate.  The timed loop is captured into ONE
+CUDA graph after the warm-up and timed as one replay.
 
 Printed JSON (one line, rank 0):
   value     whole-job images/s with the head tensors resident in HBM (device-timed, max over ranks)
-  roofline  fused decode+filter kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json);
-            achieved = algorithmic bytes (one read of the head tensors, B*N*(5+C)*4) / its mean
-            duration measured with CUDA events inside the timed region
+  roofline  algorithmic bytes per step (one read of the head tensors, B*N*(5+C)*4, per GPU) / the step period, against the
+            measured HBM copy bandwidth (MEASURED_PEAKS.json); decode-kernel intervals and the isolated launch as extras
   e2e       same metric through the host-buffer C-ABI entry (pinned host -> device copies of all
             head tensors and device -> host copy of the detections inside the timed region)
-  cpu_baseline  the CPU oracle port of the reference path on a bounded sample, all host threads
+  cpu_baseline  the CPU oracle port of the reference path on a bounded sample, all host threads (N = 1 only)
 --impl reference: the reference's own CPU implementation is Python and cannot travel to the GPU
 box, so the oracle port (oracle/yolo_ref.py: same torch CPU ops in the same order, pinned
 bit-exactly to the reference by tests/golden) is timed on the host cores instead.

@@ -1,13 +1,12 @@
 """Multi-GPU plumbing: images are sharded across ranks (one process per GPU, like the reference's
 DistributedSampler data parallelism, yolo/procedures/init_dataset.py:82-83) and the path has exactly
-one exchange step at its end -- an all-gather of the variable-length kept-detection lists, sent as
-one fixed-capacity message per rank (counts travel inside the payload) so a single NCCL collective
-replaces the reference's per-rank pickle files + barrier (yolo/procedures/eval_results.py:12-31,
-yolo/main.py:102-105) and its size-exchange/pad/gather ``utils.all_gather``
-(torchvision_models/detection/utils.py:75-115).
+one exchange step at its end -- an all-gather of the variable-length kept-detection lists -- which replaces the
+reference's per-rank pickle files + barrier (yolo/procedures/eval_results.py:12-31, yolo/main.py:102-105) and its
+size-exchange/pad/gather ``utils.all_gather`` (torchvision_models/detection/utils.py:75-115).
 
-The collective itself is ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests); the packing of
-the message is a CUDA kernel (b200_pack_detections).
+``PeerExchange`` is the default: one-sided stores into the peers' receive buffers over NVLink (csrc/exchange.cu),
+no collective kernel.  ``DetectionExchange`` is the NCCL form (pack kernel + bucketed ``ncclAllGather``), kept for
+setups without peer mapping and for the gloo CPU tests of the host-side bookkeeping.
 """
 from __future__ import annotations
 
