@@ -224,7 +224,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    VARIANTS = {"gated": 0, "stream": 1, "bulk": 2, "ring": 3}
+    VARIANTS = {"gated": 0, "stream": 1, "ring": 3}
     lib.b200_set_decode_variant(VARIANTS[args.variant])
     lib.b200_debug_set_nms_path({"auto": -1, "general": 1, "fused": 0}[args.nms_path])
 
@@ -573,7 +573,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: 64 images per GPU; strong: the same 64 images split over the GPUs (SURVEY 8e)")
-    ap.add_argument("--variant", default="ring", choices=["ring", "gated", "stream", "bulk"],
+    ap.add_argument("--variant", default="ring", choices=["ring", "gated", "stream"],
                     help="fused decode kernel variant (include/b200det.h: B200_DECODE_*)")
     ap.add_argument("--nms-path", default="auto", choices=["auto", "general", "fused"],
                     help="NMS kernels: auto = the library default (general path for segments of <= 1500 boxes + the "

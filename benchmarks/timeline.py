@@ -32,7 +32,7 @@ def main():
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     lib = _lib.load()
-    lib.b200_set_decode_variant({"gated": 0, "stream": 1, "bulk": 2, "ring": 3}[args.variant])
+    lib.b200_set_decode_variant({"gated": 0, "stream": 1, "ring": 3}[args.variant])
     lib.b200_debug_set_ring(*[int(x) for x in args.ring.split(",")])
     heads = [torch.from_numpy(h).to(dev) for h in syn.yolo_heads(1000, BATCH, IMG, NC, syn.COCO_ANCHORS, "clustered")]
     idf = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "idf_coco_smooth.npy"))).to(dev)

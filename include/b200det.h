@@ -192,11 +192,10 @@ int b200_debug_set_resolve(int threads, int smem_kb);
  *           objectness can still pass.  Every byte of the head tensors is read exactly once, whatever
  *           the input looks like: the variant the HBM roofline fraction is quoted for.
  *   STREAM  register path; every byte is read once with coalesced 128-bit loads.
- *   BULK    one 128-cell tile per CTA staged by 1-D cp.async.bulk row copies (first TMA prototype).
  *   GATED   register path; the objectness plane is read for every cell, class and box planes only by
  *           lanes that hold a cell whose objectness can still pass the threshold (score <= conf).
  *           DRAM traffic is input dependent (176 MB of the 495 MB batch on the benchmark input). */
-enum { B200_DECODE_GATED = 0, B200_DECODE_STREAM = 1, B200_DECODE_BULK = 2, B200_DECODE_RING = 3 };
+enum { B200_DECODE_GATED = 0, B200_DECODE_STREAM = 1, B200_DECODE_RING = 3 };   /* 2: retired prototype */
 int b200_set_decode_variant(int variant);
 /* Tuning hook of the RING variant (values <= 0 keep the current setting): warps per CTA (1..8),
  * shared-memory stages per warp (warps x stages <= 32), persistent CTAs per SM (1..4). */

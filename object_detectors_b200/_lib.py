@@ -10,7 +10,7 @@ MAX_ANCHORS = 8
 
 NMS_MAJORITY, NMS_TV, NMS_TV_CLASS, NMS_TV_TRICK, NMS_TV_AUTO = 0, 1, 2, 3, 4
 IOU, GIOU, DIOU, CIOU, IOU_TV = 0, 1, 2, 3, 4
-DECODE_GATED, DECODE_STREAM, DECODE_BULK, DECODE_RING = 0, 1, 2, 3
+DECODE_GATED, DECODE_STREAM, DECODE_RING = 0, 1, 3
 
 LIB_PATH = os.environ.get("B200DET_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc",
                                                          "libb200det.so")

@@ -9,7 +9,6 @@
 
 namespace b200 {
 int launch_decode_filter(const DecodeParams& p, bool softmax, int gate, cudaStream_t stream);
-int launch_decode_filter_bulk(const DecodeParams& p, bool softmax, cudaStream_t stream);
 int launch_decode_filter_ring(const DecodeParams& p, bool softmax, int* tile_counter, cudaStream_t stream);
 void ring_set_tuning(int warps, int slots_per_warp, int ctas_per_sm);
 void ring_set_tile_cells(int tc);
@@ -144,7 +143,7 @@ size_t b200_yolo_workspace_bytes(const b200_yolo_layout* layout, int32_t capacit
 // the fused decode+filter kernel, so its duration can be measured inside a timed region.
 static int g_decode_variant = B200_DECODE_RING;
 int b200_set_decode_variant(int variant) {
-    if (variant < B200_DECODE_GATED || variant > B200_DECODE_RING) return B200_ERR_INVALID;
+    if (variant < B200_DECODE_GATED || variant > B200_DECODE_RING || variant == 2) return B200_ERR_INVALID;   // 2 was the retired BULK prototype
     g_decode_variant = variant;
     return B200_OK;
 }
@@ -208,7 +207,6 @@ static int yolo_decode_phase(const b200_yolo_layout* layout, const float* const*
     if (g_ev_decode_begin) B200_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(g_ev_decode_begin), st));
     int rc2 = 1;
     if (g_decode_variant == B200_DECODE_RING) rc2 = launch_decode_filter_ring(p, layout->softmax != 0, w.ticket, st);
-    else if (g_decode_variant == B200_DECODE_BULK) rc2 = launch_decode_filter_bulk(p, layout->softmax != 0, st);
     if (rc2 == 1)   // register path asked for, or the staged tile does not fit in shared memory
         rc2 = launch_decode_filter(p, layout->softmax != 0, g_decode_variant == B200_DECODE_GATED ? 1 : 0, st);
     if (rc2 != B200_OK) return rc2;

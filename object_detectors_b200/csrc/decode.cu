@@ -153,7 +153,12 @@ __device__ __forceinline__ void decode_filter_task(const DecodeParams& p, const 
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         x[u] = HAS_IDF ? __fmul_rn(w[u], v[u][k]) : v[u][k];
-                        if (x[u] > mk) { mk = x[u]; ak = c + u; }
+                        if (x[u] > mk) {
+                            // the reference takes the first maximum of the PROBABILITIES (test_one_epoch.py:35): where
+                            // the fp32 sigmoid is flat (saturated at 1.0f above ~16.6) a larger logit is not a new maximum
+                            if (SOFTMAX || mk == -INFINITY || sigmoid_ref(x[u]) > sigmoid_ref(mk)) ak = c + u;
+                            mk = x[u];
+                        }
                     }
                     m[k] = mk;
                     arg[k] = ak;
@@ -179,7 +184,10 @@ __device__ __forceinline__ void decode_filter_task(const DecodeParams& p, const 
                 if (live[k]) {
                     const float x = HAS_IDF ? __fmul_rn(w, v[k]) : v[k];
                     const float m_old = m[k];
-                    if (x > m_old) { m[k] = x; arg[k] = c; }
+                    if (x > m_old) {
+                        if (SOFTMAX || m_old == -INFINITY || sigmoid_ref(x) > sigmoid_ref(m_old)) arg[k] = c;
+                        m[k] = x;
+                    }
                     if constexpr (SOFTMAX) {
                         float acc = __fmul_rn(s[k], ex2_approx(__fmul_rn(__fsub_rn(m_old, m[k]), kLog2e)));
                         s[k] = __fadd_rn(acc, ex2_approx(__fmul_rn(__fsub_rn(x, m[k]), kLog2e)));
@@ -294,166 +302,7 @@ int launch_decode_filter(const DecodeParams& p, bool softmax, int gate, cudaStre
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }
 
-// ------------------------------------------------------------------------------------------
-// fused decode + filter, TMA bulk-copy variant (the default for heads whose rows are 16 B aligned)
-// ------------------------------------------------------------------------------------------
-// One CTA owns 128 consecutive cells of one (scale, b, a).  Its (5+C) plane-row segments (512 B each)
-// are pulled into shared memory by cp.async.bulk copies that complete on one mbarrier, so a CTA has
-// its whole tile (43.5 KB for COCO) in flight at once and the SM keeps ~5 tiles = ~200 KB
-// outstanding -- far more than the ~45 KB the HBM latency-bandwidth product asks for -- without
-// holding the data in registers.  Threads then work cell-per-thread out of shared memory: a cell
-// whose objectness cannot pass the threshold costs one sigmoid, a live cell runs the exact
-// two-pass softmax (max, then sum of exp) like the reference.  Every byte of the head tensors is
-// fetched exactly once whatever the input looks like.
-// Scales whose plane rows are not 16 B aligned (odd grids: 13, 19, ...) run the register path
-// (decode_filter_task<VEC=1>) inside the same launch.
-static constexpr int kBulkCells = 128;
 
-struct BulkParams {
-    DecodeParams d;
-    int cta_begin[B200_MAX_SCALES + 1];
-    int bulk[B200_MAX_SCALES];        // 1: bulk-copy CTAs, 0: register-path CTAs (4 warp tasks each)
-    int tiles[B200_MAX_SCALES];       // bulk: 128-cell tiles per (b, a)
-};
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-template <bool SOFTMAX, bool HAS_IDF>
-__global__ void __launch_bounds__(kBulkCells)
-k_decode_filter_bulk(const __grid_constant__ BulkParams q) {
-    extern __shared__ __align__(128) float tile[];       // [(5+C)][128]
-    __shared__ __align__(8) unsigned long long bar;
-    const DecodeParams& p = q.d;
-    const int tid = threadIdx.x, lane = tid & 31;
-    int s = 0;
-#pragma unroll
-    for (int i = 1; i < B200_MAX_SCALES; ++i)
-        if (i < p.num_scales && (int)blockIdx.x >= q.cta_begin[i]) s = i;
-    const ScaleDev& sc = p.sc[s];
-    const int local = blockIdx.x - q.cta_begin[s];
-    if (!q.bulk[s]) {
-        const int task = local * 4 + (tid >> 5);
-        if (task >= p.B * p.A * sc.tiles) return;
-        const int t = task % sc.tiles, ba = task / sc.tiles;
-        decode_filter_task<1, SOFTMAX, HAS_IDF, 8, true>(p, sc, ba / p.A, ba % p.A, t, lane);
-        return;
-    }
-    const int tl = local % q.tiles[s];
-    const int ba = local / q.tiles[s];
-    const int a = ba % p.A, b = ba / p.A;
-    const int C = p.C, CH = 5 + C;
-    const int cell0 = tl * kBulkCells;
-    const int ncell = min(kBulkCells, sc.hw - cell0);
-    const unsigned row_bytes = (unsigned)ncell * 4u;
-    const float* base = sc.head + ((size_t)(b * p.A + a) * (size_t)CH) * (size_t)sc.hw + (size_t)cell0;
-    const unsigned bar_a = smem_u32(&bar);
-
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid < 32) {
-        if (tid == 0)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(row_bytes * (unsigned)CH) : "memory");
-        for (int c = lane; c < CH; c += 32) {
-            const unsigned dst = smem_u32(tile + c * kBulkCells);
-            const float* src = base + (size_t)c * (size_t)sc.hw;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(src), "r"(row_bytes), "r"(bar_a) : "memory");
-        }
-    }
-    {   // wait for the tile (phase 0)
-        unsigned done = 0;
-        while (!done)
-            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
-                         : "=r"(done) : "r"(bar_a) : "memory");
-    }
-
-    // ---- cell per thread -------------------------------------------------------------------------
-    const bool in = tid < ncell;
-    float conf = 0.f, score = 0.f;
-    int arg = 0;
-    bool pass = false;
-    if (in) {
-        conf = sigmoid_ref(tile[4 * kBulkCells + tid]);
-        if (conf > p.thr) {                                   // score = conf * maxp <= conf
-            float m = -INFINITY;
-            for (int c = 0; c < C; ++c) {
-                const float x = HAS_IDF ? __fmul_rn(__ldg(p.idf + c), tile[(5 + c) * kBulkCells + tid])
-                                        : tile[(5 + c) * kBulkCells + tid];
-                if (x > m) { m = x; arg = c; }                // first maximum wins
-            }
-            float best;
-            if (SOFTMAX) {
-                float sum = 0.f;
-                for (int c = 0; c < C; ++c) {
-                    const float x = HAS_IDF ? __fmul_rn(__ldg(p.idf + c), tile[(5 + c) * kBulkCells + tid])
-                                            : tile[(5 + c) * kBulkCells + tid];
-                    sum = __fadd_rn(sum, ex2_approx(__fmul_rn(__fsub_rn(x, m), kLog2e)));
-                }
-                best = __fdiv_rn(1.0f, sum);                  // max_c softmax = exp(0) / sum
-            } else {
-                best = sigmoid_ref(m);
-            }
-            score = __fmul_rn(conf, best);                    // test_one_epoch.py:25
-            pass = score > p.thr;                             // :26
-        }
-    }
-    const unsigned bal = __ballot_sync(kFullMask, pass);
-    if (bal == 0u) return;
-    int slot0 = 0;
-    if (lane == 0) slot0 = atomicAdd(p.count + b, __popc(bal));
-    slot0 = __shfl_sync(kFullMask, slot0, 0);
-    if (!pass) return;
-    const int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
-    if (slot >= p.cap) { atomicOr(p.status, 1); return; }
-    const int hw = cell0 + tid;
-    const int gy_i = hw / sc.grid, gx_i = hw - gy_i * sc.grid;
-    const float cx = __fdiv_rn((float)gx_i + 0.5f, sc.inw), cy = __fdiv_rn((float)gy_i + 0.5f, sc.inw);
-    const float bx = __fmul_rn(__fsub_rn(__fadd_rn(sigmoid_ref(tile[0 * kBulkCells + tid]), __fmul_rn(cx, sc.inw)), 0.5f), sc.stride);
-    const float by = __fmul_rn(__fsub_rn(__fadd_rn(sigmoid_ref(tile[1 * kBulkCells + tid]), __fmul_rn(cy, sc.inw)), 0.5f), sc.stride);
-    const float bw = __fmul_rn(__fmul_rn(__fmul_rn(expf(tile[2 * kBulkCells + tid]), sc.anc[a][0]), sc.inw), sc.stride);
-    const float bh = __fmul_rn(__fmul_rn(__fmul_rn(expf(tile[3 * kBulkCells + tid]), sc.anc[a][1]), sc.inw), sc.stride);
-    const Box bb = abs_coord(bx, by, bw, bh);
-    float4* d4 = reinterpret_cast<float4*>(p.slab + (size_t)b * (size_t)p.cap + (size_t)slot);
-    d4[0] = make_float4(bb.x1, bb.y1, bb.x2, bb.y2);
-    d4[1] = make_float4(score, __int_as_float(arg), __int_as_float(sc.anchor_off + hw * p.A + a), 0.f);
-}
-
-// returns B200_OK, or 1 when the tile does not fit in shared memory (caller falls back)
-int launch_decode_filter_bulk(const DecodeParams& p, bool softmax, cudaStream_t stream) {
-    const size_t smem = (size_t)(5 + p.C) * kBulkCells * sizeof(float);
-    if (smem > 100 * 1024) return 1;
-    BulkParams q;
-    q.d = p;
-    int cta = 0;
-    bool any_bulk = false;
-    for (int s = 0; s < p.num_scales; ++s) {
-        q.cta_begin[s] = cta;
-        q.bulk[s] = p.sc[s].vec == 4 ? 1 : 0;
-        q.tiles[s] = cdiv(p.sc[s].hw, kBulkCells);
-        if (q.bulk[s]) { cta += p.B * p.A * q.tiles[s]; any_bulk = true; }
-        else           cta += cdiv(p.B * p.A * p.sc[s].tiles, 4);
-    }
-    for (int s = p.num_scales; s <= B200_MAX_SCALES; ++s) q.cta_begin[s] = cta;
-    if (!any_bulk) return 1;
-    const bool idf = p.idf != nullptr;
-    static SmemOptIn optin[4];
-    const int which = (softmax ? 2 : 0) + (idf ? 1 : 0);
-    cudaError_t e;
-    if (softmax) e = idf ? optin[which].ensure(k_decode_filter_bulk<true, true>, smem) : optin[which].ensure(k_decode_filter_bulk<true, false>, smem);
-    else         e = idf ? optin[which].ensure(k_decode_filter_bulk<false, true>, smem) : optin[which].ensure(k_decode_filter_bulk<false, false>, smem);
-    if (e != cudaSuccess) return B200_ERR_CUDA;
-    if (softmax) {
-        if (idf) k_decode_filter_bulk<true, true><<<cta, kBulkCells, smem, stream>>>(q);
-        else     k_decode_filter_bulk<true, false><<<cta, kBulkCells, smem, stream>>>(q);
-    } else {
-        if (idf) k_decode_filter_bulk<false, true><<<cta, kBulkCells, smem, stream>>>(q);
-        else     k_decode_filter_bulk<false, false><<<cta, kBulkCells, smem, stream>>>(q);
-    }
-    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
-}
 
 // ------------------------------------------------------------------------------------------
 // dense decode: out[b, n, 0:5+C]

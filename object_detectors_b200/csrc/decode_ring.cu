@@ -365,10 +365,22 @@ k_decode_filter_ring(const __grid_constant__ RingParams q) {
                     varg = c_lo - 5 + lane + 32 * varg;
                     const unsigned key = orderable(vmax);
                     const unsigned kmax = __reduce_max_sync(kFullMask, key);
-                    amin[u] = (int)__reduce_min_sync(kFullMask, key == kmax ? (unsigned)varg : 0x7fffffffu);   // ... and across lanes
+                    unsigned mine = key == kmax ? (unsigned)varg : 0x7fffffffu;
                     vmax = from_orderable(kmax);
                     const float m_old = my_m[min(i0 + u, nl - 1)];
                     up[u] = vmax > m_old;                                    // strict: earlier chunks win ties
+                    if (!SOFTMAX && vmax > 5.0f) {
+                        // The reference takes the first maximum of the PROBABILITIES (test_one_epoch.py:35).  Where the
+                        // fp32 sigmoid is flat -- it saturates at 1.0f above ~16.6 and its steps widen to 0.2 at 15 --
+                        // smaller logits tie with the largest one and the lowest class index wins.
+                        const float pm = sigmoid_ref(vmax);
+#pragma unroll
+                        for (int k = 0; k < kRowsPerLane; ++k)
+                            if (x[u][k] > fminf(vmax, 17.0f) - 8.0f && sigmoid_ref(x[u][k]) == pm)
+                                mine = min(mine, (unsigned)(c_lo - 5 + lane + 32 * k));
+                        if (up[u] && m_old > -INFINITY && sigmoid_ref(m_old) == pm) up[u] = false;    // an earlier chunk already holds it
+                    }
+                    amin[u] = (int)__reduce_min_sync(kFullMask, mine);       // ... and across lanes
                     m_new[u] = up[u] ? vmax : m_old;
                     s_new[u] = 0.f;
                     if (SOFTMAX) {

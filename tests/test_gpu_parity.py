@@ -321,7 +321,7 @@ def test_rpn_filter(shape, bsz, pre, post, strategy, nms_path):
 
 @pytest.mark.parametrize("name", ["c1_416_idf", "c2_608_b4", "odd_grid_352", "lvis_96_a6", "tiny_sigmoid"])
 def test_decode_variants_agree(name):
-    """The four fetch strategies of the fused decode kernel (gated / stream / TMA bulk / TMA ring) must give the
+    """The three fetch strategies of the fused decode kernel (gated / stream / TMA ring) must give the
     same candidates: identical anchor sets and labels, values equal up to the softmax summation order."""
     from object_detectors_b200 import _lib
     ops = _ops()
@@ -331,7 +331,7 @@ def test_decode_variants_agree(name):
     gi = None if idf is None else idf.cuda()
     outs = []
     try:
-        for variant in (_lib.DECODE_GATED, _lib.DECODE_STREAM, _lib.DECODE_BULK, _lib.DECODE_RING):
+        for variant in (_lib.DECODE_GATED, _lib.DECODE_STREAM, _lib.DECODE_RING):
             assert lib.b200_set_decode_variant(variant) == 0
             o = ops.yolo_decode_filter(gh, anchors, img, c, gi, softmax, 0.1)
             torch.cuda.synchronize()
@@ -385,3 +385,42 @@ def test_c2_full_size_end_to_end(nms_path):
             total_c += n
             total_k += k
     assert (total_c, total_k) == (40762, 8365)
+
+
+def test_sigmoid_label_is_first_maximum_of_the_probabilities():
+    """in sigmoid mode the reference's label is the first maximum of the fp32 PROBABILITIES
+    (test_one_epoch.py:35), not of the logits: where the sigmoid is saturated (1.0f above ~16.6) or flat, several classes
+    tie and the lowest class index wins.  Cells are planted with such ties; every decode variant must label them like
+    the oracle."""
+    from object_detectors_b200 import _lib
+    ops = _ops()
+    lib = _lib.load()
+    img, c, b = 128, 80, 2
+    heads = syn.yolo_heads(23, b, img, c, syn.COCO_ANCHORS, "clustered", sigmoid_cls=True, max_objects=4)
+    g = np.random.default_rng(5)
+    planted = 0
+    for h in heads:
+        bsz, ch, gh, gw = h.shape
+        t = h.reshape(bsz, 3, 5 + c, gh, gw)
+        for _ in range(6):
+            bi, a, y, x = int(g.integers(bsz)), int(g.integers(3)), int(g.integers(gh)), int(g.integers(gw))
+            t[bi, a, 4, y, x] = 4.0                                  # live cell
+            lo, hi = sorted(g.choice(c, size=2, replace=False).tolist())
+            t[bi, a, 5 + lo, y, x] = 18.0 + g.random()               # saturated: sigmoid == 1.0f
+            t[bi, a, 5 + hi, y, x] = 30.0 + g.random()               # larger logit, same probability, HIGHER index
+            planted += 1
+    ref = yolo_ref.score_filter(yolo_ref.decode([torch.from_numpy(h) for h in heads], syn.COCO_ANCHORS, img, c, None, False), 0.1)
+    gh_ = _gpu_heads(heads)
+    try:
+        for variant in (_lib.DECODE_GATED, _lib.DECODE_STREAM, _lib.DECODE_RING):
+            assert lib.b200_set_decode_variant(variant) == 0
+            out = ops.yolo_decode_filter(gh_, syn.COCO_ANCHORS, img, c, None, False, 0.1)
+            for i in range(b):
+                n = int(out["count"][i])
+                assert n == ref[i]["det6"].shape[0]
+                np.testing.assert_array_equal(out["anchor"][i, :n].cpu().numpy(), ref[i]["anchor"].numpy().astype(np.int32))
+                np.testing.assert_array_equal(out["label"][i, :n].cpu().numpy(), ref[i]["det6"].numpy()[:, 5].astype(np.int32),
+                                              err_msg=f"variant {variant}")
+    finally:
+        lib.b200_set_decode_variant(_lib.DECODE_RING)
+    assert planted == 18
