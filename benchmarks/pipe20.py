@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--ring", default="4,1,101")
     ap.add_argument("--chains", type=int, default=3)
     ap.add_argument("--split", default="")
-    ap.add_argument("--nms", default="auto", choices=["auto", "general", "fused"])
+    ap.add_argument("--nms", default="auto", choices=["auto", "general", "fused", "fused256"])
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--reps", type=int, default=5)
@@ -43,7 +43,7 @@ def main():
     lib = _lib.load()
     lib.b200_set_decode_variant(3)
     lib.b200_debug_set_ring(*[int(x) for x in args.ring.split(",")])
-    lib.b200_debug_set_nms_path({"auto": -1, "general": 1, "fused": 0}[args.nms])
+    lib.b200_debug_set_nms_path({"auto": -1, "general": 1, "fused": 0, "fused256": 2}[args.nms])
     if args.resolve:
         lib.b200_debug_set_resolve(*[int(x) for x in args.resolve.split(",")])
     heads = [torch.from_numpy(h).to(dev) for h in syn.yolo_heads(1000, BATCH, IMG, NC, syn.COCO_ANCHORS, args.gen)]

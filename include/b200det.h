@@ -178,8 +178,10 @@ int b200_debug_set_resolve_prof(void* buf);
 /* NMS kernel path (process-wide): 1 = the general three-launch path (plan / pairs / resolve: spatially pruned tile
  * pairs, small CTAs that co-reside with the streaming decode kernel), 0 = segments of <= 4096 boxes take the
  * single-launch path (nms_fused.cu: no work queue, no cross-kernel dependencies), -1 (default) = by workload:
- * candidate slabs of the YOLO post-process -> general, array inputs (nms / batched_nms, RPN, ROI heads) ->
- * single-launch.  Both produce identical results (the tests run the NMS cases through both). */
+ * candidate slabs of the YOLO post-process -> general for segments above 1500 boxes plus a 256-thread single-launch
+ * kernel for the rest, array inputs (nms / batched_nms, RPN, ROI heads) -> single-launch, 2 = the 256-thread
+ * single-launch kernel for every segment (measurement only).  All produce identical results (the tests run the NMS
+ * cases through the general and the single-launch path). */
 int b200_debug_set_nms_path(int general);
 /* Tuning hook: launch shape of the NMS resolve CTAs (threads: multiple of 32 in 64..1024, dynamic shared memory
  * in KB 16..200; out-of-range values keep the current setting).  Default 1024 threads, 112 KB. */

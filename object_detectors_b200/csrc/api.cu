@@ -173,7 +173,7 @@ int b200_debug_set_resolve(int threads, int smem_kb) {
     if (smem_kb >= 16 && smem_kb <= 200) b200::g_resolve_smem_kb = smem_kb;
     return B200_OK;
 }
-int b200_debug_set_nms_path(int general) { b200::g_nms_force_general = general < 0 ? -1 : (general ? 1 : 0); return B200_OK; }
+int b200_debug_set_nms_path(int general) { b200::g_nms_force_general = general < 0 ? -1 : (general > 2 ? 1 : general); return B200_OK; }
 int b200_debug_set_resolve_prof(void* buf) { b200::g_resolve_prof = static_cast<long long*>(buf); return B200_OK; }
 static void* g_ev_decode_begin = nullptr;
 static void* g_ev_decode_end = nullptr;

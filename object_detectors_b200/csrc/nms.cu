@@ -1027,6 +1027,12 @@ int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
     P.split_lo = 0;
     P.split_hi = 0x7fffffff;
     const bool fused_ok = nms_fused_eligible(P);
+    if (fused_ok && P.force_general == 2) {                 // debug: the 256-thread instantiation for every segment
+        P.split_lo = -1;
+        const int rc = launch_nms_fused(P, num_segments, stream);
+        if (g_nms_timeline[2]) cudaEventRecord(g_nms_timeline[2], stream);
+        return rc;
+    }
     if (fused_ok && (P.force_general == 0 || (P.force_general < 0 && !P.from_slab))) {
         const int rc = launch_nms_fused(P, num_segments, stream);
         if (g_nms_timeline[2]) cudaEventRecord(g_nms_timeline[2], stream);

@@ -551,7 +551,7 @@ __device__ void fused_segment(const NmsParams& P, int seg, int member, int team,
     long long off;
     int n, n_true;
     segment_range(P, seg, off, n, n_true);
-    if (n <= P.split_lo && (n > 0 || P.split_lo > 0)) return;          // the general path's segment (it also writes n == 0)
+    if (P.split_lo > 0 && n <= P.split_lo) return;          // the general path's segment (it also writes n == 0)
     if (tid == 0 && member == 0 && SLAB && P.cand_count_out) P.cand_count_out[seg] = n_true;
     if (n == 0) {
         if (tid == 0 && member == 0) {
@@ -702,7 +702,7 @@ int launch_nms_fused(NmsParams& P, int num_segments, cudaStream_t stream) {
     // a lone small segment does not need the whole chip: at most one CTA per row tile
     const long long useful = (long long)num_segments * (P.max_words > 0 ? P.max_words : 1);
     const int sms = current_sm_count();
-    if (P.split_lo > 0) {
+    if (P.split_lo != 0) {
         // beside the general path (large segments of a candidate slab only): small CTAs, two per SM, that start next
         // to the streaming decode kernel and leave at once when the batch has no large segment
         int grid = 2 * sms;

@@ -57,6 +57,12 @@ struct RpnParams {
     int cand_stride;                  // candidates per image = sum_l slices_l * k_l (multi-slice levels only)
     unsigned long long* cand;         // [B, cand_stride] (~key << 32 | index inside the level)
     int* sel_counter;                 // [B * L] slice arrival counters (zeroed before the launch)
+    // sampled threshold (levels much larger than k): candidates = everything at least as good as a sample quantile
+    int level_mode[kMaxLevels];       // 0: one slice, 1: slices keep their local top k, 2: sampled threshold
+    int level_cap[kMaxLevels];        // mode 2: capacity of the level's candidate list
+    int level_rank[kMaxLevels];       // mode 2: rank of the threshold inside the sample
+    unsigned* thr;                    // [B * L] mode 2: threshold in key space (smaller = better)
+    int* cand_count;                  // [B * L] mode 2: candidates appended (may exceed the capacity: then fallback)
     // many-class heads (RetinaNet): a level is [anchors_l, C] logits, flattened; C == 1 for the RPN
     int C;                            // classes per anchor
     const float* class_scale;         // [C] or nullptr: logits are multiplied by it before the sigmoid (tfidf_post)
@@ -401,6 +407,31 @@ __device__ void select_block(const unsigned* vals, int cnt, int k, unsigned long
     __syncthreads();
 }
 
+__device__ int select_level_global(const RpnParams& P, int b, int l, unsigned long long* sel);
+
+static constexpr int kSample = 4096;          // logits sampled per level for the threshold estimate
+
+// Levels much larger than k (mode 2): a sample of kSample evenly spaced logits estimates a threshold that keeps about
+// twice the wanted count (the order statistic `level_rank` of the sample), so that ONE compaction pass over the level
+// -- no shared-memory slice, no histogram -- yields a candidate list of a few thousand entries that surely holds the
+// top k.  "Surely" is statistics (k sits 6-7 standard deviations below the expected count), so it is verified: a level
+// whose list ends up shorter than k or longer than its capacity is redone by select_level_global.
+__global__ void __launch_bounds__(kSelThreads, 1)
+k_rpn_sample(const __grid_constant__ RpnParams P) {
+    __shared__ unsigned keys[kSample];
+    __shared__ SelShared S;
+    const int l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    if (P.level_mode[l] != 2) return;
+    const int n = P.level_n[l];
+    const float* src = P.obj + (size_t)b * P.total + P.level_off[l];
+    for (int j = tid; j < kSample; j += kSelThreads) keys[j] = ~orderable(level_logit(P, src, (int)((long long)j * n / kSample)));
+    __syncthreads();
+    unsigned T;
+    int take_eq;
+    pick_smallest(keys, kSample, P.level_rank[l], S, 0u, 0u, 3, T, take_eq);
+    if (tid == 0) P.thr[b * P.L + l] = T;
+}
+
 // Level l of image b is cut into R_l = ceil(n_l / kSliceMax) slices, one CTA each.  A CTA reads its slice ONCE
 // (order-preserving keys into shared memory), selects its local top min(k, m) there -- a superset of its share of
 // the level's top k -- and appends them to the level's candidate list.  The CTA that arrives last at the level's
@@ -424,12 +455,49 @@ k_rpn_select_sliced(const __grid_constant__ RpnParams P) {
     const int per = (((n + R - 1) / R) + 3) & ~3;
     const int i0 = min(n, r * per), m = min(n, i0 + per) - i0;
 
+    int got;
+    unsigned long long* sel;
+    if (P.level_mode[l] == 2) {
+        // ---- sampled threshold: one compaction pass, nothing staged ----------------------------------------------------
+        const int lane = tid & 31;
+        const unsigned T0 = P.thr[b * P.L + l];
+        const int capL = P.level_cap[l];
+        unsigned long long* cand = P.cand + ((size_t)b * P.cand_stride + P.level_coff[l]);
+        int* ccount = P.cand_count + b * P.L + l;
+        for (int i = tid; i - lane < m; i += kSelThreads) {
+            const unsigned v = i < m ? ~orderable(level_logit(P, src, i0 + i)) : ~0u;
+            const bool pass = i < m && v <= T0;
+            const unsigned bal = __ballot_sync(kFullMask, pass);
+            if (!bal) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(ccount, __popc(bal));
+            base = __shfl_sync(kFullMask, base, 0);
+            const int at = base + __popc(bal & ((1u << lane) - 1u));
+            if (pass && at < capL) cand[at] = ((unsigned long long)v << 32) | (unsigned)(i0 + i);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) S.last = atomicAdd(P.sel_counter + b * P.L + l, 1) == R - 1;
+        __syncthreads();
+        if (!S.last) return;
+        __threadfence();
+        const int cnt = *reinterpret_cast<volatile int*>(ccount);
+        if (cnt < min(k, n) || cnt > capL) {
+            // the sample misjudged the level (too few candidates, or more than the list holds): robust path
+            sel = reinterpret_cast<unsigned long long*>(after);
+            got = select_level_global(P, b, l, sel);
+        } else {
+            for (int i = tid; i < cnt; i += kSelThreads) keys[i] = (unsigned)(__ldcg(cand + i) >> 32);
+            __syncthreads();
+            sel = reinterpret_cast<unsigned long long*>(after + (((size_t)cnt * 4 + 15) & ~(size_t)15));
+            select_block(keys, cnt, k, sel, [&](int i) { return (unsigned)__ldcg(cand + i); }, S, nv, ni);
+            got = min(k, cnt);
+        }
+    } else {
     // ---- the one read of the logits ---------------------------------------------------------------------------------
     for (int i = tid; i < m; i += kSelThreads) keys[i] = ~orderable(level_logit(P, src, i0 + i));
     __syncthreads();
 
-    int got;
-    unsigned long long* sel;
     if (R == 1) {
         // the slice is the level: select straight into the sort buffer behind the keys
         sel = reinterpret_cast<unsigned long long*>(after + (((size_t)m * 4 + 15) & ~(size_t)15));
@@ -463,27 +531,22 @@ k_rpn_select_sliced(const __grid_constant__ RpnParams P) {
         }, S, nv, ni);
         got = min(k, total);
     }
+    }
     int Ppad = 1;
     while (Ppad < got) Ppad <<= 1;
     rpn_finish_level(P, b, l, sel, got, Ppad, src, S.scan);
 }
 
-__global__ void __launch_bounds__(kSelThreads, 1)
-k_rpn_select(const __grid_constant__ RpnParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem_raw);  // [pow2(k)]
+// Robust single-CTA select over the level in GLOBAL memory (four histogram passes + one collection pass): the general
+// fallback -- levels whose shared-memory plan does not fit, and sampled levels whose sample misjudged the threshold.
+// Fills sel[0 .. got) with (~key << 32 | index inside the level) and returns got = min(k, n).
+__device__ int select_level_global(const RpnParams& P, int b, int l, unsigned long long* sel) {
     __shared__ int hist[256];
     __shared__ unsigned s_prefix, s_mask;
     __shared__ int s_remaining, s_cnt, s_tie;
-    __shared__ int s_scan[kSelWarps];
-
-    const int l = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = P.level_n[l], k = P.level_k[l];
     const float* src = P.obj + (size_t)b * P.total + P.level_off[l];
-    int Ppad = 1;
-    while (Ppad < k) Ppad <<= 1;
-
     // ---- radix select: key of the k-th largest logit ------------------------------------------
     if (tid == 0) { s_prefix = 0u; s_mask = 0u; s_remaining = k; s_cnt = 0; s_tie = 0; }
     __syncthreads();
@@ -542,7 +605,19 @@ k_rpn_select(const __grid_constant__ RpnParams P) {
         }
     }
     __syncthreads();
-    const int got = s_cnt;  // == k
+    return s_cnt;  // == min(k, n)
+}
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+k_rpn_select(const __grid_constant__ RpnParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem_raw);  // [pow2(k)]
+    __shared__ int s_scan[kSelWarps];
+    const int l = blockIdx.x, b = blockIdx.y;
+    const float* src = P.obj + (size_t)b * P.total + P.level_off[l];
+    const int got = select_level_global(P, b, l, sel);
+    int Ppad = 1;
+    while (Ppad < got) Ppad <<= 1;
     rpn_finish_level(P, b, l, sel, got, Ppad, src, s_scan);
 }
 
@@ -702,32 +777,56 @@ static int launch_rpn_select(RpnParams& P, int kmax, void* sel_ws, size_t sel_ws
     // shared-memory plan of the sliced kernel: the slice keys, or (last CTA) the candidates' keys + the sort buffer
     int slices = 0, coff = 0;
     size_t smem = 0;
+    bool any_sampled = false;
     for (int l = 0; l < P.L; ++l) {
         const int n = P.level_n[l], k = P.level_k[l];
-        const int R = (n + kSliceMax - 1) / kSliceMax;
-        const int per = (((n + R - 1) / R) + 3) & ~3;
         int kp = 1;
         while (kp < k) kp <<= 1;
-        P.level_slices[l] = R;
+        size_t need;
         P.level_coff[l] = coff;
-        size_t need = (size_t)per * 4;
-        if (R == 1) need = (((size_t)n * 4 + 15) & ~(size_t)15) + (size_t)kp * 8;
-        else {
+        if (n <= kSliceMax) {
+            P.level_mode[l] = 0;
+            P.level_slices[l] = 1;
+            need = (((size_t)n * 4 + 15) & ~(size_t)15) + (size_t)kp * 8;
+        } else if ((long long)n >= 8ll * k && n >= 4 * kSample) {
+            // sampled threshold: keep ~2k (+ a margin of 32 sample ranks), list capacity twice the expectation
+            P.level_mode[l] = 2;
+            const int rank = (int)((2ll * k * kSample + n - 1) / n) + 32;
+            P.level_rank[l] = rank < kSample - 1 ? rank : kSample - 1;
+            const long long expect = (long long)P.level_rank[l] * n / kSample;
+            long long cap = 2 * expect > 4ll * k ? 2 * expect : 4ll * k;
+            if (cap > 16384) cap = 16384;
+            P.level_cap[l] = (int)cap;
+            P.level_slices[l] = (n + 8191) / 8192;
+            coff += P.level_cap[l];
+            const size_t global_sel = (size_t)kp * 8;                               // fallback sorts out of the same buffer
+            need = (((size_t)cap * 4 + 15) & ~(size_t)15) + (size_t)kp * 8;
+            need = need > global_sel ? need : global_sel;
+            any_sampled = true;
+        } else {
+            P.level_mode[l] = 1;
+            const int R = (n + kSliceMax - 1) / kSliceMax;
+            const int per = (((n + R - 1) / R) + 3) & ~3;
+            P.level_slices[l] = R;
             coff += R * k;
+            need = (size_t)per * 4;
             const size_t merge = (((size_t)R * (k < per ? k : per) * 4 + 15) & ~(size_t)15) + (size_t)kp * 8;
             need = need > merge ? need : merge;
         }
         smem = smem > need ? smem : need;
-        slices += R;
+        slices += P.level_slices[l];
     }
     smem += 2 * sizeof(unsigned) * (size_t)kNarrowMax;            // the compact refinement list
     P.cand_stride = coff;
     const size_t cand_bytes = align_up(sizeof(unsigned long long) * (size_t)P.B * (size_t)(coff > 0 ? coff : 1), 256);
-    const size_t cnt_bytes = align_up(sizeof(int) * (size_t)P.B * P.L, 256);
+    const size_t cnt_bytes = align_up(sizeof(int) * 3 * (size_t)P.B * P.L, 256);
     if (smem <= 200 * 1024 && slices <= 65535 && sel_ws && sel_ws_bytes >= cand_bytes + cnt_bytes) {
         P.cand = reinterpret_cast<unsigned long long*>(sel_ws);
         P.sel_counter = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(sel_ws) + cand_bytes);
-        if (cudaMemsetAsync(P.sel_counter, 0, sizeof(int) * (size_t)P.B * P.L, stream) != cudaSuccess) return B200_ERR_CUDA;
+        P.cand_count = P.sel_counter + (size_t)P.B * P.L;
+        P.thr = reinterpret_cast<unsigned*>(P.cand_count + (size_t)P.B * P.L);
+        if (cudaMemsetAsync(P.sel_counter, 0, sizeof(int) * 2 * (size_t)P.B * P.L, stream) != cudaSuccess) return B200_ERR_CUDA;
+        if (any_sampled) k_rpn_sample<<<dim3(P.L, P.B), kSelThreads, 0, stream>>>(P);
         if (optin3.ensure(k_rpn_select_sliced, 200 * 1024) != cudaSuccess) return B200_ERR_CUDA;
         k_rpn_select_sliced<<<dim3(slices, P.B), kSelThreads, smem, stream>>>(P);
     } else {
@@ -740,8 +839,9 @@ static int launch_rpn_select(RpnParams& P, int kmax, void* sel_ws, size_t sel_ws
 // scratch of the sliced select: candidate lists of the multi-slice levels (<= 8 bytes x pre_k per started slice) + counters
 static size_t rpn_select_ws_bytes(int batch, int total, int num_levels, int pre_k) {
     const size_t slices = (size_t)(total + kSliceMax - 1) / kSliceMax + (size_t)num_levels;
-    return align_up(sizeof(unsigned long long) * (size_t)batch * slices * (size_t)pre_k, 256) +
-           align_up(sizeof(int) * (size_t)batch * num_levels, 256) + 256;
+    const size_t per_image = slices * (size_t)pre_k + 16384 * (size_t)num_levels;      // local-top-k lists or sampled lists
+    return align_up(sizeof(unsigned long long) * (size_t)batch * per_image, 256) +
+           align_up(sizeof(int) * 3 * (size_t)batch * num_levels, 256) + 256;
 }
 
 size_t rpn_workspace_bytes(int batch, int total, int num_levels, int pre_k) {

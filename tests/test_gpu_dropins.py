@@ -585,3 +585,26 @@ def test_ssd_postprocess_detections_bound_like_the_reference(strategy):
         assert np.all(np.abs(b - rb.numpy()) <= 1e-5 * np.maximum(np.abs(rb.numpy()), img))
         if strategy == "torchvision":
             np.testing.assert_array_equal(got[i]["labels"].cpu().numpy(), gold[f"labels_{i}"])
+
+
+@pytest.mark.parametrize("case", ["overflow", "underflow"])
+def test_rpn_top_n_idx_when_the_sample_misjudges_the_level(case):
+    """Large levels estimate their threshold from 4096 evenly spaced logits.  Adversarial inputs: the largest logits all
+    sit on unsampled positions and outnumber the candidate list (overflow), or ONLY the sampled positions are large
+    (underflow: far too few candidates).  Both must fall back to the exhaustive select and still return topk's list."""
+    from object_detectors_b200 import ops
+    g = np.random.default_rng(17)
+    n, k = 201600, 2000
+    obj = (g.standard_normal((2, n)) * 2 - 3).astype(np.float32)
+    sampled = np.unique((np.arange(4096, dtype=np.int64) * n) // 4096)
+    if case == "overflow":
+        free = np.setdiff1d(np.arange(n), sampled)
+        hot = g.choice(free, size=20000, replace=False)
+        for b in range(2):                                                    # tie-free: a shuffled ramp
+            obj[b, hot] = (10.0 + g.permutation(20000) * 2e-4).astype(np.float32)
+    else:
+        for b in range(2):
+            obj[b, sampled] = (20.0 + g.permutation(sampled.size) * 2e-3).astype(np.float32)
+    got = ops.rpn_top_n_idx(torch.from_numpy(obj).cuda(), [n], k).cpu()
+    want = torch.from_numpy(obj).topk(k, dim=1)[1]
+    np.testing.assert_array_equal(got.numpy(), want.numpy())
