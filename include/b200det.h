@@ -175,6 +175,9 @@ int b200_debug_set_timeline(void* after_plan, void* after_pairs, void* after_res
 /* Profiling hook: device buffer int64[segments, 16] that the resolve kernel fills with clock64 stamps at its
  * phase boundaries (A stage, B fixed point, C vote, D order, E emit, end) + n and K; NULL to disable. */
 int b200_debug_set_resolve_prof(void* buf);
+/* Same for the per-level select of the RPN / RetinaNet filter: int64[levels * batch, 8] globaltimer stamps of each
+ * level's CTA (start, -, staged, selected, sorted, done) + level and slice; NULL to disable. */
+int b200_debug_set_rpn_prof(void* buf);
 /* NMS kernel path (process-wide): 1 = the general three-launch path (plan / pairs / resolve: spatially pruned tile
  * pairs, small CTAs that co-reside with the streaming decode kernel), 0 = segments of <= 4096 boxes take the
  * single-launch path (nms_fused.cu: no work queue, no cross-kernel dependencies), -1 (default) = by workload:

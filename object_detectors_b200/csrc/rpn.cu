@@ -61,6 +61,7 @@ struct RpnParams {
     int level_mode[kMaxLevels];       // 0: one slice, 1: slices keep their local top k, 2: sampled threshold
     int level_cap[kMaxLevels];        // mode 2: capacity of the level's candidate list
     int level_rank[kMaxLevels];       // mode 2: rank of the threshold inside the sample
+    int level_chunks[kMaxLevels];     // mode 2: CTAs of k_rpn_pass (4096 logits each), 0 for the other modes
     unsigned* thr;                    // [B * L] mode 2: threshold in key space (smaller = better)
     int* cand_count;                  // [B * L] mode 2: candidates appended (may exceed the capacity: then fallback)
     // many-class heads (RetinaNet): a level is [anchors_l, C] logits, flattened; C == 1 for the RPN
@@ -72,7 +73,16 @@ struct RpnParams {
     int atotal;                       // anchors per image (= total / C): row count of deltas / proposals
     int* out_labels;                  // [B, post_k] or nullptr
     int* img_start; int* img_count;   // [B] image-wide segments (k_rpn_compact)
+    long long* prof;                  // debug: [CTAs of the sliced select, 8] globaltimer stamps (b200_debug_set_rpn_prof)
 };
+
+__device__ __forceinline__ void rpn_stamp(const RpnParams& P, int slot) {
+    if (P.prof && threadIdx.x == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.prof[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+    }
+}
 
 // the logit the selection orders by: raw objectness, or tfidf_post[c] * logit for many-class heads
 __device__ __forceinline__ float level_logit(const RpnParams& P, const float* src, int j) {
@@ -81,10 +91,72 @@ __device__ __forceinline__ float level_logit(const RpnParams& P, const float* sr
     return __fmul_rn(__ldg(P.class_scale + (j - (j / P.C) * P.C)), x);
 }
 
-// ascending bitonic sort of key[0..P) in shared memory, P a power of two.  Steps with a partner distance below 64
-// stay inside aligned blocks of 64 keys and are done by one warp per block without CTA barriers.
-__device__ __forceinline__ void bitonic_sort_u64(unsigned long long* key, int P) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+// Ascending bitonic sort of key[0..N) in shared memory, N a power of two; every thread of the CTA calls it.
+// Thread t keeps the E = max(1, N / 1024) keys [t*E, t*E + E) in registers: compare-exchange steps with a partner
+// distance below E are register moves, below 32*E warp shuffles, and only the remaining steps (15 of the 91 for 8192
+// keys) go through shared memory, with the array itself as the exchange buffer (transposed: conflict-free).
+template <int E>
+__device__ __forceinline__ void bitonic_regs(unsigned long long* key, int N) {
+    const int tid = threadIdx.x;
+    const int T = N / E;                       // active threads: a multiple of 32 (N >= 64)
+    const bool active = tid < T;
+    unsigned long long a[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) a[e] = active ? key[tid * E + e] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= N; k <<= 1) {
+        int j = k >> 1;
+        for (; j >= 32 * E; j >>= 1) {         // partner in another warp
+            const int m = j / E;
+            const bool keep_min = ((tid & m) == 0) == (((tid * E) & k) == 0);
+            if (active) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) key[e * T + tid] = a[e];
+            }
+            __syncthreads();
+            if (active) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const unsigned long long o = key[e * T + (tid ^ m)];
+                    a[e] = keep_min ? (a[e] < o ? a[e] : o) : (a[e] < o ? o : a[e]);
+                }
+            }
+            __syncthreads();
+        }
+        if (active) {
+            for (; j >= E; j >>= 1) {          // partner in another lane
+                const int m = j / E;
+                const bool keep_min = ((tid & m) == 0) == (((tid * E) & k) == 0);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const unsigned long long o = __shfl_xor_sync(kFullMask, a[e], m);
+                    a[e] = keep_min ? (a[e] < o ? a[e] : o) : (a[e] < o ? o : a[e]);
+                }
+            }
+#pragma unroll
+            for (int jj = E >> 1; jj > 0; jj >>= 1) {      // partner in this thread
+                if (jj < k) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        if ((e & jj) == 0) {
+                            const bool asc = ((tid * E + e) & k) == 0;
+                            const unsigned long long x = a[e], y = a[e | jj];
+                            if ((x > y) == asc) { a[e] = y; a[e | jj] = x; }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) key[tid * E + e] = a[e];
+    }
+    __syncthreads();
+}
+
+__device__ __noinline__ void bitonic_sort_u64(unsigned long long* key, int P) {
+    const int tid = threadIdx.x;
     if (P < 64) {
         for (int k = 2; k <= P; k <<= 1)
             for (int j = k >> 1; j > 0; j >>= 1) {
@@ -98,51 +170,24 @@ __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* key, int P)
             }
         return;
     }
-    for (int base = warp * 64; base < P; base += nwarp * 64) {
-        unsigned long long* kk = key + base;
-        for (int k = 2; k <= 64; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                const int i = ((lane & ~(j - 1)) << 1) | (lane & (j - 1));
-                const int ixj = i | j;
-                const unsigned long long a = kk[i], b = kk[ixj];
-                if ((a > b) == (((base + i) & k) == 0)) { kk[i] = b; kk[ixj] = a; }
-                __syncwarp();
-            }
-    }
-    __syncthreads();
-    for (int k = 128; k <= P; k <<= 1) {
-        for (int j = k >> 1; j >= 64; j >>= 1) {
-            for (int t = tid; t < (P >> 1); t += blockDim.x) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int ixj = i | j;
-                const unsigned long long a = key[i], b = key[ixj];
-                if ((a > b) == ((i & k) == 0)) { key[i] = b; key[ixj] = a; }
-            }
-            __syncthreads();
-        }
-        for (int base = warp * 64; base < P; base += nwarp * 64) {
-            unsigned long long* kk = key + base;
-            const bool asc = (base & k) == 0;
-            for (int j = 32; j > 0; j >>= 1) {
-                const int i = ((lane & ~(j - 1)) << 1) | (lane & (j - 1));
-                const int ixj = i | j;
-                const unsigned long long a = kk[i], b = kk[ixj];
-                if ((a > b) == asc) { kk[i] = b; kk[ixj] = a; }
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-    }
+    if (P <= 1024) bitonic_regs<1>(key, P);
+    else if (P == 2048) bitonic_regs<2>(key, P);
+    else if (P == 4096) bitonic_regs<4>(key, P);
+    else if (P == 8192) bitonic_regs<8>(key, P);
+    else bitonic_regs<16>(key, P);
 }
 
 // sorted selection -> (optional) index list, else decode / clip / filter in order.  `sel` holds `got` keys
-// (~orderable(score) << 32 | index inside the level) in shared memory, padded to Ppad.
+// (~orderable(score) << 32 | index inside the level) in shared memory, with room for Ppad (a power of two >= got).
 __device__ void rpn_finish_level(const RpnParams& P, int b, int l, unsigned long long* sel, int got, int Ppad, const float* src,
                                  int* s_scan) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = got + tid; i < Ppad; i += kSelThreads) sel[i] = ~0ull;
-    __syncthreads();
-    bitonic_sort_u64(sel, Ppad);
+    if (Ppad) {                                        // Ppad == 0: sel[0..got) already is sorted
+        for (int i = got + tid; i < Ppad; i += kSelThreads) sel[i] = ~0ull;
+        __syncthreads();
+        bitonic_sort_u64(sel, Ppad);
+    }
+    rpn_stamp(P, 4);
     const size_t out0 = (size_t)b * P.Ktot + P.level_koff[l];
     if (P.topk_out) {
         for (int r = tid; r < got; r += kSelThreads) P.topk_out[out0 + r] = P.level_off[l] + (int)(unsigned)sel[r];
@@ -263,6 +308,89 @@ __device__ __forceinline__ void find_bin(const int* hist, int rem, int& bin, int
     in_bin = __shfl_sync(kFullMask, fin, src);
 }
 
+// ------------------------------------------------------------------------------------------ bucket sort
+static constexpr int kBuckets = 2048;        // value-linear buckets between the best and the worst candidate
+static constexpr int kBucketRun = 1024;      // longest bucket that is still ranked by counting
+
+// The kk = min(k, cnt) smallest of cnt keys (value << 32 | index; value = ~orderable(logit)) in ascending order into
+// out[0..kk) -- exactly what a full sort would put there -- without a sorting network: a histogram over kBuckets
+// buckets that are linear in the LOGIT (a monotone map: the order of the buckets is the order of the keys), a scan, a
+// scatter of the buckets up to the one that holds rank kk, and a rank-by-counting inside each (short) bucket.
+// Eight barriers instead of the ~90 steps of a bitonic network.  Returns kk, or -1 when the distribution defeats
+// the buckets (non-finite or all-equal values, a bucket longer than kBucketRun, more than tmp_cap entries up to the
+// threshold bucket): the caller then sorts the slow way.  `out` may alias the storage `load` reads from.
+template <typename Load>
+__device__ int bucket_sort_topk(Load load, int cnt, int k, unsigned long long* tmp, int tmp_cap, unsigned long long* out,
+                                int* start, int* fill, SelShared& S) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kk = min(k, cnt);
+    unsigned vmin = ~0u, vmax = 0u;
+    for (int i = tid; i < cnt; i += kSelThreads) {
+        const unsigned v = (unsigned)(load(i) >> 32);
+        vmin = min(vmin, v); vmax = max(vmax, v);
+    }
+    vmin = __reduce_min_sync(kFullMask, vmin);
+    vmax = __reduce_max_sync(kFullMask, vmax);
+    if (lane == 0) { S.scan[warp] = (int)vmin; S.hist[warp] = (int)vmax; }
+    for (int i = tid; i < kBuckets; i += kSelThreads) fill[i] = 0;
+    if (tid == 0) { S.bin = -1; S.c_out = 0; }
+    __syncthreads();
+    for (int w = 0; w < kSelWarps; ++w) { vmin = min(vmin, (unsigned)S.scan[w]); vmax = max(vmax, (unsigned)S.hist[w]); }
+    const float xbest = from_orderable(~vmin), xworst = from_orderable(~vmax);
+    const float scale = __fdiv_rn((float)(kBuckets - 1), __fsub_rn(xbest, xworst));
+    if (!(xbest > xworst) || !isfinite(xbest) || !isfinite(xworst) || !isfinite(scale)) return -1;
+    auto bucket_of = [&](unsigned v) {
+        const float t = __fmul_rn(__fsub_rn(xbest, from_orderable(~v)), scale);       // >= 0, grows as the logit falls
+        return min(kBuckets - 1, (int)t);
+    };
+    __syncthreads();                                                                   // S.scan / S.hist are reused below
+    for (int i = tid; i < cnt; i += kSelThreads) atomicAdd(&fill[bucket_of((unsigned)(load(i) >> 32))], 1);
+    __syncthreads();
+    // exclusive scan of the 2048 counts, two per thread
+    {
+        const int c0 = fill[2 * tid], c1 = fill[2 * tid + 1];
+        int incl = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) S.scan[warp] = incl;
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < warp; ++w) before += S.scan[w];
+        const int e0 = before + incl - (c0 + c1), e1 = e0 + c0, e2 = e1 + c1;
+        start[2 * tid] = e0; start[2 * tid + 1] = e1;
+        if (tid == kSelThreads - 1) start[kBuckets] = e2;
+        fill[2 * tid] = 0; fill[2 * tid + 1] = 0;
+        // the bucket that holds rank kk (1-based); longer-than-allowed buckets at or before it
+        if (c0 > 0 && e0 < kk && kk <= e1) S.bin = 2 * tid;
+        if (c1 > 0 && e1 < kk && kk <= e2) S.bin = 2 * tid + 1;
+        if ((c0 > kBucketRun && e0 < kk) || (c1 > kBucketRun && e1 < kk)) S.c_out = 1;
+    }
+    __syncthreads();
+    const int bk = S.bin;
+    if (bk < 0 || S.c_out) return -1;
+    const int m = start[bk + 1];
+    if (m > tmp_cap) return -1;
+    for (int i = tid; i < cnt; i += kSelThreads) {
+        const unsigned long long key = load(i);
+        const int b = bucket_of((unsigned)(key >> 32));
+        if (b <= bk) tmp[start[b] + atomicAdd(&fill[b], 1)] = key;
+    }
+    __syncthreads();
+    for (int p = tid; p < m; p += kSelThreads) {
+        const unsigned long long key = tmp[p];
+        const int b = bucket_of((unsigned)(key >> 32));
+        const int s0 = start[b], s1 = start[b + 1];
+        int r = 0;
+        for (int q = s0; q < s1; ++q) r += tmp[q] < key;
+        if (s0 + r < kk) out[s0 + r] = key;
+    }
+    __syncthreads();
+    return kk;
+}
+
 // Block-wide MSB radix select over v[0..m) in shared memory: the threshold T and the number of entries equal to T
 // that belong to the k SMALLEST values (smaller value = larger score: v = ~orderable(logit)).  m > k >= 1.
 // `prefix0` / `mask0` / `first_pass`: bytes already decided by the caller.
@@ -362,10 +490,14 @@ __device__ void select_block(const unsigned* vals, int cnt, int k, unsigned long
     __syncthreads();
     if (tid == 0) S.c_mid = 0;
     __syncthreads();
-    for (int p = tid; p < rn; p += kSelThreads) {
-        const unsigned v = rv[p];
-        if ((v >> 24) == b1 && v < T)
-            out[above + atomicAdd(&S.c_mid, 1)] = ((unsigned long long)v << 32) | idx_of(narrow ? (int)ni[p] : p);
+    for (int p = tid; p - lane < rn; p += kSelThreads) {
+        const unsigned v = p < rn ? rv[p] : ~0u;
+        const bool in = p < rn && (v >> 24) == b1 && v < T;
+        const unsigned bal = __ballot_sync(kFullMask, in);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&S.c_mid, __popc(bal));
+        base = __shfl_sync(kFullMask, base, 0);
+        if (in) out[above + base + __popc(bal & ((1u << lane) - 1u))] = ((unsigned long long)v << 32) | idx_of(narrow ? (int)ni[p] : p);
     }
     // ties at the threshold.  Usually every entry equal to T is taken (tie-free input: T itself): append them all.
     if (tid == 0) S.c_out = 0;
@@ -381,9 +513,14 @@ __device__ void select_block(const unsigned* vals, int cnt, int k, unsigned long
     if (eq_total <= take_eq) {
         if (tid == 0) S.c_out = 0;
         __syncthreads();
-        for (int p = tid; p < rn; p += kSelThreads)
-            if (rv[p] == T)
-                out[above + lt_total + atomicAdd(&S.c_out, 1)] = ((unsigned long long)T << 32) | idx_of(narrow ? (int)ni[p] : p);
+        for (int p = tid; p - lane < rn; p += kSelThreads) {
+            const bool in = p < rn && rv[p] == T;
+            const unsigned bal = __ballot_sync(kFullMask, in);
+            int base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&S.c_out, __popc(bal));
+            base = __shfl_sync(kFullMask, base, 0);
+            if (in) out[above + lt_total + base + __popc(bal & ((1u << lane) - 1u))] = ((unsigned long long)T << 32) | idx_of(narrow ? (int)ni[p] : p);
+        }
     } else if (warp == 0) {
         // more equal entries than places: the lowest indices win.  The compact list is ascending in i only inside
         // each warp's chunk, so equal entries are ranked by index explicitly.
@@ -412,32 +549,144 @@ __device__ int select_level_global(const RpnParams& P, int b, int l, unsigned lo
 static constexpr int kSample = 4096;          // logits sampled per level for the threshold estimate
 
 // Levels much larger than k (mode 2): a sample of kSample evenly spaced logits estimates a threshold that keeps about
-// twice the wanted count (the order statistic `level_rank` of the sample), so that ONE compaction pass over the level
-// -- no shared-memory slice, no histogram -- yields a candidate list of a few thousand entries that surely holds the
-// top k.  "Surely" is statistics (k sits 6-7 standard deviations below the expected count), so it is verified: a level
-// whose list ends up shorter than k or longer than its capacity is redone by select_level_global.
+// twice the wanted count (the order statistic `level_rank` of the sample).  ONE streaming pass over the level
+// (k_rpn_pass: no shared-memory slice, no histogram) then yields a candidate list of a few thousand entries that surely
+// holds the top k, and the level's CTA of the select kernel just sorts that list.  "Surely" is statistics (k sits 6-7
+// standard deviations below the expected count), so it is verified: a level whose list ends up shorter than k or
+// longer than its capacity is redone by select_level_global.
+// The threshold itself comes from the same value-linear buckets as the sort: histogram of the sample, the bucket that
+// holds rank `level_rank`, and the worst sampled value up to that bucket (an order statistic of rank >= level_rank).
+// The kernel also zeroes the level's arrival and candidate counters.
 __global__ void __launch_bounds__(kSelThreads, 1)
 k_rpn_sample(const __grid_constant__ RpnParams P) {
     __shared__ unsigned keys[kSample];
+    __shared__ int hist[kBuckets];
     __shared__ SelShared S;
-    const int l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { P.sel_counter[b * P.L + l] = 0; P.cand_count[b * P.L + l] = 0; }
     if (P.level_mode[l] != 2) return;
-    const int n = P.level_n[l];
+    const int n = P.level_n[l], rank = P.level_rank[l];
     const float* src = P.obj + (size_t)b * P.total + P.level_off[l];
-    for (int j = tid; j < kSample; j += kSelThreads) keys[j] = ~orderable(level_logit(P, src, (int)((long long)j * n / kSample)));
+    constexpr int kPer = kSample / kSelThreads;
+    unsigned v[kPer], vmin = ~0u, vmax = 0u;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+        const int at = j * kSelThreads + tid;
+        v[j] = ~orderable(level_logit(P, src, (int)((long long)at * n / kSample)));
+        keys[at] = v[j];
+        vmin = min(vmin, v[j]); vmax = max(vmax, v[j]);
+    }
+    vmin = __reduce_min_sync(kFullMask, vmin);
+    vmax = __reduce_max_sync(kFullMask, vmax);
+    if (lane == 0) { S.scan[warp] = (int)vmin; S.hist[warp] = (int)vmax; }
+    hist[2 * tid] = 0; hist[2 * tid + 1] = 0;
+    if (tid == 0) S.bin = -1;
     __syncthreads();
-    unsigned T;
-    int take_eq;
-    pick_smallest(keys, kSample, P.level_rank[l], S, 0u, 0u, 3, T, take_eq);
-    if (tid == 0) P.thr[b * P.L + l] = T;
+    for (int w = 0; w < kSelWarps; ++w) { vmin = min(vmin, (unsigned)S.scan[w]); vmax = max(vmax, (unsigned)S.hist[w]); }
+    const float xbest = from_orderable(~vmin), xworst = from_orderable(~vmax);
+    const float scale = __fdiv_rn((float)(kBuckets - 1), __fsub_rn(xbest, xworst));
+    if (!(xbest > xworst) || !isfinite(xbest) || !isfinite(xworst) || !isfinite(scale)) {
+        unsigned T;
+        int take_eq;
+        pick_smallest(keys, kSample, rank, S, 0u, 0u, 3, T, take_eq);      // ties / non-finite logits: exact order statistic
+        if (tid == 0) P.thr[b * P.L + l] = T;
+        return;
+    }
+    int bk[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+        bk[j] = min(kBuckets - 1, (int)__fmul_rn(__fsub_rn(xbest, from_orderable(~v[j])), scale));
+        atomicAdd(&hist[bk[j]], 1);
+    }
+    __syncthreads();
+    const int c0 = hist[2 * tid], c1 = hist[2 * tid + 1];
+    int incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) S.scan[warp] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += S.scan[w];
+    const int e0 = before + incl - (c0 + c1), e1 = e0 + c0, e2 = e1 + c1;
+    if (c0 > 0 && e0 < rank && rank <= e1) S.bin = 2 * tid;
+    if (c1 > 0 && e1 < rank && rank <= e2) S.bin = 2 * tid + 1;
+    __syncthreads();
+    const int cut = S.bin;
+    unsigned worst = 0u;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) if (bk[j] <= cut) worst = max(worst, v[j]);
+    worst = __reduce_max_sync(kFullMask, worst);
+    if (lane == 0) S.hist[warp] = (int)worst;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 0; w < kSelWarps; ++w) worst = max(worst, (unsigned)S.hist[w]);
+        P.thr[b * P.L + l] = worst;
+    }
 }
 
-// Level l of image b is cut into R_l = ceil(n_l / kSliceMax) slices, one CTA each.  A CTA reads its slice ONCE
+static constexpr int kPassThreads = 256, kPassPer = 16, kPassChunk = kPassThreads * kPassPer;
+
+// mode-2 levels: append every logit at least as good as the level's sampled threshold to the level's candidate list
+// as (~key << 32 | index).  A CTA takes 4096 logits, 16 independent loads per thread, compacts inside the CTA and
+// reserves its run of the list with ONE global atomic.
+__global__ void __launch_bounds__(kPassThreads)
+k_rpn_pass(const __grid_constant__ RpnParams P) {
+    __shared__ int s_warp[kPassThreads / 32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.y;
+    int l = 0, c = blockIdx.x;
+    while (c >= P.level_chunks[l]) { c -= P.level_chunks[l]; ++l; }
+    const int n = P.level_n[l];
+    const float* src = P.obj + (size_t)b * P.total + P.level_off[l];
+    const unsigned T0 = P.thr[b * P.L + l];
+    const int i0 = c * kPassChunk;
+    unsigned v[kPassPer];
+#pragma unroll
+    for (int j = 0; j < kPassPer; ++j) {
+        const int i = i0 + j * kPassThreads + tid;
+        v[j] = i < n ? ~orderable(level_logit(P, src, i)) : ~0u;
+    }
+    unsigned hit = 0;
+#pragma unroll
+    for (int j = 0; j < kPassPer; ++j) hit |= (unsigned)(i0 + j * kPassThreads + tid < n && v[j] <= T0) << j;
+    const int mine = __popc(hit);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < kPassThreads / 32; ++w) { const int t = s_warp[w]; s_warp[w] = tot; tot += t; }
+        s_base = tot ? atomicAdd(P.cand_count + b * P.L + l, tot) : 0;
+    }
+    __syncthreads();
+    if (!hit) return;
+    int at = s_base + s_warp[warp] + incl - mine;
+    const int capL = P.level_cap[l];
+    unsigned long long* cand = P.cand + ((size_t)b * P.cand_stride + P.level_coff[l]);
+#pragma unroll
+    for (int j = 0; j < kPassPer; ++j)
+        if (hit >> j & 1u) {
+            if (at < capL) cand[at] = ((unsigned long long)v[j] << 32) | (unsigned)(i0 + j * kPassThreads + tid);
+            ++at;
+        }
+}
+
+// Level l of image b is cut into R_l = ceil(n_l / kSliceMax) slices, one CTA each (sampled levels: one CTA that
+// sorts the candidates k_rpn_pass left).  A CTA reads its slice ONCE
 // (order-preserving keys into shared memory), selects its local top min(k, m) there -- a superset of its share of
 // the level's top k -- and appends them to the level's candidate list.  The CTA that arrives last at the level's
 // counter (nobody waits) selects the top k among the R_l * k candidates, sorts them and runs the level's decode /
 // clip / filter (or emits the index list).  Single-slice levels skip the candidate round trip.
-__global__ void __launch_bounds__(kSelThreads, 2)
+__global__ void __launch_bounds__(kSelThreads, 1)
 k_rpn_select_sliced(const __grid_constant__ RpnParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned* nv = reinterpret_cast<unsigned*>(smem_raw);                       // [kNarrowMax] compact list: values
@@ -457,50 +706,53 @@ k_rpn_select_sliced(const __grid_constant__ RpnParams P) {
 
     int got;
     unsigned long long* sel;
+    bool presorted = false, bucket_scratch = true;
+    int* bstart = reinterpret_cast<int*>(nv);                                   // bucket sort: [kBuckets + 1] and [kBuckets]
+    int* bfill = bstart + kBuckets + 4;
+    rpn_stamp(P, 0);
+    if (P.prof && tid == 0) { P.prof[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + 6] = l; P.prof[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + 7] = r; }
     if (P.level_mode[l] == 2) {
-        // ---- sampled threshold: one compaction pass, nothing staged ----------------------------------------------------
-        const int lane = tid & 31;
-        const unsigned T0 = P.thr[b * P.L + l];
+        // ---- sampled threshold: k_rpn_pass left the level's candidates; sort them ------------------------------------
         const int capL = P.level_cap[l];
-        unsigned long long* cand = P.cand + ((size_t)b * P.cand_stride + P.level_coff[l]);
-        int* ccount = P.cand_count + b * P.L + l;
-        for (int i = tid; i - lane < m; i += kSelThreads) {
-            const unsigned v = i < m ? ~orderable(level_logit(P, src, i0 + i)) : ~0u;
-            const bool pass = i < m && v <= T0;
-            const unsigned bal = __ballot_sync(kFullMask, pass);
-            if (!bal) continue;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(ccount, __popc(bal));
-            base = __shfl_sync(kFullMask, base, 0);
-            const int at = base + __popc(bal & ((1u << lane) - 1u));
-            if (pass && at < capL) cand[at] = ((unsigned long long)v << 32) | (unsigned)(i0 + i);
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) S.last = atomicAdd(P.sel_counter + b * P.L + l, 1) == R - 1;
-        __syncthreads();
-        if (!S.last) return;
-        __threadfence();
-        const int cnt = *reinterpret_cast<volatile int*>(ccount);
-        if (cnt < min(k, n) || cnt > capL) {
-            // the sample misjudged the level (too few candidates, or more than the list holds): robust path
-            sel = reinterpret_cast<unsigned long long*>(after);
-            got = select_level_global(P, b, l, sel);
+        const unsigned long long* cand = P.cand + ((size_t)b * P.cand_stride + P.level_coff[l]);
+        const int cnt = P.cand_count[b * P.L + l];
+        unsigned long long* tmp = reinterpret_cast<unsigned long long*>(after);
+        const int tmp_cap = k + 1024;
+        sel = tmp + tmp_cap;
+        got = -1;
+        if (cnt >= min(k, n) && cnt <= capL)
+            got = bucket_sort_topk([&](int i) { return __ldcg(cand + i); }, cnt, k, tmp, tmp_cap, sel, bstart, bfill, S);
+        if (got >= 0) {
+            presorted = true;
         } else {
-            for (int i = tid; i < cnt; i += kSelThreads) keys[i] = (unsigned)(__ldcg(cand + i) >> 32);
-            __syncthreads();
-            sel = reinterpret_cast<unsigned long long*>(after + (((size_t)cnt * 4 + 15) & ~(size_t)15));
-            select_block(keys, cnt, k, sel, [&](int i) { return (unsigned)__ldcg(cand + i); }, S, nv, ni);
-            got = min(k, cnt);
+            // the sample misjudged the level (too few candidates, or more than the list holds), or the values defeat
+            // the buckets (ties, non-finite logits): robust path
+            sel = tmp;
+            got = select_level_global(P, b, l, sel);
+            bucket_scratch = false;                    // the selection sits where the bucket sort would scatter
         }
     } else {
     // ---- the one read of the logits ---------------------------------------------------------------------------------
     for (int i = tid; i < m; i += kSelThreads) keys[i] = ~orderable(level_logit(P, src, i0 + i));
     __syncthreads();
+    rpn_stamp(P, 2);
 
-    if (R == 1) {
-        // the slice is the level: select straight into the sort buffer behind the keys
-        sel = reinterpret_cast<unsigned long long*>(after + (((size_t)m * 4 + 15) & ~(size_t)15));
+    if (R == 1 && m >= 256) {
+        // the slice is the level: bucket-sort its top k straight out of the keys (select and sort in one go)
+        unsigned long long* tmp = reinterpret_cast<unsigned long long*>(after + (((size_t)m * 4 + 15) & ~(size_t)15));
+        const int tmp_cap = k + 1024;
+        sel = tmp + tmp_cap;
+        got = bucket_sort_topk([&](int i) { return ((unsigned long long)keys[i] << 32) | (unsigned)(i0 + i); }, m, k, tmp, tmp_cap,
+                               sel, bstart, bfill, S);
+        presorted = got >= 0;
+    } else {
+        got = -1;
+    }
+    if (got >= 0) {
+    } else if (R == 1) {
+        // (values that defeat the buckets, tiny levels) select into the sort buffer behind the keys
+        const size_t room = max(((size_t)m * 4 + 15) & ~(size_t)15, ((size_t)k * 8 + 15) & ~(size_t)15);
+        sel = reinterpret_cast<unsigned long long*>(after + room);                // leaves k keys of scratch in front
         select_block(keys, m, k, sel, [&](int i) { return (unsigned)(i0 + i); }, S, nv, ni);
         got = min(k, m);
     } else {
@@ -532,9 +784,17 @@ k_rpn_select_sliced(const __grid_constant__ RpnParams P) {
         got = min(k, total);
     }
     }
+    rpn_stamp(P, 3);
+    if (!presorted && bucket_scratch && got >= 256) {
+        // the slice keys / candidate keys are dead: scratch for the bucket sort of the selection
+        unsigned long long* picked = sel;
+        presorted = bucket_sort_topk([&](int i) { return picked[i]; }, got, got, reinterpret_cast<unsigned long long*>(after), got,
+                                     sel, bstart, bfill, S) >= 0;
+    }
     int Ppad = 1;
     while (Ppad < got) Ppad <<= 1;
-    rpn_finish_level(P, b, l, sel, got, Ppad, src, S.scan);
+    rpn_finish_level(P, b, l, sel, got, presorted ? 0 : Ppad, src, S.scan);
+    rpn_stamp(P, 5);
 }
 
 // Robust single-CTA select over the level in GLOBAL memory (four histogram passes + one collection pass): the general
@@ -770,12 +1030,14 @@ size_t rpn_carve(int batch, int total, int levels, int pre_k, void* base, size_t
 }  // namespace
 
 // per-level top-k (+ decode / filter unless P.topk_out): sliced kernel when the shared-memory plan fits
+long long* g_rpn_prof = nullptr;
 static int launch_rpn_select(RpnParams& P, int kmax, void* sel_ws, size_t sel_ws_bytes, cudaStream_t stream) {
+    P.prof = g_rpn_prof;
     int pp = 1;
     while (pp < kmax) pp <<= 1;
     static SmemOptIn optin1, optin3;
     // shared-memory plan of the sliced kernel: the slice keys, or (last CTA) the candidates' keys + the sort buffer
-    int slices = 0, coff = 0;
+    int slices = 0, coff = 0, chunks = 0;
     size_t smem = 0;
     bool any_sampled = false;
     for (int l = 0; l < P.L; ++l) {
@@ -784,10 +1046,15 @@ static int launch_rpn_select(RpnParams& P, int kmax, void* sel_ws, size_t sel_ws
         while (kp < k) kp <<= 1;
         size_t need;
         P.level_coff[l] = coff;
+        P.level_chunks[l] = 0;
         if (n <= kSliceMax) {
             P.level_mode[l] = 0;
             P.level_slices[l] = 1;
-            need = (((size_t)n * 4 + 15) & ~(size_t)15) + (size_t)kp * 8;
+            need = (((size_t)n * 4 + 15) & ~(size_t)15);
+            need = need > (((size_t)k * 8 + 15) & ~(size_t)15) ? need : (((size_t)k * 8 + 15) & ~(size_t)15);
+            need += (size_t)kp * 8;
+            const size_t direct = (((size_t)n * 4 + 15) & ~(size_t)15) + 2 * sizeof(unsigned long long) * (size_t)(k + 1024);
+            need = need > direct ? need : direct;
         } else if ((long long)n >= 8ll * k && n >= 4 * kSample) {
             // sampled threshold: keep ~2k (+ a margin of 32 sample ranks), list capacity twice the expectation
             P.level_mode[l] = 2;
@@ -797,11 +1064,12 @@ static int launch_rpn_select(RpnParams& P, int kmax, void* sel_ws, size_t sel_ws
             long long cap = 2 * expect > 4ll * k ? 2 * expect : 4ll * k;
             if (cap > 16384) cap = 16384;
             P.level_cap[l] = (int)cap;
-            P.level_slices[l] = (n + 8191) / 8192;
+            P.level_slices[l] = 1;
+            P.level_chunks[l] = (n + kPassChunk - 1) / kPassChunk;
+            chunks += P.level_chunks[l];
             coff += P.level_cap[l];
-            const size_t global_sel = (size_t)kp * 8;                               // fallback sorts out of the same buffer
-            need = (((size_t)cap * 4 + 15) & ~(size_t)15) + (size_t)kp * 8;
-            need = need > global_sel ? need : global_sel;
+            need = 2 * sizeof(unsigned long long) * (size_t)(k + 1024);          // bucket-sort scratch + the sorted list
+            need = need > (size_t)kp * 8 ? need : (size_t)kp * 8;                  // (the fallback sorts out of the same buffer)
             any_sampled = true;
         } else {
             P.level_mode[l] = 1;
@@ -825,8 +1093,12 @@ static int launch_rpn_select(RpnParams& P, int kmax, void* sel_ws, size_t sel_ws
         P.sel_counter = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(sel_ws) + cand_bytes);
         P.cand_count = P.sel_counter + (size_t)P.B * P.L;
         P.thr = reinterpret_cast<unsigned*>(P.cand_count + (size_t)P.B * P.L);
-        if (cudaMemsetAsync(P.sel_counter, 0, sizeof(int) * 2 * (size_t)P.B * P.L, stream) != cudaSuccess) return B200_ERR_CUDA;
-        if (any_sampled) k_rpn_sample<<<dim3(P.L, P.B), kSelThreads, 0, stream>>>(P);
+        if (!any_sampled) {
+            if (cudaMemsetAsync(P.sel_counter, 0, sizeof(int) * 2 * (size_t)P.B * P.L, stream) != cudaSuccess) return B200_ERR_CUDA;
+        } else {                                      // the sample kernel zeroes the counters
+            k_rpn_sample<<<dim3(P.L, P.B), kSelThreads, 0, stream>>>(P);
+            k_rpn_pass<<<dim3(chunks, P.B), kPassThreads, 0, stream>>>(P);
+        }
         if (optin3.ensure(k_rpn_select_sliced, 200 * 1024) != cudaSuccess) return B200_ERR_CUDA;
         k_rpn_select_sliced<<<dim3(slices, P.B), kSelThreads, smem, stream>>>(P);
     } else {
