@@ -177,7 +177,7 @@ __device__ __noinline__ void bitonic_sort_u64(unsigned long long* key, int P) {
     else bitonic_regs<16>(key, P);
 }
 
-// sorted selection -> (optional) index list, else decode / clip / filter in order.  `sel` holds `got` keys
+// sorted selection -> (optional) index list, else decode / clip / filter in order (s_scan: 2 * kSelWarps ints).  `sel` holds `got` keys
 // (~orderable(score) << 32 | index inside the level) in shared memory, with room for Ppad (a power of two >= got).
 __device__ void rpn_finish_level(const RpnParams& P, int b, int l, unsigned long long* sel, int got, int Ppad, const float* src,
                                  int* s_scan) {
@@ -194,57 +194,70 @@ __device__ void rpn_finish_level(const RpnParams& P, int b, int l, unsigned long
         return;
     }
     // ---- decode / clip / filter the selected anchors, keep order ------------------------------
+    // two rows per thread and round (r and r + 1024): their gathers are in flight together
     const float img_h = P.image_hw[2 * b], img_w = P.image_hw[2 * b + 1];
     int running = 0;
-    for (int r0 = 0; r0 < got; r0 += kSelThreads) {
-        const int r = r0 + tid;
-        bool ok = false;
-        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-        float prob = 0.f;
-        int a = 0, cls = 0;
-        if (r < got) {
-            const int i = (int)(unsigned)sel[r];
-            const int an = i / P.C;
-            cls = i - an * P.C;
-            a = P.level_aoff[l] + an;
-            prob = sigmoid_ref(level_logit(P, src, i));                            // rpn.py:255 / retinanet.py:436
-            float x1, y1, x2, y2;
-            if (P.proposals) {
-                const float4 pb = *reinterpret_cast<const float4*>(P.proposals + ((size_t)b * P.atotal + a) * 4);
-                x1 = pb.x; y1 = pb.y; x2 = pb.z; y2 = pb.w;
-            } else {
-                const float4 an = *reinterpret_cast<const float4*>(P.anchors + 4 * (size_t)a);
-                const float4 d = *reinterpret_cast<const float4*>(P.deltas + ((size_t)b * P.atotal + a) * 4);
-                // BoxCoder.decode_single, weights (1,1,1,1)                           _utils.py:199-221
-                const float w = __fsub_rn(an.z, an.x), h = __fsub_rn(an.w, an.y);
-                const float cx = __fadd_rn(an.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(an.y, __fmul_rn(0.5f, h));
-                const float dw = fminf(d.z, kXformClip), dh = fminf(d.w, kXformClip);
-                const float pcx = __fadd_rn(__fmul_rn(d.x, w), cx), pcy = __fadd_rn(__fmul_rn(d.y, h), cy);
-                const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
-                x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw)); y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
-                x2 = __fadd_rn(pcx, __fmul_rn(0.5f, pw)); y2 = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+    for (int r0 = 0; r0 < got; r0 += 2 * kSelThreads) {
+        bool ok[2];
+        float4 box[2];
+        float prob[2];
+        int a[2], cls[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = r0 + h * kSelThreads + tid;
+            ok[h] = false; box[h] = make_float4(0.f, 0.f, 0.f, 0.f); prob[h] = 0.f; a[h] = 0; cls[h] = 0;
+            if (r < got) {
+                const int i = (int)(unsigned)sel[r];
+                const int an = i / P.C;
+                cls[h] = i - an * P.C;
+                a[h] = P.level_aoff[l] + an;
+                prob[h] = sigmoid_ref(level_logit(P, src, i));                        // rpn.py:255 / retinanet.py:436
+                float x1, y1, x2, y2;
+                if (P.proposals) {
+                    const float4 pb = *reinterpret_cast<const float4*>(P.proposals + ((size_t)b * P.atotal + a[h]) * 4);
+                    x1 = pb.x; y1 = pb.y; x2 = pb.z; y2 = pb.w;
+                } else {
+                    const float4 an4 = *reinterpret_cast<const float4*>(P.anchors + 4 * (size_t)a[h]);
+                    const float4 d = *reinterpret_cast<const float4*>(P.deltas + ((size_t)b * P.atotal + a[h]) * 4);
+                    // BoxCoder.decode_single, weights (1,1,1,1)                           _utils.py:199-221
+                    const float w = __fsub_rn(an4.z, an4.x), hh = __fsub_rn(an4.w, an4.y);
+                    const float cx = __fadd_rn(an4.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(an4.y, __fmul_rn(0.5f, hh));
+                    const float dw = fminf(d.z, kXformClip), dh = fminf(d.w, kXformClip);
+                    const float pcx = __fadd_rn(__fmul_rn(d.x, w), cx), pcy = __fadd_rn(__fmul_rn(d.y, hh), cy);
+                    const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), hh);
+                    x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw)); y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+                    x2 = __fadd_rn(pcx, __fmul_rn(0.5f, pw)); y2 = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+                }
+                // clip_boxes_to_image (rpn.py:260)
+                x1 = fminf(fmaxf(x1, 0.f), img_w); x2 = fminf(fmaxf(x2, 0.f), img_w);
+                y1 = fminf(fmaxf(y1, 0.f), img_h); y2 = fminf(fmaxf(y2, 0.f), img_h);
+                box[h] = make_float4(x1, y1, x2, y2);
+                // remove_small_boxes + score threshold (rpn.py:263-269)
+                ok[h] = (__fsub_rn(x2, x1) >= P.min_size) && (__fsub_rn(y2, y1) >= P.min_size) &&
+                        (P.strict_thr ? prob[h] > P.score_thr : prob[h] >= P.score_thr);
             }
-            // clip_boxes_to_image (rpn.py:260)
-            x1 = fminf(fmaxf(x1, 0.f), img_w); x2 = fminf(fmaxf(x2, 0.f), img_w);
-            y1 = fminf(fmaxf(y1, 0.f), img_h); y2 = fminf(fmaxf(y2, 0.f), img_h);
-            box = make_float4(x1, y1, x2, y2);
-            // remove_small_boxes + score threshold (rpn.py:263-269)
-            ok = (__fsub_rn(x2, x1) >= P.min_size) && (__fsub_rn(y2, y1) >= P.min_size) &&
-                 (P.strict_thr ? prob > P.score_thr : prob >= P.score_thr);
         }
-        const unsigned bal = __ballot_sync(kFullMask, ok);
-        if (lane == 0) s_scan[warp] = __popc(bal);
+        const unsigned bal0 = __ballot_sync(kFullMask, ok[0]), bal1 = __ballot_sync(kFullMask, ok[1]);
+        if (lane == 0) { s_scan[warp] = __popc(bal0); s_scan[kSelWarps + warp] = __popc(bal1); }
         __syncthreads();
-        int before = 0, total = 0;
-        for (int w2 = 0; w2 < kSelWarps; ++w2) { const int c = s_scan[w2]; if (w2 < warp) before += c; total += c; }
-        if (ok) {
-            const size_t o = out0 + running + before + __popc(bal & ((1u << lane) - 1u));
-            P.box[o] = box;
-            P.score[o] = prob;
-            P.label[o] = P.label_class ? cls : l;
-            P.aidx[o] = a;
+        int before0 = 0, total0 = 0, before1 = 0, total1 = 0;
+        for (int w2 = 0; w2 < kSelWarps; ++w2) {
+            const int c0 = s_scan[w2], c1 = s_scan[kSelWarps + w2];
+            if (w2 < warp) { before0 += c0; before1 += c1; }
+            total0 += c0; total1 += c1;
         }
-        running += total;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (ok[h]) {
+                const unsigned bal = h ? bal1 : bal0;
+                const size_t o = out0 + running + (h ? total0 + before1 : before0) + __popc(bal & ((1u << lane) - 1u));
+                P.box[o] = box[h];
+                P.score[o] = prob[h];
+                P.label[o] = P.label_class ? cls[h] : l;
+                P.aidx[o] = a[h];
+            }
+        }
+        running += total0 + total1;
         __syncthreads();
     }
     if (tid == 0) {
@@ -793,7 +806,7 @@ k_rpn_select_sliced(const __grid_constant__ RpnParams P) {
     }
     int Ppad = 1;
     while (Ppad < got) Ppad <<= 1;
-    rpn_finish_level(P, b, l, sel, got, presorted ? 0 : Ppad, src, S.scan);
+    rpn_finish_level(P, b, l, sel, got, presorted ? 0 : Ppad, src, S.hist);
     rpn_stamp(P, 5);
 }
 
@@ -872,7 +885,7 @@ __global__ void __launch_bounds__(kSelThreads, 1)
 k_rpn_select(const __grid_constant__ RpnParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem_raw);  // [pow2(k)]
-    __shared__ int s_scan[kSelWarps];
+    __shared__ int s_scan[2 * kSelWarps];
     const int l = blockIdx.x, b = blockIdx.y;
     const float* src = P.obj + (size_t)b * P.total + P.level_off[l];
     const int got = select_level_global(P, b, l, sel);
@@ -884,33 +897,35 @@ k_rpn_select(const __grid_constant__ RpnParams P) {
 // merge the kept lists of an image by score, emit the first post_k (rpn.py:272-278).  Every segment's kept list
 // already is in descending score (the NMS emits in that order), so an element's place in the merged order is its own
 // position plus, for every other segment, the number of that segment's elements in front of it (binary search):
-// no sort.
+// no sort.  kFinishParts CTAs per image: each stages all keys (independent, unrolled gathers) and places its share.
+static constexpr int kFinishParts = 4;
+
 __global__ void __launch_bounds__(1024, 1)
 k_rpn_finish(const __grid_constant__ RpnParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);     // [sum of kept] grouped by segment
-    __shared__ int s_at[kMaxLevels + 1];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ int s_at[kMaxLevels + 1], s_st[kMaxLevels];
+    const int b = blockIdx.x, part = blockIdx.y, tid = threadIdx.x;
     const size_t base = (size_t)b * P.Ktot;
     const int S = P.segs_per_img;
     if (tid == 0) {
         int at = 0;
-        for (int s = 0; s < S; ++s) { s_at[s] = at; at += P.keep_count[b * S + s]; }
+        for (int s = 0; s < S; ++s) { s_at[s] = at; s_st[s] = P.seg_start[b * S + s]; at += P.keep_count[b * S + s]; }
         s_at[S] = at;
     }
     __syncthreads();
-    for (int s = 0; s < S; ++s) {
-        const int seg = b * S + s;
-        const int kc = s_at[s + 1] - s_at[s], st = P.seg_start[seg];
-        for (int i = tid; i < kc; i += 1024) {
-            const int pos = st + (int)P.keep[st + i];           // absolute row
-            key[s_at[s] + i] = ((unsigned long long)(~orderable(P.score[pos])) << 32) | (unsigned)(pos - (int)base);
-        }
+    const int total = s_at[S];
+#pragma unroll 4
+    for (int e = tid; e < total; e += 1024) {
+        int s = 0;
+        while (e >= s_at[s + 1]) ++s;
+        const int st = s_st[s];
+        const int pos = st + (int)P.keep[st + e - s_at[s]];     // absolute row
+        key[e] = ((unsigned long long)(~orderable(P.score[pos])) << 32) | (unsigned)(pos - (int)base);
     }
     __syncthreads();
-    const int total = s_at[S];
     const int nout = min(total, P.post_k);
-    for (int e = tid; e < total; e += 1024) {
+    for (int e = part * 1024 + tid; e < total; e += 1024 * kFinishParts) {
         int s = 0;
         while (e >= s_at[s + 1]) ++s;
         const unsigned long long mine = key[e];
@@ -927,12 +942,12 @@ k_rpn_finish(const __grid_constant__ RpnParams P) {
         if (rank < nout) {
             const size_t pos = base + (unsigned)mine;
             reinterpret_cast<float4*>(P.out_boxes)[(size_t)b * P.post_k + rank] = P.box[pos];
-            P.out_scores[(size_t)b * P.post_k + rank] = P.score[pos];
+            P.out_scores[(size_t)b * P.post_k + rank] = from_orderable(~(unsigned)(mine >> 32));
             if (P.out_index) P.out_index[(size_t)b * P.post_k + rank] = P.aidx[pos];
             if (P.out_labels) P.out_labels[(size_t)b * P.post_k + rank] = P.label[pos];
         }
     }
-    if (tid == 0) P.out_count[b] = nout;
+    if (tid == 0 && part == 0) P.out_count[b] = nout;
 }
 
 // image-wide segments (class-aware NMS across the levels): the per-level survivor lists of an image, written at a
@@ -1180,7 +1195,7 @@ int launch_rpn_filter_ex(const float* objectness, const float* deltas, const flo
         if (rc1 != B200_OK) return rc1;
         static SmemOptIn optin4;
         if (optin4.ensure(k_rpn_finish, 16384 * 8) != cudaSuccess) return B200_ERR_CUDA;
-        k_rpn_finish<<<batch, 1024, sizeof(unsigned long long) * (size_t)(P.Ktot > 0 ? P.Ktot : 1), stream>>>(P);
+        k_rpn_finish<<<dim3(batch, kFinishParts), 1024, sizeof(unsigned long long) * (size_t)(P.Ktot > 0 ? P.Ktot : 1), stream>>>(P);
         return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
     }
     const bool trick = nms_mode == B200_NMS_TV_TRICK;
@@ -1206,7 +1221,7 @@ int launch_rpn_filter_ex(const float* objectness, const float* deltas, const flo
     if (rc != B200_OK) return rc;
     static SmemOptIn optin2;
     if (optin2.ensure(k_rpn_finish, 16384 * 8) != cudaSuccess) return B200_ERR_CUDA;
-    k_rpn_finish<<<batch, 1024, sizeof(unsigned long long) * (size_t)(P.Ktot > 0 ? P.Ktot : 1), stream>>>(P);
+    k_rpn_finish<<<dim3(batch, kFinishParts), 1024, sizeof(unsigned long long) * (size_t)(P.Ktot > 0 ? P.Ktot : 1), stream>>>(P);
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }
 
