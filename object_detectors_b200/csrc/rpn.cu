@@ -86,7 +86,7 @@ __device__ __forceinline__ void rpn_stamp(const RpnParams& P, int slot) {
 
 // the logit the selection orders by: raw objectness, or tfidf_post[c] * logit for many-class heads
 __device__ __forceinline__ float level_logit(const RpnParams& P, const float* src, int j) {
-    const float x = ldg_stream_f32(src + j);
+    const float x = __ldg(src + j);             // (not the volatile streaming load: loops over logits must be free to batch their loads)
     if (!P.class_scale) return x;
     return __fmul_rn(__ldg(P.class_scale + (j - (j / P.C) * P.C)), x);
 }
@@ -656,12 +656,20 @@ k_rpn_pass(const __grid_constant__ RpnParams P) {
     const float* src = P.obj + (size_t)b * P.total + P.level_off[l];
     const unsigned T0 = P.thr[b * P.L + l];
     const int i0 = c * kPassChunk;
+    // all 16 loads first (clamped index, no branch between them), then the arithmetic: one memory round trip per CTA
+    float x[kPassPer];
+#pragma unroll
+    for (int j = 0; j < kPassPer; ++j) x[j] = __ldg(src + min(i0 + j * kPassThreads + tid, n - 1));
+    if (P.class_scale) {
+#pragma unroll
+        for (int j = 0; j < kPassPer; ++j) {
+            const int i = min(i0 + j * kPassThreads + tid, n - 1);
+            x[j] = __fmul_rn(__ldg(P.class_scale + (i - (i / P.C) * P.C)), x[j]);
+        }
+    }
     unsigned v[kPassPer];
 #pragma unroll
-    for (int j = 0; j < kPassPer; ++j) {
-        const int i = i0 + j * kPassThreads + tid;
-        v[j] = i < n ? ~orderable(level_logit(P, src, i)) : ~0u;
-    }
+    for (int j = 0; j < kPassPer; ++j) v[j] = ~orderable(x[j]);
     unsigned hit = 0;
 #pragma unroll
     for (int j = 0; j < kPassPer; ++j) hit |= (unsigned)(i0 + j * kPassThreads + tid < n && v[j] <= T0) << j;
@@ -746,6 +754,7 @@ k_rpn_select_sliced(const __grid_constant__ RpnParams P) {
         }
     } else {
     // ---- the one read of the logits ---------------------------------------------------------------------------------
+#pragma unroll 4
     for (int i = tid; i < m; i += kSelThreads) keys[i] = ~orderable(level_logit(P, src, i0 + i));
     __syncthreads();
     rpn_stamp(P, 2);
