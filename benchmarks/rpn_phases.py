@@ -48,6 +48,39 @@ def main():
         if len(tails):
             d = np.diff(tails[:, [0, 2, 3, 4, 5]].astype(np.float64), axis=1) / 1e3
             print("        tail phase durations (median us): stage %.1f  select %.1f  sort %.1f  decode/emit %.1f" % tuple(np.median(d, axis=0)))
+    nms_phases(lib, lambda: ops.rpn_filter(to, td, ta, per_level, hw, args.k, args.k, 0.7, 0.0, 1e-3, ops.NMS_TV_CLASS))
+
+
+def nms_phases(lib, run):
+    """phase stamps of the single-launch NMS kernel inside the filter (per CTA: start, seg|team|n, ranked, strips,
+    arrived, blocks, votes, emit)"""
+    prof = torch.zeros((160, 8), dtype=torch.int64, device="cuda")
+    lib.b200_debug_set_resolve_prof(C.c_void_p(prof.data_ptr()))
+    run()
+    torch.cuda.synchronize()
+    lib.b200_debug_set_resolve_prof(None)
+    pr = prof.cpu().numpy()
+    pr = pr[pr[:, 0] > 0]
+    t0 = pr[:, 0].min()
+    n = pr[:, 1] & 0xffffffff
+    team = (pr[:, 1] >> 32) & 0xff
+    res = pr[:, 7] > 0
+    us = lambda a: np.round(np.asarray(a, dtype=np.float64) / 1e3, 1)   # noqa: E731
+    print(f"NMS kernel: {len(pr)} CTAs, span {us(pr[:, 2:].max() - t0)} us, teams {sorted(set(team.tolist()))}")
+    seg = pr[:, 1] >> 40
+    for lv in range(5):
+        m = (seg % 5) == lv
+        if m.any():
+            print(f"  level {lv}: {int(m.sum())} CTAs, n {int(n[m].min())}..{int(n[m].max())} | rank {us((pr[m, 2] - pr[m, 0]).mean())} | strips mean "
+                  f"{us((pr[m, 3] - pr[m, 2]).mean())} max {us((pr[m, 3] - pr[m, 2]).max())}")
+    for lo, hi in ((0, 1000), (1000, 4097)):
+        m = (n > lo) & (n <= hi)
+        if not m.any():
+            continue
+        r = m & res
+        print(f"  segments of {lo + 1}..{hi} boxes: {int(m.sum())} CTAs | rank {us((pr[m, 2] - pr[m, 0]).mean())} | strips mean "
+              f"{us((pr[m, 3] - pr[m, 2]).mean())} max {us((pr[m, 3] - pr[m, 2]).max())} | strips end (since start) max {us((pr[m, 3] - t0).max())}"
+              f" | resolver: blocks {us((pr[r, 5] - pr[r, 4]).mean())} votes+emit {us((pr[r, 7] - pr[r, 5]).mean())} end max {us((pr[r, 7] - t0).max())}")
 
 
 if __name__ == "__main__":
