@@ -442,6 +442,7 @@ struct Dense2Params {
     int softmax;
     int cta_begin[B200_MAX_SCALES + 1];
     int tiles[B200_MAX_SCALES];
+    unsigned long long tiles_inv[B200_MAX_SCALES], a_inv;      // ceil(2^40 / d): n / d == (n * inv) >> 40 for n * d < 2^40
     // legacy (YOLOLoss) mode: one scale, rows ordered (a, h, w), xy = (sigmoid + grid) * stride, sigmoid classes
     int legacy, in_w;
     float stride_w, stride_h;
@@ -464,8 +465,9 @@ k_decode_dense2(const __grid_constant__ Dense2Params q) {
         if (i < p.num_scales && (int)blockIdx.x >= q.cta_begin[i]) s = i;
     const ScaleDev& sc = p.sc[s];
     const int local = blockIdx.x - q.cta_begin[s];
-    const int tl = local % q.tiles[s], ba = local / q.tiles[s];
-    const int a = ba % p.A, b = ba / p.A;
+    // (divisions by run-time values cost ~100 instructions per warp -- 8 % of this kernel -- hence the reciprocals)
+    const int ba = (int)(((unsigned long long)local * q.tiles_inv[s]) >> 40), tl = local - ba * q.tiles[s];
+    const int b = (int)(((unsigned long long)ba * q.a_inv) >> 40), a = ba - b * p.A;
     const int cell0 = tl * kDenseCells;
     const int ncell = min(kDenseCells, sc.hw - cell0);
     const float* src = sc.head + (size_t)ba * (size_t)CH * (size_t)sc.hw + (size_t)cell0;
@@ -481,6 +483,18 @@ k_decode_dense2(const __grid_constant__ Dense2Params q) {
             for (int k = 0; k < 2; ++k) {
                 const int c = lane + 32 * k;
                 v[j][k] = (r < CH && c < ncell) ? ldg_stream_f32(row + c) : 0.f;
+            }
+        }
+        if (p.idf) {
+            // class planes are staged already multiplied by their IDF weight (one scalar per row = per warp)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = r0 + 8 * j;
+                if (r >= 5 && r < CH) {
+                    const float wgt = __ldg(p.idf + (r - 5));
+                    v[j][0] = __fmul_rn(wgt, v[j][0]);
+                    v[j][1] = __fmul_rn(wgt, v[j][1]);
+                }
             }
         }
 #pragma unroll
@@ -499,18 +513,17 @@ k_decode_dense2(const __grid_constant__ Dense2Params q) {
     if (softmax) {
         const int cell = tid & 63, qtr = tid >> 6;
         float m = -INFINITY;
-        for (int c = qtr; c < C; c += 4) {
-            const float x = p.idf ? __fmul_rn(__ldg(p.idf + c), tile[(5 + c) * kDenseLd + cell]) : tile[(5 + c) * kDenseLd + cell];
-            m = fmaxf(m, x);
-        }
+        for (int c = qtr; c < C; c += 4) m = fmaxf(m, tile[(5 + c) * kDenseLd + cell]);
         part[qtr * kDenseCells + cell] = m;
         __syncthreads();
         m = fmaxf(fmaxf(part[cell], part[kDenseCells + cell]), fmaxf(part[2 * kDenseCells + cell], part[3 * kDenseCells + cell]));
         __syncthreads();
         float sum = 0.f;
         for (int c = qtr; c < C; c += 4) {
-            const float x = p.idf ? __fmul_rn(__ldg(p.idf + c), tile[(5 + c) * kDenseLd + cell]) : tile[(5 + c) * kDenseLd + cell];
-            sum = __fadd_rn(sum, ex2_approx(__fmul_rn(__fsub_rn(x, m), kLog2e)));
+            // the exponential is kept in place: phase D only scales it by 1 / denominator
+            const float e = ex2_approx(__fmul_rn(__fsub_rn(tile[(5 + c) * kDenseLd + cell], m), kLog2e));
+            tile[(5 + c) * kDenseLd + cell] = e;
+            sum = __fadd_rn(sum, e);
         }
         part[qtr * kDenseCells + cell] = sum;
         __syncthreads();
@@ -560,17 +573,11 @@ k_decode_dense2(const __grid_constant__ Dense2Params q) {
         const int hw = cell0 + cl;
         float* dst = q.legacy ? q.out + ((size_t)ba * (size_t)sc.hw + (size_t)hw) * (size_t)CH            // n = a*H*W + h*W + w
                               : q.out + ((size_t)b * (size_t)p.N + (size_t)sc.anchor_off + (size_t)hw * p.A + a) * (size_t)CH;
-        const float m = softmax ? st_m[cl] : 0.f, rinv = softmax ? st_r[cl] : 0.f;
+        const float rinv = softmax ? st_r[cl] : 0.f;
         for (int ch = lane; ch < CH; ch += 32) {
             const float t = tile[ch * kDenseLd + cl];
             float r = t;                                     // planes 0-4 are final already
-            if (ch >= 5) {
-                if (q.legacy) r = sigmoid_fast(t);
-                else {
-                    const float x = p.idf ? __fmul_rn(__ldg(p.idf + (ch - 5)), t) : t;
-                    r = softmax ? __fmul_rn(ex2_approx(__fmul_rn(__fsub_rn(x, m), kLog2e)), rinv) : sigmoid_fast(x);
-                }
-            }
+            if (ch >= 5) r = softmax ? __fmul_rn(t, rinv) : sigmoid_fast(t);      // t: IDF-scaled logit, or its exponential
             dst[ch] = r;
         }
     }
@@ -586,8 +593,11 @@ static int launch_dense2(Dense2Params& q, cudaStream_t stream) {
             q.tiles[s] = cdiv(p.sc[s].hw, kDenseCells);
             t += p.B * p.A * q.tiles[s];
         }
+        q.tiles_inv[s] = ((1ull << 40) + (unsigned long long)q.tiles[s] - 1) / (unsigned long long)q.tiles[s];
     }
     q.cta_begin[B200_MAX_SCALES] = t;
+    q.a_inv = ((1ull << 40) + (unsigned long long)p.A - 1) / (unsigned long long)p.A;
+    if ((long long)t * (long long)(p.A > q.tiles[0] ? p.A : q.tiles[0]) >= (1ll << 40)) return B200_ERR_INVALID;
     const size_t smem = (size_t)((5 + p.C) * kDenseLd + 6 * kDenseCells) * sizeof(float);
     static SmemOptIn optin;
     if (optin.ensure(k_decode_dense2, smem) != cudaSuccess) return B200_ERR_CUDA;
