@@ -472,11 +472,11 @@ k_decode_dense2(const __grid_constant__ Dense2Params q) {
     const int ncell = min(kDenseCells, sc.hw - cell0);
     const float* src = sc.head + (size_t)ba * (size_t)CH * (size_t)sc.hw + (size_t)cell0;
 
-    // ---- A. stage the tile: one warp per plane row, 2 cells per lane; 4 rows (8 loads) in flight per warp ----
-    for (int r0 = warp; r0 < CH; r0 += 32) {
-        float v[4][2];
+    // ---- A. stage the tile: one warp per plane row, 2 cells per lane; 6 rows (12 loads) in flight per warp ----
+    for (int r0 = warp; r0 < CH; r0 += 48) {
+        float v[6][2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 6; ++j) {
             const int r = r0 + 8 * j;
             const float* row = src + (size_t)r * (size_t)sc.hw;
 #pragma unroll
@@ -488,7 +488,7 @@ k_decode_dense2(const __grid_constant__ Dense2Params q) {
         if (p.idf) {
             // class planes are staged already multiplied by their IDF weight (one scalar per row = per warp)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 6; ++j) {
                 const int r = r0 + 8 * j;
                 if (r >= 5 && r < CH) {
                     const float wgt = __ldg(p.idf + (r - 5));
@@ -498,7 +498,7 @@ k_decode_dense2(const __grid_constant__ Dense2Params q) {
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 6; ++j) {
             const int r = r0 + 8 * j;
             if (r < CH) {
                 tile[r * kDenseLd + lane] = v[j][0];
