@@ -194,6 +194,28 @@ k_iou_match(const float* __restrict__ gt, const int* __restrict__ gt_count, int 
         a2[k] = __fmul_rn(__fsub_rn(anc[k].x2, anc[k].x1), __fsub_rn(anc[k].y2, anc[k].y1));
     }
 
+    // SKIP: the extent of this warp's anchors (consecutive anchors are neighbouring cells: a strip of the image).  A
+    // ground-truth box that misses the extent intersects none of the 128 anchors: one warp-uniform test replaces 128
+    // pair tests.  A NaN coordinate in the warp switches the shortcut off (NaN pairs must reach the exact path).
+    float ex1 = INFINITY, ey1 = INFINITY, ex2 = -INFINITY, ey2 = -INFINITY;
+    bool warp_extent = false;
+    if (SKIP) {
+        bool nan = false;
+#pragma unroll
+        for (int k = 0; k < kMatchItems; ++k)
+            if (valid[k]) {
+                ex1 = fminf(ex1, anc[k].x1); ey1 = fminf(ey1, anc[k].y1);
+                ex2 = fmaxf(ex2, anc[k].x2); ey2 = fmaxf(ey2, anc[k].y2);
+                nan |= !(anc[k].x1 == anc[k].x1) || !(anc[k].y1 == anc[k].y1) || !(anc[k].x2 == anc[k].x2) || !(anc[k].y2 == anc[k].y2);
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ex1 = fminf(ex1, __shfl_xor_sync(kFullMask, ex1, o)); ey1 = fminf(ey1, __shfl_xor_sync(kFullMask, ey1, o));
+            ex2 = fmaxf(ex2, __shfl_xor_sync(kFullMask, ex2, o)); ey2 = fmaxf(ey2, __shfl_xor_sync(kFullMask, ey2, o));
+        }
+        warp_extent = !__any_sync(kFullMask, nan);
+    }
+
     for (int mc = 0; mc < M; mc += kGtChunk) {
         const int mm = min(kGtChunk, M - mc);
         __syncthreads();
@@ -206,6 +228,9 @@ k_iou_match(const float* __restrict__ gt, const int* __restrict__ gt_count, int 
         __syncthreads();
         for (int i = 0; i < mm; ++i) {
             const Box g = sgt[i];
+            // min(g.x2, a.x2) <= g.x2 <= a.x1 <= max(g.x1, a.x1) for every anchor of the warp: w <= 0 everywhere (same for
+            // the other three sides); comparisons with a NaN box are false, so it is not skipped
+            if (SKIP && warp_extent && (g.x2 <= ex1 || g.x1 >= ex2 || g.y2 <= ey1 || g.y1 >= ey2)) continue;
             const float a1e = sarea[i];
             unsigned bk = 0u;          // orderable(best iou) over this thread's anchors
             int bkk = -1;              // which of its anchors

@@ -917,9 +917,11 @@ k_rpn_finish(const __grid_constant__ RpnParams P) {
     const int b = blockIdx.x, part = blockIdx.y, tid = threadIdx.x;
     const size_t base = (size_t)b * P.Ktot;
     const int S = P.segs_per_img;
+    if (tid < S) { s_st[tid] = P.seg_start[b * S + tid]; s_at[tid + 1] = P.keep_count[b * S + tid]; }   // one round trip
+    __syncthreads();
     if (tid == 0) {
         int at = 0;
-        for (int s = 0; s < S; ++s) { s_at[s] = at; s_st[s] = P.seg_start[b * S + s]; at += P.keep_count[b * S + s]; }
+        for (int s = 0; s < S; ++s) { const int c = s_at[s + 1]; s_at[s] = at; at += c; }
         s_at[S] = at;
     }
     __syncthreads();
