@@ -113,16 +113,17 @@ __device__ __forceinline__ void f_bitonic(unsigned long long* key, int P2) {
 }
 
 // Sort by buckets instead of a sorting network (the idea of rpn.cu's bucket_sort_topk, whole array): a histogram over
-// 2048 buckets linear in the SCORE between the best and the worst key -- a monotone map, so bucket order is key order --
+// NB buckets linear in the SCORE between the best and the worst key -- a monotone map, so bucket order is key order --
 // a scan, a scatter into `tmp` (this CTA's private global scratch) and a rank-by-counting inside each (short) bucket
 // leave key[0..n) ascending, exactly as the network would (keys are unique).  Seven barriers instead of 66 steps for
 // 2048 keys.  Returns false -- key[] untouched -- when the scores defeat the buckets (non-finite, all equal, a run of
 // more than kFBucketRun equal-ish scores): the caller then runs the network.
-static constexpr int kFBuckets = 2048, kFBucketRun = 256;
+static constexpr int kFBucketRun = 256;
 
-template <int NT>
+template <int NT, int NB>
 __device__ bool f_bucket_sort(unsigned long long* key, int n, unsigned long long* tmp, int* start, int* fill, int* sc) {
-    constexpr int kFW = NT / 32, kPer = kFBuckets / NT;
+    constexpr int kFW = NT / 32, kPer = NB / NT;
+    static_assert(NB % NT == 0 && kPer >= 1, "buckets per thread");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned vmin = ~0u, vmax = 0u;
     for (int i = tid; i < n; i += NT) {
@@ -133,17 +134,18 @@ __device__ bool f_bucket_sort(unsigned long long* key, int n, unsigned long long
     vmax = __reduce_max_sync(kFullMask, vmax);
     __syncthreads();
     if (lane == 0) { sc[warp] = (int)vmin; start[warp] = (int)vmax; }
-    for (int i = tid; i < kFBuckets; i += NT) fill[i] = 0;
     __syncthreads();
     for (int w = 0; w < kFW; ++w) { vmin = min(vmin, (unsigned)sc[w]); vmax = max(vmax, (unsigned)start[w]); }
     const float xbest = from_orderable(~vmin), xworst = from_orderable(~vmax);
-    const float scale = __fdiv_rn((float)(kFBuckets - 1), __fsub_rn(xbest, xworst));
+    const float scale = __fdiv_rn((float)(NB - 1), __fsub_rn(xbest, xworst));
     if (!(xbest > xworst) || !(fabsf(xbest) < 3.0e38f) || !(fabsf(xworst) < 3.0e38f) || !(scale < 3.0e38f)) return false;
     auto bucket_of = [&](unsigned long long k) {
         const float t = __fmul_rn(__fsub_rn(xbest, from_orderable(~(unsigned)(k >> 32))), scale);
-        return min(kFBuckets - 1, (int)t);
+        return min(NB - 1, (int)t);
     };
     __syncthreads();                                                   // sc / start are reused below
+    for (int i = tid; i < NB; i += NT) fill[i] = 0;
+    __syncthreads();
     for (int i = tid; i < n; i += NT) atomicAdd(&fill[bucket_of(key[i])], 1);
     __syncthreads();
     // exclusive scan of the counts, kPer consecutive buckets per thread
@@ -160,7 +162,6 @@ __device__ bool f_bucket_sort(unsigned long long* key, int n, unsigned long long
     for (int w = 0; w < warp; ++w) at += sc[w];
 #pragma unroll
     for (int j = 0; j < kPer; ++j) { start[tid * kPer + j] = at; at += cnt[j]; fill[tid * kPer + j] = 0; }
-    if (tid == NT - 1) start[kFBuckets] = at;
     __syncthreads();
     for (int i = tid; i < n; i += NT) {
         const unsigned long long k = key[i];
@@ -171,7 +172,7 @@ __device__ bool f_bucket_sort(unsigned long long* key, int n, unsigned long long
     for (int p = tid; p < n; p += NT) {
         const unsigned long long k = tmp[p];
         const int b = bucket_of(k);
-        const int s0 = start[b], s1 = start[b + 1];
+        const int s0 = start[b], s1 = b + 1 < NB ? start[b + 1] : n;
         int r = 0;
         for (int q = s0; q < s1; ++q) r += tmp[q] < k;
         key[s0 + r] = k;
@@ -228,9 +229,14 @@ __device__ bool fused_rank(const NmsParams& P, int seg, long long off, int n, in
     }
     __syncthreads();
     bool sorted = false;
-    if (n >= 256 && n <= 2048)                   // 16 KB of keys + 16 KB of bucket counters fit the 40 KB scratch
-        sorted = f_bucket_sort<NT>(key, n, R.key, reinterpret_cast<int*>(smem + 16384), reinterpret_cast<int*>(smem + 16384) + kFBuckets + 4,
-                                   reinterpret_cast<int*>(red));
+    {
+        // the 40 KB scratch holds the keys and the bucket counters: 16 + 16 KB up to 2048 boxes, 32 + 8 KB up to 4096
+        int* sc = reinterpret_cast<int*>(red);
+        if (n >= 256 && n <= 2048)
+            sorted = f_bucket_sort<NT, 2048>(key, n, R.key, reinterpret_cast<int*>(smem + 16384), reinterpret_cast<int*>(smem + 16384) + 2048, sc);
+        else if (n > 2048 && n <= 4096)
+            sorted = f_bucket_sort<NT, 1024>(key, n, R.key, reinterpret_cast<int*>(smem + 32768), reinterpret_cast<int*>(smem + 32768) + 1024, sc);
+    }
     if (!sorted) f_bitonic<NT>(key, P2);
     int bad = 0;
     for (int r = tid; r < n; r += kFT) {
