@@ -82,6 +82,8 @@ SIGNATURES = {
     "b200_match_boxes_workspace_bytes": (_sz, [_i32, _i32]),
     "b200_match_boxes": (C.c_int, [_p, _i32, _p, _i32, _f32, _f32, _i32, _i32, _p, _p, _p, _sz, _p]),
     "b200_matcher_ssd_override": (C.c_int, [_p, _i32, _i32, _p, _p, _sz, _p]),
+    "b200_clip_boxes_to_image": (C.c_int, [_p, _i64, _f32, _f32, _p, _p]),
+    "b200_remove_small_boxes": (C.c_int, [_p, _i32, _f32, _p, _p, _p]),
     "b200_emit_results": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _f32, _p, _i32, _i32, _p, _p, _p, _p, _p]),
     "b200_pack_detections": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),
     "b200_allgather_dets": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p]),

@@ -56,7 +56,65 @@ k_emit_results(const float* __restrict__ det, const int* __restrict__ cnt, int b
     }
 }
 
+// torchvision.ops.boxes.clip_boxes_to_image (tvision/boxes.py, called at rpn.py:260, roi_heads.py:735, retinanet.py:455,
+// ssd.py:398): x coordinates clamped to [0, width], y coordinates to [0, height]; any leading shape, 4 floats per box
+__global__ void __launch_bounds__(256)
+k_clip_boxes(const float4* __restrict__ boxes, long long n, float height, float width, float4* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        float4 b = boxes[i];
+        // torch.clamp(min, max) = min(max(x, lo), hi); NaN propagates
+        b.x = b.x != b.x ? b.x : fminf(fmaxf(b.x, 0.f), width);  b.z = b.z != b.z ? b.z : fminf(fmaxf(b.z, 0.f), width);
+        b.y = b.y != b.y ? b.y : fminf(fmaxf(b.y, 0.f), height); b.w = b.w != b.w ? b.w : fminf(fmaxf(b.w, 0.f), height);
+        out[i] = b;
+    }
+}
+
+// torchvision.ops.boxes.remove_small_boxes: indices (ascending) of the boxes with w >= min_size and h >= min_size.
+// One CTA walks the boxes 1024 at a time with a running offset (an ordered compaction; the callers hold a few thousand
+// boxes per image); count[0] = number of indices written.
+__global__ void __launch_bounds__(1024, 1)
+k_small_box_keep(const float4* __restrict__ boxes, int n, float min_size, long long* __restrict__ keep, int* __restrict__ count) {
+    __shared__ int s_warp[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int running = 0;
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + tid;
+        bool ok = false;
+        if (i < n) {
+            const float4 b = boxes[i];
+            ok = __fsub_rn(b.z, b.x) >= min_size && __fsub_rn(b.w, b.y) >= min_size;
+        }
+        const unsigned bal = __ballot_sync(kFullMask, ok);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 32; ++w) { const int c = s_warp[w]; if (w < warp) before += c; total += c; }
+        if (ok) keep[running + before + __popc(bal & ((1u << lane) - 1u))] = i;
+        running += total;
+        __syncthreads();
+    }
+    if (tid == 0) *count = running;
+}
+
 }  // namespace b200
+
+extern "C" int b200_clip_boxes_to_image(const float* boxes, int64_t n, float height, float width, float* out, void* stream) {
+    if (n < 0 || (n > 0 && (!boxes || !out))) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;
+    if ((reinterpret_cast<uintptr_t>(boxes) | reinterpret_cast<uintptr_t>(out)) & 15) return B200_ERR_INVALID;
+    const long long ctas = (n + 255) / 256;
+    b200::k_clip_boxes<<<(unsigned)(ctas < 4096 ? ctas : 4096), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(boxes), n, height, width, reinterpret_cast<float4*>(out));
+    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
+
+extern "C" int b200_remove_small_boxes(const float* boxes, int32_t n, float min_size, int64_t* keep, int32_t* count, void* stream) {
+    if (n < 0 || !count || (n > 0 && (!boxes || !keep))) return B200_ERR_INVALID;
+    if (n > 0 && (reinterpret_cast<uintptr_t>(boxes) & 15)) return B200_ERR_INVALID;
+    b200::k_small_box_keep<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(boxes), n, min_size, reinterpret_cast<long long*>(keep), count);
+    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
 
 extern "C" int b200_emit_results(const float* det, const int32_t* det_count, int32_t batch, int32_t max_det,
                                  const float* img_hw, const int64_t* image_id, float inp_dim, const int32_t* class_map,

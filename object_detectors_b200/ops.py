@@ -715,6 +715,31 @@ def retinanet_postprocess(cls_logits: Tensor, bbox_regression: Tensor, anchors: 
 
 
 @_device_guard
+def clip_boxes_to_image(boxes: Tensor, size) -> Tensor:
+    """b200_clip_boxes_to_image: ``boxes [..., 4]`` xyxy clamped to the image ``size = (height, width)``."""
+    lib = _lib.load()
+    b = _need_cuda(boxes, "boxes", torch.float32)
+    out = torch.empty_like(b)
+    h, w = size
+    _lib.check(lib.b200_clip_boxes_to_image(_ptr(b), b.numel() // 4, float(h), float(w), _ptr(out), _stream()),
+               "b200_clip_boxes_to_image")
+    return out
+
+
+@_device_guard
+def remove_small_boxes(boxes: Tensor, min_size: float) -> Tensor:
+    """b200_remove_small_boxes: int64 indices of the boxes whose width and height are both >= ``min_size``."""
+    lib = _lib.load()
+    b = _need_cuda(boxes, "boxes", torch.float32)
+    n = b.shape[0]
+    keep = torch.empty((n,), dtype=torch.int64, device=b.device)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=b.device)
+    _lib.check(lib.b200_remove_small_boxes(_ptr(b), n, float(np.float32(min_size)), _ptr(keep), _ptr(cnt), _stream()),
+               "b200_remove_small_boxes")
+    return keep[:int(cnt.item())]          # the reference's torch.where() synchronises here as well
+
+
+@_device_guard
 def emit_results(det: Tensor, det_count: Tensor, img_hw: Tensor, image_id: Tensor, inp_dim: float,
                  class_map: Optional[Tensor] = None, strict_reference: bool = True):
     """b200_emit_results: packed evaluation records of a whole batch.  -> (records [B*max_det, 6] fp32,

@@ -53,12 +53,12 @@ def box_iou(boxes1: Tensor, boxes2: Tensor) -> Tensor:
 
 
 def clip_boxes_to_image(boxes: Tensor, size: Tuple[int, int]) -> Tensor:
-    h, w = size
-    x = boxes[..., 0::2].clamp(min=0, max=w)
-    y = boxes[..., 1::2].clamp(min=0, max=h)
-    return torch.stack((x, y), dim=boxes.dim()).reshape(boxes.shape)
+    if boxes.numel() == 0:
+        return boxes.clone()
+    return ops.clip_boxes_to_image(boxes.float(), size).to(boxes.dtype)
 
 
 def remove_small_boxes(boxes: Tensor, min_size: float) -> Tensor:
-    ws, hs = boxes[:, 2] - boxes[:, 0], boxes[:, 3] - boxes[:, 1]
-    return torch.where((ws >= min_size) & (hs >= min_size))[0]
+    if boxes.shape[0] == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    return ops.remove_small_boxes(boxes.float(), min_size)

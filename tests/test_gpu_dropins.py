@@ -608,3 +608,33 @@ def test_rpn_top_n_idx_when_the_sample_misjudges_the_level(case):
     got = ops.rpn_top_n_idx(torch.from_numpy(obj).cuda(), [n], k).cpu()
     want = torch.from_numpy(obj).topk(k, dim=1)[1]
     np.testing.assert_array_equal(got.numpy(), want.numpy())
+
+
+@pytest.mark.gpu
+def test_clip_boxes_and_remove_small_boxes_match_torch():
+    """tvision/boxes.py clip_boxes_to_image / remove_small_boxes as kernels: same values / indices as the torch
+    expressions of the reference (x clamped to [0, w], y to [0, h]; w >= min and h >= min), incl. NaN rows, leading
+    batch dimensions, empty inputs and exact-threshold sizes."""
+    from object_detectors_b200.tvision import boxes as bx
+    g = np.random.default_rng(77)
+    b = (g.standard_normal((3, 1777, 4)) * 400 + 300).astype(np.float32)
+    b[1, 5] = np.nan
+    t = torch.from_numpy(b).cuda()
+    got = bx.clip_boxes_to_image(t, (480, 640)).cpu()
+    x = torch.from_numpy(b)[..., 0::2].clamp(min=0, max=640)
+    y = torch.from_numpy(b)[..., 1::2].clamp(min=0, max=480)
+    want = torch.stack((x, y), dim=3).reshape(b.shape)
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0))
+    assert bx.clip_boxes_to_image(torch.empty((0, 4), device="cuda"), (4, 4)).shape == (0, 4)
+
+    f = b[0].copy()
+    f[:, 2:] = f[:, :2] + np.abs(g.standard_normal((f.shape[0], 2)).astype(np.float32)) * 2
+    f[10, 2] = f[10, 0] + np.float32(1.0)             # exactly the threshold (when the subtraction is exact)
+    f[11] = np.nan
+    tf = torch.from_numpy(f).cuda()
+    for ms in (1e-3, 1.0, 2.5):
+        gotk = bx.remove_small_boxes(tf, ms).cpu()
+        ws, hs = torch.from_numpy(f)[:, 2] - torch.from_numpy(f)[:, 0], torch.from_numpy(f)[:, 3] - torch.from_numpy(f)[:, 1]
+        wantk = torch.where((ws >= ms) & (hs >= ms))[0]
+        assert torch.equal(gotk, wantk)
+    assert bx.remove_small_boxes(torch.empty((0, 4), device="cuda"), 1.0).numel() == 0
