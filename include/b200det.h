@@ -178,6 +178,11 @@ int b200_debug_set_resolve_prof(void* buf);
 /* Same for the per-level select of the RPN / RetinaNet filter: int64[levels * batch, 8] globaltimer stamps of each
  * level's CTA (start, -, staged, selected, sorted, done) + level and slice; NULL to disable. */
 int b200_debug_set_rpn_prof(void* buf);
+/* Tuning hook: segment size above which a SERIAL post-process call (b200_yolo_postprocess: decode and NMS of one batch
+ * on one stream) hands a segment to the 1024-thread single-launch NMS kernel instead of the three-launch path
+ * (default and maximum 1500; lower values measured worse on the C2 workload: both paths then run back to back;
+ * pipelined calls always split at 1500 and use the 256-thread instantiation). */
+int b200_debug_set_serial_split(int boxes);
 /* NMS kernel path (process-wide): 1 = the general three-launch path (plan / pairs / resolve: spatially pruned tile
  * pairs, small CTAs that co-reside with the streaming decode kernel), 0 = segments of <= 4096 boxes take the
  * single-launch path (nms_fused.cu: no work queue, no cross-kernel dependencies), -1 (default) = by workload:

@@ -47,6 +47,7 @@ SIGNATURES = {
     "b200_debug_set_timeline": (C.c_int, [_p, _p, _p]),
     "b200_debug_set_resolve_prof": (C.c_int, [_p]),
     "b200_debug_set_rpn_prof": (C.c_int, [_p]),
+    "b200_debug_set_serial_split": (C.c_int, [C.c_int]),
     "b200_debug_set_nms_path": (C.c_int, [C.c_int]),
     "b200_debug_set_resolve": (C.c_int, [C.c_int, C.c_int]),
     "b200_set_decode_variant": (C.c_int, [C.c_int]),

@@ -96,7 +96,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 }  // namespace b200
 
 
-namespace b200 { extern cudaEvent_t g_nms_timeline[3]; extern long long* g_resolve_prof; extern long long* g_rpn_prof; extern long long g_batched_nms_auto_limit; extern int g_resolve_threads, g_resolve_smem_kb, g_nms_force_general; }
+namespace b200 { extern cudaEvent_t g_nms_timeline[3]; extern long long* g_resolve_prof; extern long long* g_rpn_prof; extern int g_serial_split; extern long long g_batched_nms_auto_limit; extern int g_resolve_threads, g_resolve_smem_kb, g_nms_force_general; }
 using namespace b200;
 
 extern "C" {
@@ -175,6 +175,7 @@ int b200_debug_set_resolve(int threads, int smem_kb) {
 }
 int b200_debug_set_nms_path(int general) { b200::g_nms_force_general = general < 0 ? -1 : (general > 2 ? 1 : general); return B200_OK; }
 int b200_debug_set_resolve_prof(void* buf) { b200::g_resolve_prof = static_cast<long long*>(buf); return B200_OK; }
+int b200_debug_set_serial_split(int boxes) { b200::g_serial_split = boxes < 1 ? 1 : boxes; return B200_OK; }
 int b200_debug_set_rpn_prof(void* buf) { b200::g_rpn_prof = static_cast<long long*>(buf); return B200_OK; }
 static void* g_ev_decode_begin = nullptr;
 static void* g_ev_decode_end = nullptr;
@@ -281,6 +282,7 @@ int b200_yolo_postprocess(const b200_yolo_layout* layout, const float* const* he
     np.det = det; np.det_keep = det_keep; np.det_anchor = det_anchor; np.det_count = det_count;
     np.cand_count_out = cand_count;
     np.max_det = max_det;
+    np.serial = 1;                     // decode and NMS of ONE batch back to back on one stream: nothing to co-reside with
     return yolo_run(layout, heads, idf, conf_thr, capacity, w.count, np, w, static_cast<cudaStream_t>(stream));
 }
 

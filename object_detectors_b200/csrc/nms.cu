@@ -46,6 +46,7 @@ static constexpr int kRankSortMax = 1024;       // kept boxes ordered by countin
 static constexpr int kVoteFlag = 1 << 30;
 static constexpr int kVoteListCap = 128;
 static constexpr int kSplitBoxes = 1500;        // largest segment the shared-memory resolve holds at its default 112 KB
+int g_serial_split = 1500;                      // split point of serial calls (b200_debug_set_serial_split)
 
 
 
@@ -1043,7 +1044,8 @@ int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
     // decode kernel of the next batch); the single-launch kernel takes the larger ones, which would otherwise fall
     // back to the global-memory resolve (20x slower).  Each kernel returns at once from segments that are not its own.
     const bool split = fused_ok && P.force_general < 0 && P.from_slab;
-    if (split) P.split_hi = kSplitBoxes;
+    const int split_at = P.serial ? (g_serial_split < kSplitBoxes ? g_serial_split : kSplitBoxes) : kSplitBoxes;
+    if (split) P.split_hi = split_at;
     const int sms = current_sm_count();
     if (cudaMemsetAsync(P.work_count, 0, 2 * sizeof(int), stream) != cudaSuccess) return B200_ERR_CUDA;
     if (P.from_slab) k_nms_plan<true><<<num_segments, kPlanThreads, 0, stream>>>(P);
@@ -1070,7 +1072,7 @@ int launch_nms(NmsParams& P, int num_segments, cudaStream_t stream) {
     if (g_nms_timeline[2]) cudaEventRecord(g_nms_timeline[2], stream);
     if (cudaGetLastError() != cudaSuccess) return B200_ERR_CUDA;
     if (split) {
-        P.split_lo = kSplitBoxes;
+        P.split_lo = split_at;
         P.split_hi = 0x7fffffff;
         return launch_nms_fused(P, num_segments, stream);
     }

@@ -67,6 +67,8 @@ struct NmsParams {
     int* f_rlabel;
     unsigned long long* f_rkey; // (~orderable(score) << 32) | tie << 12 | index inside the segment
     int force_general;          // debug: 1 = always take the three-launch path
+    int serial;                 // the call is not overlapped with the decode of another batch (b200_yolo_postprocess):
+                                // the large segments of a slab go to the 1024-thread single-launch kernel, not the 256-thread one
     int split_lo, split_hi;     // this launch only handles segments with split_lo < n <= split_hi (others are left alone)
 };
 

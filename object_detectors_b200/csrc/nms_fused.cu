@@ -780,7 +780,7 @@ int launch_nms_fused(NmsParams& P, int num_segments, cudaStream_t stream) {
     // a lone small segment does not need the whole chip: at most one CTA per row tile
     const long long useful = (long long)num_segments * (P.max_words > 0 ? P.max_words : 1);
     const int sms = current_sm_count();
-    if (P.split_lo != 0) {
+    if (P.split_lo != 0 && !P.serial) {
         // beside the general path (large segments of a candidate slab only): small CTAs, two per SM, that start next
         // to the streaming decode kernel and leave at once when the batch has no large segment
         int grid = 2 * sms;
