@@ -638,3 +638,32 @@ def test_clip_boxes_and_remove_small_boxes_match_torch():
         wantk = torch.where((ws >= ms) & (hs >= ms))[0]
         assert torch.equal(gotk, wantk)
     assert bx.remove_small_boxes(torch.empty((0, 4), device="cuda"), 1.0).numel() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("per_level,k", [
+    ([50400], 7000),              # multi-slice level that does not qualify for sampling: local top-k per slice + merge
+    ([30000, 9000], 8192),        # two slices with k close to the slice length; a single-slice level with k < n
+    ([70000, 200, 33], 3000),     # sampled level beside levels smaller than k (taken whole) and smaller than a warp
+    ([20480, 20481], 512),        # the single-slice limit and one logit more
+    ([300000], 8192),             # sampled level with the largest k (candidate list near its capacity)
+])
+def test_rpn_top_n_idx_select_plans(per_level, k):
+    """Every shared-memory plan of the per-level select (single slice, slices + merge, sampled threshold, bucket sort
+    and its fallbacks) returns torch.topk's index list on tie-free logits."""
+    from object_detectors_b200 import ops
+    g = np.random.default_rng(k + len(per_level))
+    total = sum(per_level)
+    obj = np.empty((3, total), dtype=np.float32)
+    for b in range(3):                     # tie-free by construction: a shuffled ramp with Gaussian-like spacing
+        ramp = np.sort(g.standard_normal(total) * 2 - 3).astype(np.float64) + np.arange(total) * 1e-4
+        obj[b] = g.permutation(ramp).astype(np.float32)
+        assert np.unique(obj[b]).size == total
+    got = ops.rpn_top_n_idx(torch.from_numpy(obj).cuda(), per_level, k).cpu().numpy()
+    off = col = 0
+    for n in per_level:
+        kk = min(k, n)
+        want = torch.from_numpy(obj[:, off:off + n]).topk(kk, dim=1)[1].numpy() + off
+        np.testing.assert_array_equal(got[:, col:col + kk], want)
+        off += n
+        col += kk
