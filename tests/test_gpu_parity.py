@@ -205,6 +205,32 @@ def test_nms_modes_bit_exact(sizes, nms_path):
             np.testing.assert_array_equal(got, want, err_msg=f"mode {mode} segment {s} (n={n})")
 
 
+@pytest.mark.parametrize("quantum", [0.05, 1e-3])
+def test_nms_with_tied_scores(quantum, nms_path):
+    """Scores quantised to a few (0.05) or many (1e-3) levels: runs of equal scores longer than the bucket sort of the
+    single-launch kernel ranks by counting (-> its sorting-network fallback) and short runs inside buckets; equal
+    scores keep their index order (the oracle's canonical order)."""
+    ops = _ops()
+    sizes = [1500, 2000, 3000, 257]
+    boxes, scores, labels, off, bs, ss, ls = _segments(sizes, 91, 20, 5)
+    scores = (np.round(scores / quantum) * quantum).astype(np.float32)
+    ss = [scores[off[i]:off[i + 1]] for i in range(len(sizes))]
+    tb, ts = torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda()
+    tl, to = torch.from_numpy(labels).cuda(), torch.from_numpy(off).cuda()
+    for mode, thr in ((ops.NMS_TV, 0.5), (ops.NMS_MAJORITY, 0.6), (ops.NMS_TV_CLASS, 0.5)):
+        keep, kc, lout = ops.nms_segments(tb, ts, tl, to, thr, mode)
+        keep, kc = keep.cpu().numpy(), kc.cpu().numpy()
+        for s_, n in enumerate(sizes):
+            got = keep[off[s_]:off[s_] + kc[s_]]
+            if mode == ops.NMS_MAJORITY:
+                det6 = np.concatenate([bs[s_], ss[s_][:, None], ls[s_][:, None].astype(np.float32)], 1)
+                want, wl = cref.nms_majority(det6, thr, 5)
+                np.testing.assert_array_equal(lout.cpu().numpy()[off[s_]:off[s_] + kc[s_]], wl)
+            else:
+                want = cref.nms_tv(bs[s_], ss[s_], thr, ls[s_] if mode == ops.NMS_TV_CLASS else None)
+            np.testing.assert_array_equal(got, want, err_msg=f"mode {mode} segment {s_} (n={n})")
+
+
 def test_nms_threshold_semantics(nms_path):
     """IoU == fp32(0.6) exactly: torchvision suppresses ((double)0.6f > 0.6), nms_majority removes it
     without a vote; zero-area pairs: NaN IoU never suppresses in torchvision, is removed in majority."""
