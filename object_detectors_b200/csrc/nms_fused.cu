@@ -8,7 +8,7 @@
 //   TEAMS   Every CTA reads the segment sizes and derives the same assignment: segment s gets a team of g_s CTAs,
 //           g_s proportional to its pair count (largest-remainder rounding, so every CTA of the grid is used).  With
 //           more segments than CTAs every CTA owns whole segments.
-//   RANK    Each team member sorts the segment by (score desc, index asc) -- bitonic network in shared memory -- and
+//   RANK    Each team member sorts the segment by (score desc, index asc) -- bucket sort, bitonic network as fallback -- and
 //           writes the boxes in RANK order to its private scratch.  The work is redundant inside a team (a few
 //           microseconds) and buys independence: nobody waits for a "planner".
 //   STRIPS  The dominator bitmask lives in rank space: bit q of row r <=> q precedes r and suppresses it, so only
