@@ -295,7 +295,7 @@ int b200_roi_postprocess(const float* class_logits, const float* box_regression,
     np.det = det; np.det_keep = det_keep; np.det_anchor = nullptr; np.det_count = det_count;
     np.cand_count_out = cand_count;
     np.max_det = max_det;
-    np.slab = slab; np.count = count; np.cap = capacity; np.from_slab = 1;
+    np.slab = slab; np.count = count; np.cap = capacity; np.from_slab = 1; np.serial = 1;
     np.anchor_space = 0;                 // flat (row, class) indices: rank by counting
     np.max_seg = capacity;
     return launch_nms(np, batch, st);
@@ -342,7 +342,7 @@ int b200_ssd_postprocess(const float* cls_logits, const float* bbox_regression, 
     np.det = det; np.det_keep = nullptr; np.det_anchor = nullptr; np.det_count = det_count;
     np.cand_count_out = cand_count;
     np.max_det = max_det;
-    np.slab = slab; np.count = count; np.cap = capacity; np.from_slab = 1;
+    np.slab = slab; np.count = count; np.cap = capacity; np.from_slab = 1; np.serial = 1;
     np.anchor_space = 0;
     np.max_seg = capacity;
     return launch_nms(np, batch, st);
