@@ -1,3 +1,4 @@
+"""Three serial post-process calls of C3 (LVIS-1203, A=6, b32): per-kernel launch list of the LVIS configuration."""
 import sys, os, torch, numpy as np
 sys.path.insert(0, os.getcwd())
 from object_detectors_b200 import ops, synthetic as syn

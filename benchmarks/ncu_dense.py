@@ -1,3 +1,4 @@
+"""Three dense `[B,N,85]` decodes of the C2 batch: the target of the ncu captures of k_decode_dense2."""
 import sys, os, torch, numpy as np
 sys.path.insert(0, os.getcwd())
 from object_detectors_b200 import ops, synthetic as syn

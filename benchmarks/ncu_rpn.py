@@ -1,3 +1,8 @@
+"""Three C5 RPN filter calls (b16, 800x1344, k=2000) and nothing else: the target of the ncu launch list /
+`--set full` captures behind profiles/r02_rpn_kernels.csv and profiles/r02_nms_fused_notes.md.
+
+    ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_rpn|k_nms" python benchmarks/ncu_rpn.py
+"""
 import sys, os, torch
 sys.path.insert(0, os.getcwd())
 from object_detectors_b200 import ops, synthetic as syn
