@@ -259,7 +259,7 @@ def run_b200(args):
     # and the copy it reads was last touched n_p steps (~3 GB of traffic) ago.
     inputs = [[h.roll(7 * k, 0).contiguous() for h in heads] for k in range(n_p)]
     d_streams = [torch.cuda.Stream(device=dev) for _ in range(n_d)]
-    n_streams_ = [torch.cuda.Stream(device=dev) for _ in range(n_n)]
+    n_streams_ = [torch.cuda.Stream(device=dev, priority=args.nms_priority) for _ in range(n_n)]
     p_stream = torch.cuda.Stream(device=dev)      # pushes, in step order
     w_stream = torch.cuda.Stream(device=dev)      # waits, in step order
     streams = d_streams + n_streams_ + [p_stream, w_stream]
@@ -534,7 +534,7 @@ def run_b200(args):
                        "l2_policy": f"inputs ({algo_bytes / 1e6:.1f} MB/step) larger than L2 (126 MB); {n_p} distinct input copies "
                                     "rotate, so concurrent decode kernels never read the same lines; no flush needed",
                        "candidates_per_step": cands, "kept_per_step": kept,
-                       "pipeline": {"decode_streams": n_d, "nms_streams": n_n, "workspaces": n_p, "ring": args.ring,
+                       "pipeline": {"decode_streams": n_d, "nms_streams": n_n, "nms_stream_priority": args.nms_priority, "workspaces": n_p, "ring": args.ring,
                                     "nms_path": args.nms_path},
                        "decode_variant": args.variant, "exchange": exch, "exchange_verified": exchange_verified},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -580,6 +580,9 @@ def main():
                          "single-launch path for larger ones), general / fused = one path only")
     ap.add_argument("--dstreams", type=int, default=3, help="decode streams = decode kernels in flight")
     ap.add_argument("--nstreams", type=int, default=3, help="streams for the NMS chains")
+    ap.add_argument("--nms-priority", type=int, default=-5,
+                    help="CUDA stream priority of the NMS streams (lower = more urgent; clamped to the device's range): their CTAs are "
+                         "placed before those of the next decode launch, which shortens the NMS chains (+4 %% at 20 steps)")
     ap.add_argument("--plans", type=int, default=6, help="rotating workspaces")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: one-sided peer-memory exchange (default) or bucketed ncclAllGather")
