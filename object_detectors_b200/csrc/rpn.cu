@@ -759,6 +759,7 @@ k_rpn_select_sliced(const __grid_constant__ RpnParams P) {
     __syncthreads();
     rpn_stamp(P, 2);
 
+    got = -1;
     if (R == 1 && m >= 256) {
         // the slice is the level: bucket-sort its top k straight out of the keys (select and sort in one go)
         unsigned long long* tmp = reinterpret_cast<unsigned long long*>(after + (((size_t)m * 4 + 15) & ~(size_t)15));
@@ -767,10 +768,9 @@ k_rpn_select_sliced(const __grid_constant__ RpnParams P) {
         got = bucket_sort_topk([&](int i) { return ((unsigned long long)keys[i] << 32) | (unsigned)(i0 + i); }, m, k, tmp, tmp_cap,
                                sel, bstart, bfill, S);
         presorted = got >= 0;
-    } else {
-        got = -1;
     }
-    if (got >= 0) {
+    if (presorted) {
+        // nothing left to select
     } else if (R == 1) {
         // (values that defeat the buckets, tiny levels) select into the sort buffer behind the keys
         const size_t room = max(((size_t)m * 4 + 15) & ~(size_t)15, ((size_t)k * 8 + 15) & ~(size_t)15);
