@@ -425,12 +425,12 @@ int b200_emit_results(const float* det, const int32_t* det_count, int32_t batch,
                       int32_t num_map, int32_t strict_reference, float* records, int32_t* category,
                       int64_t* image, int32_t* total, void* stream);
 
-/* torchvision.ops.boxes.clip_boxes_to_image (reference tvision/boxes.py; callers rpn.py:260, roi_heads.py:735,
- * retinanet.py:455, ssd.py:398): boxes [n, 4] xyxy (16-byte aligned), x clamped to [0, width], y to [0, height];
+/* torchvision.ops.boxes.clip_boxes_to_image (reference tvision/boxes.py; callers rpn.py:260, roi_heads.py:746,
+ * retinanet.py:452, ssd.py:397): boxes [n, 4] xyxy (16-byte aligned), x clamped to [0, width], y to [0, height];
  * out may alias boxes. */
 int b200_clip_boxes_to_image(const float* boxes, int64_t n, float height, float width, float* out, void* stream);
 
-/* torchvision.ops.boxes.remove_small_boxes (callers rpn.py:263, roi_heads.py:752, retinanet/ssd post-process):
+/* torchvision.ops.boxes.remove_small_boxes (callers rpn.py:263, roi_heads.py:767):
  * keep [<= n] int64 = ascending indices of the boxes with (x2 - x1) >= min_size and (y2 - y1) >= min_size,
  * count[0] = how many. */
 int b200_remove_small_boxes(const float* boxes, int32_t n, float min_size, int64_t* keep, int32_t* count, void* stream);

@@ -56,8 +56,8 @@ k_emit_results(const float* __restrict__ det, const int* __restrict__ cnt, int b
     }
 }
 
-// torchvision.ops.boxes.clip_boxes_to_image (tvision/boxes.py, called at rpn.py:260, roi_heads.py:735, retinanet.py:455,
-// ssd.py:398): x coordinates clamped to [0, width], y coordinates to [0, height]; any leading shape, 4 floats per box
+// torchvision.ops.boxes.clip_boxes_to_image (tvision/boxes.py, called at rpn.py:260, roi_heads.py:746, retinanet.py:452,
+// ssd.py:397): x coordinates clamped to [0, width], y coordinates to [0, height]; any leading shape, 4 floats per box
 __global__ void __launch_bounds__(256)
 k_clip_boxes(const float4* __restrict__ boxes, long long n, float height, float width, float4* __restrict__ out) {
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {

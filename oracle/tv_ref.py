@@ -314,3 +314,20 @@ def ssd_postprocess(cls_logits: Tensor, bbox_regression: Tensor, image_anchors: 
         keep = keep[:detections_per_img]
         out.append((ib[keep], isc[keep], il[keep]))
     return out
+
+
+def clip_boxes_to_image(boxes: Tensor, size: Tuple[int, int]) -> Tensor:
+    """torchvision.ops.boxes.clip_boxes_to_image as the reference calls it (rpn.py:260, roi_heads.py:746,
+    retinanet.py:452, ssd.py:397): x to [0, width], y to [0, height]."""
+    height, width = size
+    x = boxes[..., 0::2].clamp(min=0, max=width)
+    y = boxes[..., 1::2].clamp(min=0, max=height)
+    return torch.stack((x, y), dim=boxes.dim()).reshape(boxes.shape)
+
+
+def remove_small_boxes(boxes: Tensor, min_size: float) -> Tensor:
+    """torchvision.ops.boxes.remove_small_boxes (rpn.py:263, roi_heads.py:767): indices of the boxes whose width and
+    height are both >= min_size."""
+    ws, hs = boxes[:, 2] - boxes[:, 0], boxes[:, 3] - boxes[:, 1]
+    return torch.where((ws >= min_size) & (hs >= min_size))[0]
+

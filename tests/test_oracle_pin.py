@@ -77,3 +77,16 @@ def test_encode_boxes_matches_reference_utils():
         from torchvision.models.detection import _utils as ref_utils
     want = ref_utils.BoxCoder((10.0, 10.0, 5.0, 5.0)).encode_single(ref, prop)
     np.testing.assert_array_equal(tv_ref.encode_boxes(ref, prop, (10.0, 10.0, 5.0, 5.0)).numpy(), want.numpy())
+
+
+def test_clip_and_small_box_helpers_match_torchvision():
+    """clip_boxes_to_image / remove_small_boxes restatements == the installed torchvision functions the reference calls
+    (rpn.py:260,263; roi_heads.py:746,767), incl. a leading batch dimension and sizes exactly at the threshold."""
+    g = np.random.default_rng(5)
+    b = torch.from_numpy((g.standard_normal((2, 500, 4)) * 300 + 200).astype(np.float32))
+    assert torch.equal(tv_ref.clip_boxes_to_image(b, (480, 640)), tvb.clip_boxes_to_image(b, (480, 640)))
+    f = b[0].clone()
+    f[:, 2:] = f[:, :2] + torch.rand(500, 2) * 3
+    f[7, 2] = f[7, 0] + 1.0
+    for ms in (1e-3, 1e-2, 1.0):
+        assert torch.equal(tv_ref.remove_small_boxes(f, ms), tvb.remove_small_boxes(f, ms))
