@@ -56,6 +56,11 @@ def test_invalid_arguments_are_rejected_without_touching_the_gpu(lib):
     assert lib.b200_nms(None, None, None, None, -1, 0, 0, 0.5, 1, None, None, None, None, 0, None) == -1
     assert lib.b200_box_iou(None, 3, None, 3, 9, 0, None, None) == -1
     assert lib.b200_yolo_workspace_bytes(None, 16) == 0
+    assert lib.b200_clip_boxes_to_image(None, 5, 4.0, 4.0, None, None) == -1
+    assert lib.b200_clip_boxes_to_image(None, 0, 4.0, 4.0, None, None) == 0          # empty input: nothing to do
+    assert lib.b200_remove_small_boxes(None, 5, 1.0, None, None, None) == -1
+    assert lib.b200_match_boxes_workspace_bytes(0, 10) == 0
+    assert lib.b200_debug_set_serial_split(1500) == 0 and lib.b200_debug_set_nms_path(-1) == 0
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
